@@ -1,0 +1,636 @@
+/*
+ * ee_oracle.c -- CPU ORACLE for the edge-enhancement + PGD-step hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * this file's shared object.  The product (edge-enhancement_b200/) never does and has no
+ * CPU fallback.
+ *
+ * What it is: a plain-C, whole-image, full-plane restatement of the reference's algorithm
+ * (Aiqz/Edge-Enhancement, utils/core.py and utils/attacks.py).  Every function cites the
+ * reference file:line it follows.  It is written independently of the CUDA kernels
+ * (image-level loops over complete planes, no tiling) but evaluates the SAME canonical
+ * fp32 expression trees (DESIGN.md "Canonical arithmetic"), so CUDA-vs-oracle comparisons
+ * are bit-exact, while oracle-vs-reference comparisons (tests/golden, made by running the
+ * real reference modules) are within the north-star tolerances.
+ *
+ * Parity pin: the reference has no tests/golden vectors of its own, so
+ * the oracle is pinned against outputs of the reference itself run in the build container
+ * (oracle/make_golden.py -> tests/golden/ *.npz).
+ *
+ * Build: gcc -O2 -ffp-contract=off -fno-fast-math [-mfma] -fopenmp -shared -fPIC
+ *        (-ffp-contract=off is REQUIRED: fused multiply-adds happen only where fmaf() is
+ *        written.)
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define EE_STEP125 0
+#define EE_CANNY   1
+#define EE_BPDA    2
+
+typedef struct {
+    int   variant;            /* EE_STEP125 / EE_CANNY / EE_BPDA                           */
+    float c0, c1, c2;         /* 3x3 Gaussian: corner, edge, centre (core.py:58-72, :164)  */
+    float alpha;              /* magnitude gate (core.py:263-264, :574-575); unused by BPDA */
+    float low_thr, high_thr;  /* thresholds, already rounded to fp32 like torch does       */
+    int   has_low, has_high;  /* "is not None" flags of forward() (core.py:295,309)        */
+    int   hysteresis;         /* core.py:317                                               */
+} ee_oracle_params;
+
+static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* To_compare.forward, core.py:338-347:  out = in.clone(); out[out <= thr] = 0; out[out > thr] = 1.
+ * The two masked writes run in that order, so with a NEGATIVE threshold the zeros written by
+ * the first are turned into ones by the second (0 > thr).  NaN stays NaN. */
+static inline float to_compare(float v, float thr)
+{
+    if (v > thr) return 1.0f;
+    if (v <= thr) return (0.0f > thr) ? 1.0f : 0.0f;
+    return v;
+}
+/* (sign(v - thr) + 1) / 2 with safeSign(0) = -1, core.py:115-118, :299-310. */
+static inline float sign_step(float v, float thr) { return (v - thr > 0.0f) ? 1.0f : 0.0f; }
+
+/* ------------------------------------------------------------------------------------
+ * Stage A: channel sum.  The reference blurs every channel (core.py:560-563) and lets the
+ * Sobel conv sum over channels (weight.repeat(1,C,1,1), core.py:566-567).  Blur, replicate
+ * padding and the Sobel conv are all linear, so summing the channels FIRST is the same
+ * function; it is the canonical order here: s = ((x0 + x1) + x2) + ...
+ * ---------------------------------------------------------------------------------- */
+static void channel_sum(const float *x, int C, int H, int W, float *s)
+{
+    const size_t hw = (size_t)H * W;
+    for (size_t i = 0; i < hw; ++i) {
+        float acc = x[i];
+        for (int c = 1; c < C; ++c) acc = acc + x[(size_t)c * hw + i];
+        s[i] = acc;
+    }
+}
+
+/* ------------------------------------------------------------------------------------
+ * Stage B: 3x3 Gaussian with ReplicationPad2d(1)  (core.py:162, :233-236, :560-563).
+ * G = [[c0,c1,c0],[c1,c2,c1],[c0,c1,c0]] (symmetric because it depends on the distance to
+ * the centre only, core.py:62-66).  Canonical order:
+ *     e = left + right;  P = fma(c1, mid, c0*e);  Q = fma(c2, mid, c1*e)
+ *     blur(i,j) = (P(i-1,j) + Q(i,j)) + P(i+1,j)          rows/cols clamped (replicate)
+ * ---------------------------------------------------------------------------------- */
+static void blur3_replicate(const float *s, int H, int W, float c0, float c1, float c2,
+                            float *P, float *Q, float *out)
+{
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            float l = s[(size_t)i * W + clampi(j - 1, 0, W - 1)];
+            float r = s[(size_t)i * W + clampi(j + 1, 0, W - 1)];
+            float m = s[(size_t)i * W + j];
+            float e = l + r;
+            P[(size_t)i * W + j] = fmaf(c1, m, c0 * e);
+            Q[(size_t)i * W + j] = fmaf(c2, m, c1 * e);
+        }
+    for (int i = 0; i < H; ++i) {
+        int iu = clampi(i - 1, 0, H - 1), id = clampi(i + 1, 0, H - 1);
+        for (int j = 0; j < W; ++j)
+            out[(size_t)i * W + j] = (P[(size_t)iu * W + j] + Q[(size_t)i * W + j]) + P[(size_t)id * W + j];
+    }
+}
+
+/* ------------------------------------------------------------------------------------
+ * Stage C: Sobel x / y with ReplicationPad2d(1) on the BLURRED image (core.py:176, :250-252,
+ * :565-567).  Kx = [[-.5,0,.5],[-1,0,1],[-.5,0,.5]] (core.py:75-84), Ky = Kx^T (core.py:180).
+ *     D(i,j) = b(i,j+1) - b(i,j-1)                 V(i,j) = fma(.5, b(i,j-1)+b(i,j+1), b(i,j))
+ *     Sgx    = fma(.5, D(i-1,j)+D(i+1,j), D(i,j))  Sgy    = V(i+1,j) - V(i-1,j)
+ * then /C (true division, core.py:256,446,570).
+ * ---------------------------------------------------------------------------------- */
+static void sobel3_replicate(const float *b, int H, int W, int C, float *D, float *V,
+                             float *gx1, float *gy1)
+{
+    const float fC = (float)C;
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            float l = b[(size_t)i * W + clampi(j - 1, 0, W - 1)];
+            float r = b[(size_t)i * W + clampi(j + 1, 0, W - 1)];
+            float m = b[(size_t)i * W + j];
+            D[(size_t)i * W + j] = r - l;
+            V[(size_t)i * W + j] = fmaf(0.5f, l + r, m);
+        }
+    for (int i = 0; i < H; ++i) {
+        int iu = clampi(i - 1, 0, H - 1), id = clampi(i + 1, 0, H - 1);
+        for (int j = 0; j < W; ++j) {
+            float sgx = fmaf(0.5f, D[(size_t)iu * W + j] + D[(size_t)id * W + j], D[(size_t)i * W + j]);
+            float sgy = V[(size_t)id * W + j] - V[(size_t)iu * W + j];
+            gx1[(size_t)i * W + j] = sgx / fC;
+            gy1[(size_t)i * W + j] = sgy / fC;
+        }
+    }
+}
+
+/* Orientation bin of core.py:258-260,270:  atan(gy/gx)*(360/pi)+180 -> round(/45)*45 -> (/45)%8.
+ * v = atan(r)*8/pi + 4 in [0,8]; bin = round(v) mod 8; the boundaries v = k+.5 are at
+ * r = tan((k-3.5)*pi/8).  Canonical form: count the boundaries below r (no atan; see
+ * DESIGN.md).  0/0 = NaN matches no direction (-1). */
+static const float EE_TAN_BOUNDS[8] = {
+    -5.02733949212584810451f, -1.49660576266548901760f, -0.66817863791929891999f,
+    -0.19891236737965800691f,  0.19891236737965800691f,  0.66817863791929891999f,
+     1.49660576266548901760f,  5.02733949212584810451f };
+
+static inline int orient_bin(float gx1, float gy1)
+{
+    float r = gy1 / gx1;
+    if (r != r) return -1;
+    int k = 0;
+    for (int t = 0; t < 8; ++t) k += (r > EE_TAN_BOUNDS[t]);
+    return k & 7;
+}
+
+/* (row, col) offset of the -1 tap of directional kernel k (core.py:87-112; cv2 output). */
+static const int EE_DIR_DR[8] = { 0, -1, -1, -1, 0, 1, 1, 1 };
+static const int EE_DIR_DC[8] = { 1, 1, 0, -1, -1, -1, 0, 1 };
+
+typedef struct {
+    float *s, *P, *Q, *blur, *D, *V, *gx1, *gy1, *mag, *magm, *thin, *t, *hi;
+    unsigned char *removed, *wih;
+} planes_t;
+
+static int planes_alloc(planes_t *p, size_t hw)
+{
+    float *buf = (float *)malloc(sizeof(float) * hw * 13);
+    if (!buf) return -1;
+    p->s = buf; p->P = buf + hw; p->Q = buf + 2 * hw; p->blur = buf + 3 * hw; p->D = buf + 4 * hw;
+    p->V = buf + 5 * hw; p->gx1 = buf + 6 * hw; p->gy1 = buf + 7 * hw; p->mag = buf + 8 * hw;
+    p->magm = buf + 9 * hw; p->thin = buf + 10 * hw; p->t = buf + 11 * hw; p->hi = buf + 12 * hw;
+    p->removed = (unsigned char *)malloc(hw * 2);
+    if (!p->removed) { free(buf); return -1; }
+    p->wih = p->removed + hw;
+    return 0;
+}
+static void planes_free(planes_t *p) { free(p->s); free(p->removed); }
+
+/* Forward of one image: fills every intermediate plane and the edge map.
+ * STEP125: core.py:549-585.  CANNY: core.py:222-326.  BPDA: core.py:426-505. */
+static void edge_forward_image(const float *x, int C, int H, int W, const ee_oracle_params *pr,
+                               planes_t *pl, float *edge)
+{
+    const size_t hw = (size_t)H * W;
+    channel_sum(x, C, H, W, pl->s);
+    blur3_replicate(pl->s, H, W, pr->c0, pr->c1, pr->c2, pl->P, pl->Q, pl->blur);
+    sobel3_replicate(pl->blur, H, W, C, pl->D, pl->V, pl->gx1, pl->gy1);
+    for (size_t i = 0; i < hw; ++i) {
+        float gx = pl->gx1[i], gy = pl->gy1[i];
+        float m = sqrtf(gx * gx + gy * gy);               /* core.py:257,447,571 */
+        pl->mag[i] = m;
+        if (pr->variant == EE_BPDA) pl->magm[i] = m;      /* BPDA has no alpha gate */
+        else pl->magm[i] = (m < pr->alpha) ? 0.0f : m;    /* core.py:263-264,574-575 */
+    }
+    if (pr->variant == EE_STEP125) {
+        /* To_compare.forward, core.py:338-347 (strict >) ; core.py:578-583 */
+        for (size_t i = 0; i < hw; ++i) edge[i] = to_compare(pl->magm[i], pr->high_thr);
+        return;
+    }
+    /* non-maximum suppression, core.py:268-290 / :455-480 (directional conv is zero padded) */
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            size_t q = (size_t)i * W + j;
+            int bin = orient_bin(pl->gx1[q], pl->gy1[q]);
+            int rem = 0;
+            if (bin >= 0) {
+                int k = bin & 3;
+                float m = pl->magm[q];
+                int i1 = i + EE_DIR_DR[k], j1 = j + EE_DIR_DC[k];
+                int i2 = i + EE_DIR_DR[k + 4], j2 = j + EE_DIR_DC[k + 4];
+                float n1 = (i1 >= 0 && i1 < H && j1 >= 0 && j1 < W) ? pl->magm[(size_t)i1 * W + j1] : 0.0f;
+                float n2 = (i2 >= 0 && i2 < H && j2 >= 0 && j2 < W) ? pl->magm[(size_t)i2 * W + j2] : 0.0f;
+                float d1 = m - n1, d2 = m - n2;
+                float mn = d1 < d2 ? d1 : d2;
+                rem = !(mn > 0.0f);
+            }
+            pl->removed[q] = (unsigned char)rem;
+            pl->thin[q] = rem ? 0.0f : pl->magm[q];
+        }
+    const int bpda = (pr->variant == EE_BPDA);
+    /* core.py:326: no low threshold -> the thinned magnitude itself.  CannyFilter_BPDA has no
+     * `else: thin_edges = low` branch (core.py:482-505), so it ALSO returns the raw thinned
+     * magnitude when only the low threshold is given. */
+    if (!pr->has_low || (bpda && !pr->has_high)) { memcpy(edge, pl->thin, hw * sizeof(float)); return; }
+    if (!pr->has_high) {                                                        /* core.py:323-324 */
+        for (size_t i = 0; i < hw; ++i) edge[i] = sign_step(pl->thin[i], pr->low_thr);
+        return;
+    }
+    for (size_t i = 0; i < hw; ++i) {   /* core.py:300,310,315 / :486-492 */
+        float lo = bpda ? to_compare(pl->thin[i], pr->low_thr) : sign_step(pl->thin[i], pr->low_thr);
+        float hi = bpda ? to_compare(pl->thin[i], pr->high_thr) : sign_step(pl->thin[i], pr->high_thr);
+        pl->hi[i] = hi;
+        pl->t[i] = lo * 0.5f + hi * 0.5f;
+    }
+    if (!pr->hysteresis) { memcpy(edge, pl->t, hw * sizeof(float)); return; }
+    /* hysteresis, core.py:317-321 / :494-503: weak = (t == .5); keep if 1.25*sum3x3(t) > 1 */
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            size_t q = (size_t)i * W + j;
+            float acc = 0.0f;
+            for (int a = -1; a <= 1; ++a)
+                for (int b = -1; b <= 1; ++b) {
+                    int ii = i + a, jj = j + b;
+                    if (ii >= 0 && ii < H && jj >= 0 && jj < W) acc += 1.25f * pl->t[(size_t)ii * W + jj];
+                }
+            int weak = (pl->t[q] == 0.5f);
+            int wih = weak && (acc > 1.0f);
+            pl->wih[q] = (unsigned char)wih;
+            edge[q] = pl->hi[q] + (wih ? 1.0f : 0.0f);
+        }
+}
+
+/* edge [B,1,H,W] = filter(x [B,C,H,W]) */
+int ee_oracle_edge_fwd(const float *x, float *edge, int B, int C, int H, int W,
+                       const ee_oracle_params *pr)
+{
+    const size_t hw = (size_t)H * W;
+    int err = 0;
+#pragma omp parallel
+    {
+        planes_t pl;
+        int ok = planes_alloc(&pl, hw) == 0;
+        if (!ok) {
+#pragma omp atomic write
+            err = -1;
+        }
+#pragma omp for schedule(static)
+        for (int b = 0; b < B; ++b)
+            if (ok) edge_forward_image(x + (size_t)b * C * hw, C, H, W, pr, &pl, edge + (size_t)b * hw);
+        if (ok) planes_free(&pl);
+    }
+    return err;
+}
+
+/* Blend, e.g. Tiny_ImageNet/models_tinyimagenet/resnet_EE.py:189-191:
+ *     out_c = clamp(base_c + w*edge, 0, 1)      (NaN propagates through torch.clamp) */
+static inline float clamp01_nan(float v) { return (v != v) ? v : (v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v)); }
+
+int ee_oracle_edge_blend_fwd(const float *x, const float *base, float *out, float *edge_or_null,
+                             int B, int C, int H, int W, const ee_oracle_params *pr, float w)
+{
+    const size_t hw = (size_t)H * W;
+    int err = 0;
+#pragma omp parallel
+    {
+        planes_t pl;
+        float *edge = (float *)malloc(hw * sizeof(float));
+        int ok = (planes_alloc(&pl, hw) == 0) && edge;
+        if (!ok) {
+#pragma omp atomic write
+            err = -1;
+        }
+#pragma omp for schedule(static)
+        for (int b = 0; b < B; ++b) {
+            if (!ok) continue;
+            edge_forward_image(x + (size_t)b * C * hw, C, H, W, pr, &pl, edge);
+            if (edge_or_null) memcpy(edge_or_null + (size_t)b * hw, edge, hw * sizeof(float));
+            for (int c = 0; c < C; ++c) {
+                const float *bs = base + ((size_t)b * C + c) * hw;
+                float *o = out + ((size_t)b * C + c) * hw;
+                for (size_t i = 0; i < hw; ++i) {
+                    float we = w * edge[i];
+                    o[i] = clamp01_nan(bs[i] + we);
+                }
+            }
+        }
+        free(edge);
+        if (ok) planes_free(&pl);
+    }
+    return err;
+}
+
+/* ------------------------------------------------------------------------------------
+ * Backward.  g_thin from the gradient w.r.t. the module output, per variant / mode.
+ *   STEP125: To_compare.backward, core.py:350-358:      g * [thr < in <= 1.001]
+ *   CANNY  : BinaryConnectDeterministic.backward core.py:138-145 through (sign(.)+1)/2:
+ *            0.5 * g * [|thin - thr| <= 1.001]; with hysteresis only `high` carries gradient
+ *            (core.py:319-321: weak / weak_is_high are integer tensors).
+ *   BPDA   : To_compare / To_eq (core.py:482-503); closed form in SURVEY.md A.3.
+ * ---------------------------------------------------------------------------------- */
+static inline float ste_window(float v, float thr) { return (v > thr && v <= 1.001f) ? 1.0f : 0.0f; }
+static inline float bcd_window(float v, float thr) { return (fabsf(v - thr) > 1.001f) ? 0.0f : 1.0f; }
+
+static float g_thin_of(const ee_oracle_params *pr, const planes_t *pl, size_t q, float ge)
+{
+    float th = pl->thin[q];
+    if (!pr->has_low) return ge;
+    if (pr->variant == EE_CANNY) {
+        if (!pr->has_high) return (0.5f * ge) * bcd_window(th, pr->low_thr);
+        if (!pr->hysteresis) {
+            float h = 0.5f * ge;   /* d(low*.5 + high*.5) */
+            return (0.5f * h) * bcd_window(th, pr->low_thr) + (0.5f * h) * bcd_window(th, pr->high_thr);
+        }
+        return (0.5f * ge) * bcd_window(th, pr->high_thr);
+    }
+    /* BPDA */
+    if (!pr->has_high) return ge;           /* raw thinned magnitude is returned, see forward */
+    if (!pr->hysteresis) {
+        float h = 0.5f * ge;
+        return h * ste_window(th, pr->low_thr) + h * ste_window(th, pr->high_thr);
+    }
+    {
+        float wih = pl->wih[q] ? 1.0f : 0.0f;
+        float gt = ge * wih;                        /* through To_eq(t) * weak_1 */
+        float g_low = 0.5f * gt;
+        float g_high = ge + 0.5f * gt;
+        return g_low * ste_window(th, pr->low_thr) + g_high * ste_window(th, pr->high_thr);
+    }
+}
+
+/* Adjoint of Stage C + Stage B for one image.  a = dL/dSgx, b = dL/dSgy on the image domain.
+ * corr^T into the padded frame followed by the replicate-pad fold, written as
+ * a gather with a fixed evaluation order:
+ *   HA(r,q) = a(r,q-1) - a(r,q+1)                       (zero extended)
+ *   HB(r,q) = fma(.5, b(r,q-1)+b(r,q+1), b(r,q))        (zero extended)
+ *   T(p,q)  = fma(.5, HA(p-1,q)+HA(p+1,q), HA(p,q)) + (HB(p-1,q) - HB(p+1,q)),  p in [-1,H], q in [-1,W]
+ *   column fold: F(p,j) = T(p,j) [+ T(p,-1) if j==0] [+ T(p,W) if j==W-1]
+ *   row fold   : gb(i,j) = F(i,j) [+ F(-1,j) if i==0] [+ F(H,j) if i==H-1]
+ * and the same with the Gaussian for the blur stage. */
+static inline float at0(const float *p, int H, int W, int i, int j)
+{
+    return (i >= 0 && i < H && j >= 0 && j < W) ? p[(size_t)i * W + j] : 0.0f;
+}
+
+static float sobelT_T(const float *a, const float *b, int H, int W, int p, int q)
+{
+    float ha[3], hb[3];
+    for (int d = -1; d <= 1; ++d) {
+        int r = p + d;
+        ha[d + 1] = at0(a, H, W, r, q - 1) - at0(a, H, W, r, q + 1);
+        hb[d + 1] = fmaf(0.5f, at0(b, H, W, r, q - 1) + at0(b, H, W, r, q + 1), at0(b, H, W, r, q));
+    }
+    float xa = fmaf(0.5f, ha[0] + ha[2], ha[1]);
+    float yb = hb[0] - hb[2];
+    return xa + yb;
+}
+
+static float gaussT_T(const float *g, int H, int W, float c0, float c1, float c2, int p, int q)
+{
+    float P[3], Qm = 0.0f;
+    for (int d = -1; d <= 1; ++d) {
+        int r = p + d;
+        float l = at0(g, H, W, r, q - 1), rr = at0(g, H, W, r, q + 1), m = at0(g, H, W, r, q);
+        float e = l + rr;
+        P[d + 1] = fmaf(c1, m, c0 * e);
+        if (d == 0) Qm = fmaf(c2, m, c1 * e);
+    }
+    return (P[0] + Qm) + P[2];
+}
+
+typedef float (*tapfn)(const void *ctx, int p, int q);
+
+static float fold_cols(tapfn f, const void *ctx, int W, int p, int j)
+{
+    float v = f(ctx, p, j);
+    if (j == 0) v = v + f(ctx, p, -1);
+    if (j == W - 1) v = v + f(ctx, p, W);
+    return v;
+}
+static float fold_all(tapfn f, const void *ctx, int H, int W, int i, int j)
+{
+    float v = fold_cols(f, ctx, W, i, j);
+    if (i == 0) v = v + fold_cols(f, ctx, W, -1, j);
+    if (i == H - 1) v = v + fold_cols(f, ctx, W, H, j);
+    return v;
+}
+
+typedef struct { const float *a, *b; int H, W; } sob_ctx;
+typedef struct { const float *g; int H, W; float c0, c1, c2; } gau_ctx;
+static float sob_tap(const void *c, int p, int q) { const sob_ctx *s = (const sob_ctx *)c; return sobelT_T(s->a, s->b, s->H, s->W, p, q); }
+static float gau_tap(const void *c, int p, int q) { const gau_ctx *s = (const gau_ctx *)c; return gaussT_T(s->g, s->H, s->W, s->c0, s->c1, s->c2, p, q); }
+
+/* ge[H*W] = dL/d(edge) ; writes gs[H*W] = dL/d(s) (identical for every channel of x). */
+static void edge_backward_image(const float *ge, int C, int H, int W, const ee_oracle_params *pr,
+                                const planes_t *pl, float *a, float *b, float *gb, float *gs)
+{
+    const size_t hw = (size_t)H * W;
+    const float fC = (float)C;
+    for (size_t q = 0; q < hw; ++q) {
+        float gm;
+        if (pr->variant == EE_STEP125) {
+            gm = ge[q] * ste_window(pl->magm[q], pr->high_thr);
+            if (pl->mag[q] < pr->alpha) gm = 0.0f;              /* torch.where backward */
+        } else {
+            gm = g_thin_of(pr, pl, q, ge[q]);
+            if (pl->removed[q]) gm = 0.0f;                       /* core.py:290 / :480 */
+            if (pr->variant == EE_CANNY && pl->mag[q] < pr->alpha) gm = 0.0f;
+        }
+        /* mag = u^0.5, u = gx1^2 + gy1^2 ; autograd: g*0.5*u^-0.5 then *2*gx1 then /C.
+         * Sub-gradient at mag == 0 defined as 0 (the reference yields NaN). */
+        float m = pl->mag[q];
+        if (gm == 0.0f || m == 0.0f) { a[q] = 0.0f; b[q] = 0.0f; continue; }
+        float t = (gm * 0.5f) / m;
+        a[q] = (t * (2.0f * pl->gx1[q])) / fC;
+        b[q] = (t * (2.0f * pl->gy1[q])) / fC;
+    }
+    sob_ctx sc = { a, b, H, W };
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) gb[(size_t)i * W + j] = fold_all(sob_tap, &sc, H, W, i, j);
+    gau_ctx gc = { gb, H, W, pr->c0, pr->c1, pr->c2 };
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) gs[(size_t)i * W + j] = fold_all(gau_tap, &gc, H, W, i, j);
+}
+
+/* g_x [B,C,H,W] from g_edge [B,1,H,W] (module-level backward of CannyFilter*.forward). */
+int ee_oracle_edge_bwd(const float *g_edge, const float *x, float *g_x, int B, int C, int H, int W,
+                       const ee_oracle_params *pr)
+{
+    const size_t hw = (size_t)H * W;
+    int err = 0;
+#pragma omp parallel
+    {
+        planes_t pl;
+        float *tmp = (float *)malloc(hw * sizeof(float) * 5);
+        int ok = (planes_alloc(&pl, hw) == 0) && tmp;
+        if (!ok) {
+#pragma omp atomic write
+            err = -1;
+        }
+#pragma omp for schedule(static)
+        for (int bi = 0; bi < B; ++bi) {
+            if (!ok) continue;
+            float *edge = tmp, *a = tmp + hw, *b = tmp + 2 * hw, *gb = tmp + 3 * hw, *gs = tmp + 4 * hw;
+            edge_forward_image(x + (size_t)bi * C * hw, C, H, W, pr, &pl, edge);
+            edge_backward_image(g_edge + (size_t)bi * hw, C, H, W, pr, &pl, a, b, gb, gs);
+            for (int c = 0; c < C; ++c) memcpy(g_x + ((size_t)bi * C + c) * hw, gs, hw * sizeof(float));
+        }
+        free(tmp);
+        if (ok) planes_free(&pl);
+    }
+    return err;
+}
+
+/* Fused backward of out = clamp(base + w*edge(x), 0, 1):
+ *   g_pre_c = g_out_c * [0 <= pre_c <= 1]  (clamp backward, inclusive) ; g_base_c = g_pre_c
+ *   g_e     = sum_c (g_pre_c * w)          (mul backward then broadcast-sum over channels)
+ *   g_x     = edge_backward(g_e)           (edge path only; HFS^T(g_base) is added by autograd) */
+int ee_oracle_edge_blend_bwd(const float *g_out, const float *x, const float *base, float *g_x,
+                             float *g_base, int B, int C, int H, int W, const ee_oracle_params *pr, float w)
+{
+    const size_t hw = (size_t)H * W;
+    int err = 0;
+#pragma omp parallel
+    {
+        planes_t pl;
+        float *tmp = (float *)malloc(hw * sizeof(float) * 6);
+        int ok = (planes_alloc(&pl, hw) == 0) && tmp;
+        if (!ok) {
+#pragma omp atomic write
+            err = -1;
+        }
+#pragma omp for schedule(static)
+        for (int bi = 0; bi < B; ++bi) {
+            if (!ok) continue;
+            float *edge = tmp, *a = tmp + hw, *b = tmp + 2 * hw, *gb = tmp + 3 * hw, *gs = tmp + 4 * hw, *ge = tmp + 5 * hw;
+            edge_forward_image(x + (size_t)bi * C * hw, C, H, W, pr, &pl, edge);
+            for (size_t q = 0; q < hw; ++q) {
+                float acc = 0.0f;
+                for (int c = 0; c < C; ++c) {
+                    size_t o = ((size_t)bi * C + c) * hw + q;
+                    float we = w * edge[q];
+                    float pre = base[o] + we;
+                    float gp = (pre >= 0.0f && pre <= 1.0f) ? g_out[o] : 0.0f;
+                    if (g_base) g_base[o] = gp;
+                    acc = (c == 0) ? gp * w : fmaf(gp, w, acc);
+                }
+                ge[q] = acc;
+            }
+            if (g_x) {
+                edge_backward_image(ge, C, H, W, pr, &pl, a, b, gb, gs);
+                for (int c = 0; c < C; ++c) memcpy(g_x + ((size_t)bi * C + c) * hw, gs, hw * sizeof(float));
+            }
+        }
+        free(tmp);
+        if (ok) planes_free(&pl);
+    }
+    return err;
+}
+
+/* ------------------------------------------------------------------------------------
+ * Attack updates (utils/attacks.py).  torch.sign: sign(0) = 0, sign(NaN) = 0 (probed on
+ * torch 2.11: (0<g)-(g<0)).  torch.min/max/clamp propagate NaN.
+ * ---------------------------------------------------------------------------------- */
+static inline float sgn(float g) { return (float)((g > 0.0f) - (g < 0.0f)); }
+static inline float maxn(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
+static inline float minn(float a, float b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
+
+/* PGD L-inf step, attacks.py:25-27 (also :52-54, :82-84, :257-259, :298-300, :318-320,
+ * :353-355, :414-416, :466-468, :505-507 with alpha_signed = -step for the targeted ones). */
+void ee_oracle_pgd_linf_step(const float *x, const float *g, const float *x0, float *out, int64_t n,
+                             float alpha_signed, float eps, float lo, float hi)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        float t = x[i] + alpha_signed * sgn(g[i]);
+        t = minn(maxn(t, x0[i] - eps), x0[i] + eps);
+        out[i] = minn(maxn(t, lo), hi);
+    }
+}
+
+/* FGSM, attacks.py:121-126: one signed step and the [0,1] clamp, no eps projection. */
+void ee_oracle_fgsm_step(const float *x, const float *g, float *out, int64_t n, float alpha_signed,
+                         float lo, float hi)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        float t = x[i] + alpha_signed * sgn(g[i]);
+        out[i] = minn(maxn(t, lo), hi);
+    }
+}
+
+/* free / fast AT delta update, ImageNet/free_imagenet/AT_hfs_canny_free_imagenet_ddp.py:330-332
+ * then :314-315 of the next repeat:  delta += a*sign(g); delta.clamp_(-eps,eps);
+ * x_adv = clamp(x0 + delta, 0, 1). */
+void ee_oracle_free_at_step(float *delta, const float *g, const float *x0, float *x_adv, int64_t n,
+                            float alpha, float eps, float lo, float hi)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        float d = delta[i] + alpha * sgn(g[i]);
+        d = minn(maxn(d, -eps), eps);
+        delta[i] = d;
+        if (x_adv) x_adv[i] = minn(maxn(x0[i] + d, lo), hi);
+    }
+}
+
+/* CW L-inf inner update, attacks.py:213-222. */
+void ee_oracle_cw_linf_step(const float *adv, const float *g, const float *x, const float *min_x,
+                            const float *max_x, float *out, int64_t n, float step, float magnitude)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        float t = adv[i] + step * sgn(g[i]);
+        t = maxn(minn(t, x[i] + magnitude), x[i] - magnitude);
+        t = minn(maxn(t, 0.0f), 1.0f);
+        out[i] = maxn(minn(t, max_x[i]), min_x[i]);
+    }
+}
+
+/* Per-sample RMS "l2_norm" of attacks.py:360-366: sqrt(mean(v^2)).  Canonical reduction
+ * order (shared with the CUDA kernel): 1024 lane partials, lane l sums elements l, l+1024,
+ * ... in index order; then a fixed pairwise tree: strides 16..1 inside every group of 32
+ * lanes, then strides 16..1 over the 32 group sums. */
+#define EE_L2_LANES 1024
+static float rms_canonical(const float *v, int64_t n, const float *v2_sub, int mode)
+{
+    /* mode 0: v ; mode 1: v - v2_sub */
+    float part[EE_L2_LANES];
+    for (int l = 0; l < EE_L2_LANES; ++l) {
+        float acc = 0.0f;
+        for (int64_t i = l; i < n; i += EE_L2_LANES) {
+            float e = mode ? (v[i] - v2_sub[i]) : v[i];
+            acc = fmaf(e, e, acc);
+        }
+        part[l] = acc;
+    }
+    /* warp-first tree: inside each group of 32 lanes strides 16..1, then the 32 group sums */
+    float wsum[32];
+    for (int w = 0; w < EE_L2_LANES / 32; ++w) {
+        float *p = part + 32 * w;
+        for (int s = 16; s >= 1; s >>= 1)
+            for (int l = 0; l < s; ++l) p[l] = p[l] + p[l + s];
+        wsum[w] = p[0];
+    }
+    for (int s = 16; s >= 1; s >>= 1)
+        for (int l = 0; l < s; ++l) wsum[l] = wsum[l] + wsum[l + s];
+    return sqrtf(wsum[0] / (float)n);
+}
+
+/* TRADES PGD-L2 step, attacks.py:391-399. */
+void ee_oracle_pgd_l2_step(const float *x, const float *g, const float *x0, float *out, int B,
+                           int64_t n_per, float step, float eps)
+{
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b) {
+        const float *xb = x + (int64_t)b * n_per, *gb = g + (int64_t)b * n_per, *x0b = x0 + (int64_t)b * n_per;
+        float *ob = out + (int64_t)b * n_per;
+        float gn = rms_canonical(gb, n_per, NULL, 0) + 1e-8f;      /* :391 */
+        for (int64_t i = 0; i < n_per; ++i) ob[i] = xb[i] + step * (gb[i] / gn);   /* :391-392 */
+        float dn = rms_canonical(ob, n_per, x0b, 1);               /* :394-395 */
+        int cond = dn > eps;                                       /* :396 */
+        float scale = eps / dn;                                    /* :397 */
+        for (int64_t i = 0; i < n_per; ++i) {
+            float d = ob[i] - x0b[i];
+            if (cond) d = d * scale;
+            ob[i] = minn(maxn(x0b[i] + d, 0.0f), 1.0f);            /* :398-399 */
+        }
+    }
+}
+
+/* STE helper Functions (core.py:115-145, :329-382), elementwise. */
+void ee_oracle_to_compare_fwd(const float *in, float *out, int64_t n, float thr)
+{ for (int64_t i = 0; i < n; ++i) out[i] = to_compare(in[i], thr); }
+void ee_oracle_to_compare_bwd(const float *g, const float *in, float *out, int64_t n, float thr)
+{ for (int64_t i = 0; i < n; ++i) out[i] = (in[i] <= thr || in[i] > 1.001f) ? 0.0f : g[i]; }
+void ee_oracle_to_eq_fwd(const float *in, float *out, int64_t n)
+{ for (int64_t i = 0; i < n; ++i) out[i] = (in[i] == 0.5f) ? 1.0f : 0.0f; }
+void ee_oracle_to_eq_bwd(const float *g, const float *in, float *out, int64_t n)
+{ for (int64_t i = 0; i < n; ++i) out[i] = (in[i] != 0.5f) ? 0.0f : g[i]; }
+void ee_oracle_safe_sign_fwd(const float *in, float *out, int64_t n)
+{ for (int64_t i = 0; i < n; ++i) { float s = sgn(in[i]); out[i] = (s == 0.0f) ? -1.0f : s; } }
+void ee_oracle_safe_sign_bwd(const float *g, const float *in, float *out, int64_t n)
+{ for (int64_t i = 0; i < n; ++i) out[i] = (fabsf(in[i]) > 1.001f) ? 0.0f : g[i]; }
+
+int ee_oracle_version(void) { return 1; }

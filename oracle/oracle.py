@@ -1,0 +1,202 @@
+"""numpy/ctypes front-end of the C oracle (oracle/ee_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- see oracle/__init__.py.  All functions take and return
+C-contiguous float32 numpy arrays in NCHW; nothing here touches CUDA or torch.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+STEP125, CANNY, BPDA = 0, 1, 2
+VARIANTS = {"step125": STEP125, "canny": CANNY, "bpda": BPDA}
+
+
+class OracleParams(ctypes.Structure):
+    _fields_ = [("variant", ctypes.c_int),
+                ("c0", ctypes.c_float), ("c1", ctypes.c_float), ("c2", ctypes.c_float),
+                ("alpha", ctypes.c_float),
+                ("low_thr", ctypes.c_float), ("high_thr", ctypes.c_float),
+                ("has_low", ctypes.c_int), ("has_high", ctypes.c_int),
+                ("hysteresis", ctypes.c_int)]
+
+
+def gaussian3(mu=0.0, sigma=1.0):
+    """fp32 3x3 Gaussian exactly as utils/core.py:58-72 + the .type(torch.float) of :164."""
+    g1 = np.linspace(-1, 1, 3)
+    x, y = np.meshgrid(g1, g1)
+    d = (x ** 2 + y ** 2) ** 0.5
+    g = np.exp(-(d - mu) ** 2 / (2 * sigma ** 2)) / (2 * np.pi * sigma ** 2)
+    g = g / np.sum(g)
+    return g.astype(np.float32)
+
+
+def make_params(variant="step125", mu=0.0, sigma=1.0, alpha=0.0, low=None, high=None, hysteresis=False):
+    g = gaussian3(mu, sigma)
+    v = VARIANTS[variant] if isinstance(variant, str) else int(variant)
+    return OracleParams(v, float(g[0, 0]), float(g[0, 1]), float(g[1, 1]), float(np.float32(alpha)),
+                        float(np.float32(0.0 if low is None else low)),
+                        float(np.float32(0.0 if high is None else high)),
+                        int(low is not None), int(high is not None), int(bool(hysteresis)))
+
+
+_LIB = None
+
+
+def _cpu_has_fma():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    fl = line.split()
+                    return "fma" in fl and "avx2" in fl
+    except OSError:
+        pass
+    return False
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    kind = "fma" if _cpu_has_fma() else "generic"
+    path = _build.lib_path(kind)
+    if not os.path.exists(path):
+        _build.build()
+    L = ctypes.CDLL(path)
+    fp = ctypes.POINTER(ctypes.c_float)
+    pp = ctypes.POINTER(OracleParams)
+    i, i64, f = ctypes.c_int, ctypes.c_int64, ctypes.c_float
+    L.ee_oracle_edge_fwd.argtypes = [fp, fp, i, i, i, i, pp]
+    L.ee_oracle_edge_fwd.restype = i
+    L.ee_oracle_edge_blend_fwd.argtypes = [fp, fp, fp, fp, i, i, i, i, pp, f]
+    L.ee_oracle_edge_blend_fwd.restype = i
+    L.ee_oracle_edge_bwd.argtypes = [fp, fp, fp, i, i, i, i, pp]
+    L.ee_oracle_edge_bwd.restype = i
+    L.ee_oracle_edge_blend_bwd.argtypes = [fp, fp, fp, fp, fp, i, i, i, i, pp, f]
+    L.ee_oracle_edge_blend_bwd.restype = i
+    L.ee_oracle_pgd_linf_step.argtypes = [fp, fp, fp, fp, i64, f, f, f, f]
+    L.ee_oracle_pgd_linf_step.restype = None
+    L.ee_oracle_fgsm_step.argtypes = [fp, fp, fp, i64, f, f, f]
+    L.ee_oracle_fgsm_step.restype = None
+    L.ee_oracle_free_at_step.argtypes = [fp, fp, fp, fp, i64, f, f, f, f]
+    L.ee_oracle_free_at_step.restype = None
+    L.ee_oracle_cw_linf_step.argtypes = [fp, fp, fp, fp, fp, fp, i64, f, f]
+    L.ee_oracle_cw_linf_step.restype = None
+    L.ee_oracle_pgd_l2_step.argtypes = [fp, fp, fp, fp, i, i64, f, f]
+    L.ee_oracle_pgd_l2_step.restype = None
+    for name in ("to_compare",):
+        getattr(L, "ee_oracle_%s_fwd" % name).argtypes = [fp, fp, i64, f]
+        getattr(L, "ee_oracle_%s_bwd" % name).argtypes = [fp, fp, fp, i64, f]
+    for name in ("to_eq", "safe_sign"):
+        getattr(L, "ee_oracle_%s_fwd" % name).argtypes = [fp, fp, i64]
+        getattr(L, "ee_oracle_%s_bwd" % name).argtypes = [fp, fp, fp, i64]
+    _LIB = L
+    return L
+
+
+def _f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def _chk(rc):
+    if rc != 0:
+        raise MemoryError("oracle allocation failed")
+
+
+def edge_fwd(x, params):
+    x = _f32(x)
+    B, C, H, W = x.shape
+    edge = np.empty((B, 1, H, W), np.float32)
+    _chk(lib().ee_oracle_edge_fwd(_p(x), _p(edge), B, C, H, W, ctypes.byref(params)))
+    return edge
+
+
+def edge_blend_fwd(x, base, params, w, want_edge=False):
+    x, base = _f32(x), _f32(base)
+    B, C, H, W = x.shape
+    out = np.empty_like(x)
+    edge = np.empty((B, 1, H, W), np.float32) if want_edge else None
+    _chk(lib().ee_oracle_edge_blend_fwd(_p(x), _p(base), _p(out), _p(edge), B, C, H, W,
+                                        ctypes.byref(params), float(np.float32(w))))
+    return (out, edge) if want_edge else out
+
+
+def edge_bwd(g_edge, x, params):
+    g_edge, x = _f32(g_edge), _f32(x)
+    B, C, H, W = x.shape
+    g_x = np.empty_like(x)
+    _chk(lib().ee_oracle_edge_bwd(_p(g_edge), _p(x), _p(g_x), B, C, H, W, ctypes.byref(params)))
+    return g_x
+
+
+def edge_blend_bwd(g_out, x, base, params, w):
+    g_out, x, base = _f32(g_out), _f32(x), _f32(base)
+    B, C, H, W = x.shape
+    g_x, g_base = np.empty_like(x), np.empty_like(x)
+    _chk(lib().ee_oracle_edge_blend_bwd(_p(g_out), _p(x), _p(base), _p(g_x), _p(g_base), B, C, H, W,
+                                        ctypes.byref(params), float(np.float32(w))))
+    return g_x, g_base
+
+
+def pgd_linf_step(x, g, x0, alpha_signed, eps, lo=0.0, hi=1.0):
+    x, g, x0 = _f32(x), _f32(g), _f32(x0)
+    out = np.empty_like(x)
+    lib().ee_oracle_pgd_linf_step(_p(x), _p(g), _p(x0), _p(out), x.size, alpha_signed, eps, lo, hi)
+    return out
+
+
+def fgsm_step(x, g, alpha_signed, lo=0.0, hi=1.0):
+    x, g = _f32(x), _f32(g)
+    out = np.empty_like(x)
+    lib().ee_oracle_fgsm_step(_p(x), _p(g), _p(out), x.size, alpha_signed, lo, hi)
+    return out
+
+
+def free_at_step(delta, g, x0, alpha, eps, lo=0.0, hi=1.0):
+    """Returns (delta_new, x_adv); does not modify its inputs."""
+    d = _f32(delta).copy()
+    g, x0 = _f32(g), _f32(x0)
+    x_adv = np.empty_like(x0)
+    lib().ee_oracle_free_at_step(_p(d), _p(g), _p(x0), _p(x_adv), d.size, alpha, eps, lo, hi)
+    return d, x_adv
+
+
+def cw_linf_step(adv, g, x, min_x, max_x, step, magnitude):
+    adv, g, x, min_x, max_x = map(_f32, (adv, g, x, min_x, max_x))
+    out = np.empty_like(adv)
+    lib().ee_oracle_cw_linf_step(_p(adv), _p(g), _p(x), _p(min_x), _p(max_x), _p(out), adv.size, step, magnitude)
+    return out
+
+
+def pgd_l2_step(x, g, x0, step, eps):
+    x, g, x0 = _f32(x), _f32(g), _f32(x0)
+    out = np.empty_like(x)
+    B = x.shape[0]
+    lib().ee_oracle_pgd_l2_step(_p(x), _p(g), _p(x0), _p(out), B, x.size // B, step, eps)
+    return out
+
+
+def _ew(name, *arrs, thr=None):
+    arrs = [_f32(a) for a in arrs]
+    out = np.empty_like(arrs[0])
+    args = [_p(a) for a in arrs] + [_p(out), arrs[0].size]
+    if thr is not None:
+        args.append(float(np.float32(thr)))
+    getattr(lib(), name)(*args)
+    return out
+
+
+def to_compare_fwd(v, thr): return _ew("ee_oracle_to_compare_fwd", v, thr=thr)
+def to_compare_bwd(g, v, thr): return _ew("ee_oracle_to_compare_bwd", g, v, thr=thr)
+def to_eq_fwd(v): return _ew("ee_oracle_to_eq_fwd", v)
+def to_eq_bwd(g, v): return _ew("ee_oracle_to_eq_bwd", g, v)
+def safe_sign_fwd(v): return _ew("ee_oracle_safe_sign_fwd", v)
+def safe_sign_bwd(g, v): return _ew("ee_oracle_safe_sign_bwd", g, v)
