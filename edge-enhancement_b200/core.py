@@ -1,0 +1,348 @@
+"""Drop-in for the reference's ``utils/core.py`` -- same names, constructor and forward signatures.
+
+    CannyFilter, CannyFilter_BPDA, CannyFilter_step125_1      (utils/core.py:148, :386, :509)
+    To_compare, To_eq, BinaryConnectDeterministic, safeSign   (utils/core.py:329, :361, :121, :115)
+    get_gaussian_kernel, get_sobel_kernel, get_thin_kernels   (utils/core.py:58, :75, :87)
+    HighFreqSuppress, Add_Square                              (utils/core.py:15, :589; torch pass-through)
+
+plus the fused entry the *_EE models should call instead of ``clamp(x_hfs + w*canny(x), 0, 1)``:
+
+    edge_enhance(img, base, canny_module, w, low_threshold, high_threshold, hysteresis)
+
+The filters run as ONE fused CUDA kernel per direction (libedge_b200.so) instead of the
+reference's ~35-120 eager launches.  CUDA-only, fp32-only, 3x3 Gaussian / 3x3 Sobel (every
+reference config); anything else raises.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import functional as F_ee
+
+
+# ---------------------------------------------------------------------------------------------
+# kernel builders (host side, numpy) -- same arithmetic as the reference
+# ---------------------------------------------------------------------------------------------
+def get_gaussian_kernel(k=3, mu=0, sigma=1, normalize=True):
+    """utils/core.py:58-72: 2-D Gaussian of the distance to the centre on a linspace(-1,1,k) grid."""
+    gaussian_1D = np.linspace(-1, 1, k)
+    x, y = np.meshgrid(gaussian_1D, gaussian_1D)
+    distance = (x ** 2 + y ** 2) ** 0.5
+    gaussian_2D = np.exp(-(distance - mu) ** 2 / (2 * sigma ** 2))
+    gaussian_2D = gaussian_2D / (2 * np.pi * sigma ** 2)
+    if normalize:
+        gaussian_2D = gaussian_2D / np.sum(gaussian_2D)
+    return gaussian_2D
+
+
+def get_sobel_kernel(k=3):
+    """utils/core.py:75-84: x / (x^2 + y^2) with the centre column's denominator forced to 1."""
+    rng = np.linspace(-(k // 2), k // 2, k)
+    x, y = np.meshgrid(rng, rng)
+    sobel_2D_numerator = x
+    sobel_2D_denominator = (x ** 2 + y ** 2)
+    sobel_2D_denominator[:, k // 2] = 1
+    return sobel_2D_numerator / sobel_2D_denominator
+
+
+# (row, col) of the -1 tap of the k-th directional kernel; centre tap is +1.  These are the
+# values cv2.warpAffine(INTER_NEAREST) produces in utils/core.py:87-112 (asserted against cv2 in
+# tests/test_host_logic.py when cv2 is importable).
+_THIN_OFFSETS = [(0, 1), (-1, 1), (-1, 0), (-1, -1), (0, -1), (1, -1), (1, 0), (1, 1)]
+
+
+def get_thin_kernels(start=0, end=360, step=45):
+    """utils/core.py:87-112 without the cv2 dependency (multiples of 45 degrees only)."""
+    kernels = []
+    for angle in range(start, end, step):
+        if angle % 45 != 0:
+            raise NotImplementedError("directional kernels are tabulated for multiples of 45 degrees")
+        dr, dc = _THIN_OFFSETS[(angle // 45) % 8]
+        k = np.zeros((3, 3))
+        k[1, 1] = 1.0
+        k[1 + dr, 1 + dc] = -1.0
+        kernels.append(k)
+    return kernels
+
+
+# ---------------------------------------------------------------------------------------------
+# straight-through Functions (CUDA elementwise kernels)
+# ---------------------------------------------------------------------------------------------
+def safeSign(tensor):
+    """utils/core.py:115-118: sign with sign(0) := -1."""
+    return F_ee.safe_sign(tensor)
+
+
+class BinaryConnectDeterministic(torch.autograd.Function):
+    """utils/core.py:121-145: forward safeSign, backward g * [|x| <= 1.001]."""
+
+    @staticmethod
+    def forward(ctx, input):
+        return F_ee.SafeSignFn.forward(ctx, input)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return F_ee.SafeSignFn.backward(ctx, grad_output)
+
+
+class To_compare(torch.autograd.Function):
+    """utils/core.py:329-358: forward [x > thr], backward g * [thr < x <= 1.001]; thr is a 0-dim tensor."""
+
+    @staticmethod
+    def forward(ctx, input, threshold):
+        return F_ee.ToCompareFn.forward(ctx, input, threshold)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return F_ee.ToCompareFn.backward(ctx, grad_output)
+
+
+class To_eq(torch.autograd.Function):
+    """utils/core.py:361-382: forward [x == 0.5], backward g * [x == 0.5]."""
+
+    @staticmethod
+    def forward(ctx, input):
+        return F_ee.ToEqFn.forward(ctx, input)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return F_ee.ToEqFn.backward(ctx, grad_output)
+
+
+# ---------------------------------------------------------------------------------------------
+# the three filters
+# ---------------------------------------------------------------------------------------------
+def _kernel_tensors(k_gaussian, mu, sigma, k_sobel):
+    if k_gaussian != 3 or k_sobel != 3:
+        raise NotImplementedError("edge_b200 implements k_gaussian=3, k_sobel=3 (all reference configs); got %d / %d"
+                                  % (k_gaussian, k_sobel))
+    gaussian_2D = get_gaussian_kernel(k_gaussian, mu, sigma)
+    g = torch.from_numpy(gaussian_2D).unsqueeze(0).unsqueeze(0).type(torch.float)
+    sobel_2D = get_sobel_kernel(k_sobel)
+    sx = torch.from_numpy(sobel_2D).unsqueeze(0).unsqueeze(0).type(torch.float)
+    sy = torch.from_numpy(sobel_2D.T.copy()).unsqueeze(0).unsqueeze(0).type(torch.float)
+    thin = get_thin_kernels()
+    d = torch.from_numpy(np.stack(thin)).unsqueeze(1).type(torch.float)
+    h = torch.from_numpy(np.ones((3, 3)) + 0.25).unsqueeze(0).unsqueeze(0).type(torch.float)
+    return g, sx, sy, d, h, thin[0].shape[-1] // 2
+
+
+class _EdgeFilterBase(nn.Module):
+    _variant = None
+
+    def _setup(self, k_gaussian, mu, sigma, k_sobel, use_cuda, alpha):
+        self.device = 'cuda' if use_cuda else 'cpu'
+        print('CannyFilter; sigma:{}, alpha:{}'.format(sigma, alpha))      # reference banner (core.py:160)
+        self.pad_gaussian = nn.ReplicationPad2d(k_gaussian // 2)
+        self.reflect_pad = nn.ReplicationPad2d(k_sobel // 2)
+        g, sx, sy, d, h, pad_dir = _kernel_tensors(k_gaussian, mu, sigma, k_sobel)
+        self.padding_directional = pad_dir
+        self._alpha_f = float(alpha)
+        self._gauss_np = g.reshape(3, 3).numpy().copy()      # host copy: no device sync per forward
+        self._sobel_np = sx.reshape(3, 3).numpy().copy()
+        return g, sx, sy, d, h
+
+    def params(self, low_threshold=None, high_threshold=None, hysteresis=False):
+        """EEParams for one forward() call (C-ABI struct, passed by value to the kernels)."""
+        return F_ee.make_params(self._variant, self._gauss_np, self._alpha_f, low_threshold, high_threshold,
+                                hysteresis, sobel=self._sobel_np)
+
+    def forward(self, img, low_threshold=None, high_threshold=None, hysteresis=False):
+        return F_ee.EdgeMapFn.apply(img, self.params(low_threshold, high_threshold, hysteresis))
+
+
+class CannyFilter(_EdgeFilterBase):
+    """utils/core.py:148-326.  Frozen kernels are registered nn.Parameters exactly like the
+    reference, so checkpoints keep their ``canny.weight_*`` keys."""
+    _variant = "canny"
+
+    def __init__(self, k_gaussian=3, mu=0, sigma=1, k_sobel=3, use_cuda=False, alpha=0.0):
+        super(CannyFilter, self).__init__()
+        g, sx, sy, d, h = self._setup(k_gaussian, mu, sigma, k_sobel, use_cuda, alpha)
+        self.alpha = alpha
+        self.weight_gaussian = nn.Parameter(data=g, requires_grad=False)
+        self.weight_sobel_x = nn.Parameter(data=sx, requires_grad=False)
+        self.weight_sobel_y = nn.Parameter(data=sy, requires_grad=False)
+        self.weight_directional = nn.Parameter(data=d, requires_grad=False)
+        self.weight_hysteresis = nn.Parameter(data=h, requires_grad=False)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        super(CannyFilter, self)._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        # the kernels read the Gaussian taps from a host copy; keep it in step with a loaded checkpoint
+        self._gauss_np = self.weight_gaussian.detach().cpu().reshape(3, 3).numpy().copy()
+        self._sobel_np = self.weight_sobel_x.detach().cpu().reshape(3, 3).numpy().copy()
+
+
+class _PlainTensorFilter(_EdgeFilterBase):
+    """BPDA / step125_1 keep their kernels as plain tensors moved with .to(self.device)
+    (utils/core.py:403-424, :526-547): no state-dict keys, no .to()/DataParallel tracking."""
+
+    def __init__(self, k_gaussian=3, mu=0, sigma=1, k_sobel=3, use_cuda=False, alpha=0.0):
+        super(_PlainTensorFilter, self).__init__()
+        g, sx, sy, d, h = self._setup(k_gaussian, mu, sigma, k_sobel, use_cuda, alpha)
+        self.alpha = torch.tensor(alpha)
+        self.weight_gaussian = g.to(self.device)
+        self.weight_sobel_x = sx.to(self.device)
+        self.weight_sobel_y = sy.to(self.device)
+        self.weight_directional = d.to(self.device)
+        self.weight_hysteresis = h.to(self.device)
+
+
+class CannyFilter_BPDA(_PlainTensorFilter):
+    """utils/core.py:386-505."""
+    _variant = "bpda"
+
+
+class CannyFilter_step125_1(_PlainTensorFilter):
+    """utils/core.py:509-585.  low_threshold / hysteresis are accepted and ignored like the reference;
+    high_threshold=None raises UnboundLocalError like the reference (core.py:578-583)."""
+    _variant = "step125"
+
+    def forward(self, img, low_threshold=None, high_threshold=None, hysteresis=False):
+        if high_threshold is None:
+            raise UnboundLocalError("cannot access local variable 'high' where it is not associated with a value "
+                                    "(CannyFilter_step125_1 needs high_threshold)")
+        return F_ee.EdgeMapFn.apply(img, self.params(None, high_threshold, False))
+
+
+# ---------------------------------------------------------------------------------------------
+# fused edge + blend (what the *_EE models should call)
+# ---------------------------------------------------------------------------------------------
+def edge_enhance(img, base, canny, w, low_threshold=None, high_threshold=None, hysteresis=False):
+    """clamp(base + w * canny(img, low, high, hysteresis), 0, 1) as one kernel per direction.
+
+    Replaces e.g. Tiny_ImageNet/models_tinyimagenet/resnet_EE.py:182-191 (gf=False):
+        x_canny = self.canny(x, ...); x = x_hfs + self.w * x_canny; x = torch.clamp(x, 0.0, 1.0)
+    `base` is x_hfs (any tensor shaped like img); gradients flow to both img and base.
+    """
+    if isinstance(canny, CannyFilter_step125_1):
+        if high_threshold is None:
+            raise UnboundLocalError("CannyFilter_step125_1 needs high_threshold")
+        p = canny.params(None, high_threshold, False)
+    else:
+        p = canny.params(low_threshold, high_threshold, hysteresis)
+    return F_ee.EdgeEnhanceFn.apply(img, base, p, float(w))
+
+
+class EdgeEnhance(nn.Module):
+    """Module form of edge_enhance: the `hfs -> canny -> blend -> clamp` front end of every *_EE model
+    (MNIST/models_mnist/Net2_EE.py:36-49, Tiny_ImageNet/.../resnet_EE.py:176-191,
+    ImageNet/models_imagenet/resnet_EE.py:167-179, AWP/.../preactresnet_EE*.py:145-159)."""
+
+    def __init__(self, cize=224, r=16, w=0.5, low=60.0, high=120.0, alpha=0.0, sigma=1,
+                 type_canny='CannyFilter', hfs=True):
+        super(EdgeEnhance, self).__init__()
+        self.w = w
+        self.low = low / 255
+        self.high = high / 255
+        self.hfs = HighFreqSuppress(cize, cize, r) if hfs else None
+        if type_canny == 'CannyFilter':
+            self.canny = CannyFilter(sigma=sigma, use_cuda=True, alpha=alpha)
+        elif type_canny == 'CannyFilter_step125_1':
+            self.canny = CannyFilter_step125_1(sigma=sigma, use_cuda=False, alpha=alpha)
+        elif type_canny == 'CannyFilter_BPDA':
+            self.canny = CannyFilter_BPDA(sigma=sigma, use_cuda=False, alpha=alpha)
+        else:
+            raise NotImplementedError
+
+    def forward(self, x):
+        base = self.hfs(x) if self.hfs is not None else x
+        return edge_enhance(x, base, self.canny, self.w, self.low, self.high, True)
+
+
+# ---------------------------------------------------------------------------------------------
+# adjacent modules that stay on torch ops (SURVEY.md section 8f "next" rows)
+# ---------------------------------------------------------------------------------------------
+class HighFreqSuppress(torch.nn.Module):
+    """utils/core.py:15-55: square low-pass in the 2-D Fourier domain.  The reference calls
+    torch.rfft / torch.irfft (removed in torch 1.8) and hard-codes .cuda(); this is the
+    torch.fft restatement (onesided=False forward, C2R inverse that reads the one-sided half),
+    following the input's device.  cuFFT stays the engine; parity for this module is UNPINNED
+    (the reference version cannot run on any torch that supports sm_100)."""
+
+    def __init__(self, w, h, r):
+        super(HighFreqSuppress, self).__init__()
+        self.w = w
+        self.h = h
+        self.r = r
+        self.templete()
+
+    def templete(self):
+        temp = np.zeros((self.w, self.h), "float32")
+        cw = self.w // 2
+        ch = self.h // 2
+        dw = self.r if self.w % 2 == 0 else self.r + 1
+        dh = self.r if self.h % 2 == 0 else self.r + 1
+        temp[cw - self.r:cw + dw, ch - self.r:ch + dh] = 1.0
+        temp = np.roll(temp, -cw, axis=0)
+        temp = np.roll(temp, -ch, axis=1)
+        temp = torch.tensor(temp)
+        temp = temp.unsqueeze(0).unsqueeze(0).unsqueeze(-1)
+        self.temp = temp                     # [1,1,w,h,1] like the reference
+        self._mask_cache = {}
+
+    def _mask(self, device):
+        m = self._mask_cache.get(device)
+        if m is None:
+            half = self.h // 2 + 1
+            m = self.temp[..., 0][..., :half].to(device)
+            self._mask_cache[device] = m
+        return m
+
+    def forward(self, x):
+        half = x.shape[-1] // 2 + 1
+        x_hat = torch.fft.fft2(x)[..., :half]
+        x_hat = x_hat * self._mask(x.device)
+        return torch.fft.irfft2(x_hat, s=x.shape[-2:])
+
+    def extra_repr(self):
+        return 'feature_width={}, feature_height={}, radius={}'.format(self.w, self.h, self.r)
+
+
+class Add_Square(nn.Module):
+    """utils/core.py:589-655 (random square perturbation of the *_square models); torch pass-through
+    that follows the input's device instead of the reference's hard .cuda()."""
+
+    def __init__(self, channels=3, size=224, epsilon=0.05, p_init=0.8, n_queries=5000, rescale_schedule=False):
+        super(Add_Square, self).__init__()
+        self.c = channels
+        self.h = size
+        self.eps = epsilon
+        self.p_init = p_init
+        self.n_queries = n_queries
+        self.rescale_schedule = rescale_schedule
+        self._dev = None
+
+    def random_choice(self, shape):
+        t = 2 * torch.rand(shape).to(self._dev) - 1
+        return torch.sign(t)
+
+    def random_int(self, low=0, high=1, shape=[1]):
+        t = low + (high - low) * torch.rand(shape).to(self._dev)
+        return t.long()
+
+    def p_selection(self, it):
+        if self.rescale_schedule:
+            it = int(it / self.n_queries * 10000)
+        for bound, div in ((10, 1), (50, 2), (200, 4), (500, 8), (1000, 16), (2000, 32), (4000, 64),
+                           (6000, 128), (8000, 256)):
+            if it <= bound:
+                return self.p_init / div
+        return self.p_init / 512
+
+    def forward(self, x):
+        self._dev = x.device
+        x_best = torch.clamp(x + self.eps * self.random_choice([x.shape[0], self.c, 1, self.h]), 0., 1.)
+        n_features = self.c * self.h * self.h
+        for i_iter in range(self.n_queries):
+            p = self.p_selection(i_iter)
+            s = max(int(round(math.sqrt(p * n_features / self.c))), 1)
+            vh = self.random_int(0, self.h - s)
+            new_deltas = torch.zeros([self.c, self.h, self.h], device=x.device)
+            new_deltas[:, vh:vh + s, vh:vh + s] = 2. * self.eps * self.random_choice([self.c, 1, 1])
+            x_best = x_best + new_deltas
+            x_best = torch.min(torch.max(x_best, x - self.eps), x + self.eps)
+            x_best = torch.clamp(x_best, 0., 1.)
+        return x_best

@@ -1,0 +1,292 @@
+// ee_capi.cu -- the C ABI of libedge_b200.so (include/edge_b200.h): argument validation, launch
+// configuration and error reporting.  No torch types, no allocation, no host synchronisation.
+#include "../../include/edge_b200.h"
+#include "ee_attack.cuh"
+#include "ee_edge_canny.cuh"
+#include "ee_edge_step125.cuh"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<int> g_th_fwd{0}, g_th_bwd{0}, g_staging{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+}
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+constexpr int kMaxSmem = 227 * 1024;
+constexpr int kThreads = 256;
+
+// Validate EEParams and extract the three Gaussian taps.
+int check_params(const EEParams* p, float& c0, float& c1, float& c2) {
+    if (!p) return fail(EE_ERR_INVALID_ARG, "EEParams is null");
+    if (p->variant < EE_VARIANT_STEP125 || p->variant > EE_VARIANT_BPDA)
+        return fail(EE_ERR_INVALID_ARG, "unknown variant %d", p->variant);
+    if (p->layout != EE_LAYOUT_NCHW) return fail(EE_ERR_UNSUPPORTED, "only dense NCHW is supported");
+    if (p->reserved != 0) return fail(EE_ERR_INVALID_ARG, "EEParams.reserved must be 0");
+    const float* g = p->gauss;
+    if (!(g[0] == g[2] && g[0] == g[6] && g[0] == g[8] && g[1] == g[3] && g[1] == g[5] && g[1] == g[7]))
+        return fail(EE_ERR_UNSUPPORTED, "gauss[9] lacks the corner/edge/centre symmetry of get_gaussian_kernel(3,..)");
+    static const float kSobel[9] = {-0.5f, 0.f, 0.5f, -1.f, 0.f, 1.f, -0.5f, 0.f, 0.5f};
+    for (int i = 0; i < 9; ++i)
+        if (p->sobel[i] != kSobel[i]) return fail(EE_ERR_UNSUPPORTED, "sobel[9] must equal get_sobel_kernel(3)");
+    if (p->variant == EE_VARIANT_STEP125 && !p->has_high)
+        return fail(EE_ERR_INVALID_ARG, "CannyFilter_step125_1 needs high_threshold (reference raises UnboundLocalError, core.py:578-583)");
+    c0 = g[0]; c1 = g[1]; c2 = g[4];
+    return EE_OK;
+}
+
+struct Launch { int vec, threads, GX, RY, TH, tiles; size_t smem; };
+
+// rows_fixed / rows_per_th: the kernel needs (rows_per_th*TH + rows_fixed) plane rows of W floats.
+int plan(int H, int W, bool vec_ok, int rows_per_th, int rows_fixed, int max_halo_rows, int budget_bytes,
+         int forced_th, Launch& L) {
+    L.vec = vec_ok ? 4 : 1;
+    const int G = (W + L.vec - 1) / L.vec;
+    const size_t row_bytes = (size_t)W * sizeof(float);
+    auto smem_of = [&](int th) { return (size_t)(rows_per_th * th + rows_fixed) * row_bytes; };
+    int th;
+    if (forced_th > 0) {
+        th = forced_th < H ? forced_th : H;
+    } else {
+        long fit = ((long)(budget_bytes / row_bytes) - rows_fixed) / rows_per_th;
+        th = (int)(fit < 1 ? 1 : (fit > H ? H : fit));
+        const int tiles = (H + th - 1) / th;
+        th = (H + tiles - 1) / tiles;   // equalise the strips
+    }
+    while (th > 1 && smem_of(th) > (size_t)kMaxSmem) --th;
+    if (smem_of(th) > (size_t)kMaxSmem)
+        return fail(EE_ERR_TOO_LARGE, "one row strip of width %d needs %zu B of shared memory (> %d)", W, smem_of(th), kMaxSmem);
+    L.TH = th;
+    L.tiles = (H + th - 1) / th;
+    L.smem = smem_of(th);
+    if (G >= kThreads) { L.GX = kThreads; L.RY = 1; }
+    else {
+        L.GX = G;
+        int ry = kThreads / G;
+        const int max_rows = th + max_halo_rows;
+        if (ry > max_rows) ry = max_rows;
+        if (ry < 1) ry = 1;
+        L.RY = ry;
+    }
+    L.threads = ((L.GX * L.RY + 31) / 32) * 32;
+    return EE_OK;
+}
+
+template <typename K>
+int launch(K kernel, const Launch& L, int B, const ee::EdgeArgs& a, cudaStream_t s, const char* name) {
+    if (L.smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+    }
+    const long long grid = (long long)B * L.tiles;
+    if (grid > 0x7fffffffLL) return fail(EE_ERR_TOO_LARGE, "too many tiles");
+    kernel<<<(unsigned)grid, L.threads, L.smem, s>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, name);
+    return EE_OK;
+}
+
+int fill_args(ee::EdgeArgs& a, int B, int C, int H, int W, const EEParams* p, float w) {
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return fail(EE_ERR_INVALID_ARG, "non-positive shape %dx%dx%dx%d", B, C, H, W);
+    float c0, c1, c2;
+    int rc = check_params(p, c0, c1, c2);
+    if (rc) return rc;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.C = C; a.H = H; a.W = W;
+    a.c0 = c0; a.c1 = c1; a.c2 = c2; a.fC = (float)C;
+    a.alpha = p->alpha; a.low = p->low_thr; a.high = p->high_thr; a.w = w;
+    a.variant = p->variant; a.has_low = p->has_low != 0; a.has_high = p->has_high != 0; a.hyst = p->hysteresis != 0;
+    return EE_OK;
+}
+
+#define EE_DISPATCH(KERNEL, BLEND, L, B, a, s, name)                                              \
+    do {                                                                                          \
+        if ((L).vec == 4) {                                                                       \
+            if ((a).C == 3) return launch(KERNEL<4, 3, BLEND>, L, B, a, s, name);                 \
+            if ((a).C == 1) return launch(KERNEL<4, 1, BLEND>, L, B, a, s, name);                 \
+            return launch(KERNEL<4, 0, BLEND>, L, B, a, s, name);                                 \
+        }                                                                                         \
+        if ((a).C == 3) return launch(KERNEL<1, 3, BLEND>, L, B, a, s, name);                     \
+        if ((a).C == 1) return launch(KERNEL<1, 1, BLEND>, L, B, a, s, name);                     \
+        return launch(KERNEL<1, 0, BLEND>, L, B, a, s, name);                                     \
+    } while (0)
+
+int edge_forward(const float* x, const float* base, float* out, float* edge, int B, int C, int H, int W,
+                 const EEParams* p, float w, bool blend, void* stream) {
+    ee::EdgeArgs a;
+    int rc = fill_args(a, B, C, H, W, p, w);
+    if (rc) return rc;
+    if (!x) return fail(EE_ERR_INVALID_ARG, "x is null");
+    if (blend && (!base || !out)) return fail(EE_ERR_INVALID_ARG, "base/out is null");
+    if (!blend && !edge) return fail(EE_ERR_INVALID_ARG, "edge is null");
+    a.x = x; a.base = base; a.out = out; a.edge = edge;
+    const bool vec_ok = (W % 4 == 0) && aligned16(x) && aligned16(base) && aligned16(out) && aligned16(edge);
+    cudaStream_t s = (cudaStream_t)stream;
+    Launch L;
+    if (p->variant == EE_VARIANT_STEP125) {
+        rc = plan(H, W, vec_ok, 2, 6, 4, 44 * 1024, g_th_fwd.load(), L);
+        if (rc) return rc;
+        a.TH = L.TH; a.tiles_per_img = L.tiles; a.GX = L.GX; a.RY = L.RY;
+        if (blend) EE_DISPATCH(ee::edge_fwd_step125_kernel, true, L, B, a, s, "edge_fwd_step125");
+        else EE_DISPATCH(ee::edge_fwd_step125_kernel, false, L, B, a, s, "edge_fwd_step125");
+    }
+    rc = plan(H, W, vec_ok, ee::kCannyFwdRowsPerTH, ee::kCannyFwdRowsFixed, 8, 64 * 1024, g_th_fwd.load(), L);
+    if (rc) return rc;
+    a.TH = L.TH; a.tiles_per_img = L.tiles; a.GX = L.GX; a.RY = L.RY;
+    if (blend) EE_DISPATCH(ee::edge_fwd_canny_kernel, true, L, B, a, s, "edge_fwd_canny");
+    else EE_DISPATCH(ee::edge_fwd_canny_kernel, false, L, B, a, s, "edge_fwd_canny");
+}
+
+int edge_backward(const float* g_in, const float* x, const float* base, float* g_x, float* g_base, int B, int C,
+                  int H, int W, const EEParams* p, float w, bool blend, void* stream) {
+    ee::EdgeArgs a;
+    int rc = fill_args(a, B, C, H, W, p, w);
+    if (rc) return rc;
+    if (!x || !g_in) return fail(EE_ERR_INVALID_ARG, "x/g is null");
+    if (blend && !base) return fail(EE_ERR_INVALID_ARG, "base is null");
+    if (!blend && !g_x) return fail(EE_ERR_INVALID_ARG, "g_x is null");
+    if (blend && !g_x && !g_base) return EE_OK;   // nothing requested
+    a.x = x; a.base = base; a.g_in = g_in; a.g_x = g_x; a.g_base = g_base;
+    const bool vec_ok = (W % 4 == 0) && aligned16(x) && aligned16(base) && aligned16(g_in) && aligned16(g_x) && aligned16(g_base);
+    cudaStream_t s = (cudaStream_t)stream;
+    Launch L;
+    if (p->variant == EE_VARIANT_STEP125) {
+        rc = plan(H, W, vec_ok, 3, 18, 8, 56 * 1024, g_th_bwd.load(), L);
+        if (rc) return rc;
+        a.TH = L.TH; a.tiles_per_img = L.tiles; a.GX = L.GX; a.RY = L.RY;
+        if (blend) EE_DISPATCH(ee::edge_bwd_step125_kernel, true, L, B, a, s, "edge_bwd_step125");
+        else EE_DISPATCH(ee::edge_bwd_step125_kernel, false, L, B, a, s, "edge_bwd_step125");
+    }
+    rc = plan(H, W, vec_ok, ee::kCannyBwdRowsPerTH, ee::kCannyBwdRowsFixed, 12, 80 * 1024, g_th_bwd.load(), L);
+    if (rc) return rc;
+    a.TH = L.TH; a.tiles_per_img = L.tiles; a.GX = L.GX; a.RY = L.RY;
+    if (blend) EE_DISPATCH(ee::edge_bwd_canny_kernel, true, L, B, a, s, "edge_bwd_canny");
+    else EE_DISPATCH(ee::edge_bwd_canny_kernel, false, L, B, a, s, "edge_bwd_canny");
+}
+
+// ---- elementwise launcher ----------------------------------------------------------------
+template <int NIN, typename F>
+int launch_ew(const float* i0, const float* i1, const float* i2, const float* i3, const float* i4, float* out,
+              int64_t n, F f, void* stream, const char* name) {
+    if (n < 0) return fail(EE_ERR_INVALID_ARG, "negative element count");
+    if (n == 0) return EE_OK;
+    const float* in[5] = {i0, i1, i2, i3, i4};
+    int vec_ok = aligned16(out);
+    for (int q = 0; q < NIN; ++q) {
+        if (!in[q]) return fail(EE_ERR_INVALID_ARG, "%s: input %d is null", name, q);
+        vec_ok = vec_ok && aligned16(in[q]);
+    }
+    if (!out) return fail(EE_ERR_INVALID_ARG, "%s: out is null", name);
+    const int64_t work = vec_ok ? ((n >> 2) + 1023) / 1024 : (n + 255) / 256;
+    int64_t grid = work < 1 ? 1 : work;
+    if (grid > 148 * 64) grid = 148 * 64;     // grid-stride beyond that
+    ee::ew_kernel<NIN, F><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(i0, i1, i2, i3, i4, out, n, vec_ok, f);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, name);
+    return EE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ee_edge_fwd_f32(const float* x, float* edge, int B, int C, int H, int W, const EEParams* p, void* stream) {
+    return edge_forward(x, nullptr, nullptr, edge, B, C, H, W, p, 0.0f, false, stream);
+}
+int ee_edge_blend_fwd_f32(const float* x, const float* base, float* out, float* edge_or_null, int B, int C, int H,
+                          int W, const EEParams* p, float w, void* stream) {
+    return edge_forward(x, base, out, edge_or_null, B, C, H, W, p, w, true, stream);
+}
+int ee_edge_bwd_f32(const float* g_edge, const float* x, float* g_x, int B, int C, int H, int W, const EEParams* p,
+                    void* stream) {
+    return edge_backward(g_edge, x, nullptr, g_x, nullptr, B, C, H, W, p, 0.0f, false, stream);
+}
+int ee_edge_blend_bwd_f32(const float* g_out, const float* x, const float* base, float* g_x_or_null,
+                          float* g_base_or_null, int B, int C, int H, int W, const EEParams* p, float w, void* stream) {
+    return edge_backward(g_out, x, base, g_x_or_null, g_base_or_null, B, C, H, W, p, w, true, stream);
+}
+size_t ee_aux_bytes(int, int, int, int, int) { return 0; }
+
+int ee_pgd_linf_step_f32(const float* x, const float* g, const float* x0, float* out, int64_t n, float alpha_signed,
+                         float eps, float lo, float hi, void* stream) {
+    return launch_ew<3>(x, g, x0, nullptr, nullptr, out, n, ee::FPgdLinf{alpha_signed, eps, lo, hi}, stream, "ee_pgd_linf_step_f32");
+}
+int ee_fgsm_step_f32(const float* x, const float* g, float* out, int64_t n, float alpha_signed, float lo, float hi,
+                     void* stream) {
+    return launch_ew<2>(x, g, nullptr, nullptr, nullptr, out, n, ee::FFgsm{alpha_signed, lo, hi}, stream, "ee_fgsm_step_f32");
+}
+int ee_cw_linf_step_f32(const float* adv, const float* g, const float* x, const float* min_x, const float* max_x,
+                        float* out, int64_t n, float step, float magnitude, void* stream) {
+    return launch_ew<5>(adv, g, x, min_x, max_x, out, n, ee::FCwLinf{step, magnitude}, stream, "ee_cw_linf_step_f32");
+}
+int ee_free_at_step_f32(float* delta, const float* g, const float* x0, float* x_adv, int64_t n, float alpha, float eps,
+                        float lo, float hi, void* stream) {
+    if (n < 0) return fail(EE_ERR_INVALID_ARG, "negative element count");
+    if (n == 0) return EE_OK;
+    if (!delta || !g || (x_adv && !x0)) return fail(EE_ERR_INVALID_ARG, "ee_free_at_step_f32: null pointer");
+    const int vec_ok = aligned16(delta) && aligned16(g) && aligned16(x0) && aligned16(x_adv);
+    const int64_t work = vec_ok ? ((n >> 2) + 1023) / 1024 : (n + 255) / 256;
+    int64_t grid = work < 1 ? 1 : work;
+    if (grid > 148 * 64) grid = 148 * 64;
+    ee::free_at_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(delta, g, x0, x_adv, n, vec_ok, alpha, eps, lo, hi);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ee_free_at_step_f32");
+    return EE_OK;
+}
+int ee_pgd_l2_step_f32(const float* x, const float* g, const float* x0, float* out, int B, int64_t n_per, float step,
+                       float eps, void* stream) {
+    if (B < 0 || n_per < 0) return fail(EE_ERR_INVALID_ARG, "negative size");
+    if (B == 0 || n_per == 0) return EE_OK;
+    if (!x || !g || !x0 || !out) return fail(EE_ERR_INVALID_ARG, "ee_pgd_l2_step_f32: null pointer");
+    if (out == x) return fail(EE_ERR_INVALID_ARG, "ee_pgd_l2_step_f32: out must not alias x");
+    ee::pgd_l2_kernel<<<(unsigned)B, 1024, 0, (cudaStream_t)stream>>>(x, g, x0, out, n_per, step, eps);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ee_pgd_l2_step_f32");
+    return EE_OK;
+}
+
+int ee_to_compare_fwd_f32(const float* in, float* out, int64_t n, float thr, void* stream) {
+    return launch_ew<1>(in, nullptr, nullptr, nullptr, nullptr, out, n, ee::FToCompareFwd{thr}, stream, "ee_to_compare_fwd_f32");
+}
+int ee_to_compare_bwd_f32(const float* g, const float* in, float* out, int64_t n, float thr, void* stream) {
+    return launch_ew<2>(g, in, nullptr, nullptr, nullptr, out, n, ee::FToCompareBwd{thr}, stream, "ee_to_compare_bwd_f32");
+}
+int ee_to_eq_fwd_f32(const float* in, float* out, int64_t n, void* stream) {
+    return launch_ew<1>(in, nullptr, nullptr, nullptr, nullptr, out, n, ee::FToEqFwd{}, stream, "ee_to_eq_fwd_f32");
+}
+int ee_to_eq_bwd_f32(const float* g, const float* in, float* out, int64_t n, void* stream) {
+    return launch_ew<2>(g, in, nullptr, nullptr, nullptr, out, n, ee::FToEqBwd{}, stream, "ee_to_eq_bwd_f32");
+}
+int ee_safe_sign_fwd_f32(const float* in, float* out, int64_t n, void* stream) {
+    return launch_ew<1>(in, nullptr, nullptr, nullptr, nullptr, out, n, ee::FSafeSignFwd{}, stream, "ee_safe_sign_fwd_f32");
+}
+int ee_safe_sign_bwd_f32(const float* g, const float* in, float* out, int64_t n, void* stream) {
+    return launch_ew<2>(g, in, nullptr, nullptr, nullptr, out, n, ee::FSafeSignBwd{}, stream, "ee_safe_sign_bwd_f32");
+}
+
+const char* ee_last_error(void) { return g_err; }
+int ee_version(void) { return EE_VERSION; }
+int ee_set_tuning(int strip_rows_fwd, int strip_rows_bwd, int staging) {
+    g_th_fwd.store(strip_rows_fwd < 0 ? 0 : strip_rows_fwd);
+    g_th_bwd.store(strip_rows_bwd < 0 ? 0 : strip_rows_bwd);
+    g_staging.store(staging);
+    return EE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,316 @@
+"""Torch-facing wrappers over the C ABI: raw ops and the autograd.Functions.
+
+PyTorch is plumbing here (device memory, current stream, autograd bookkeeping); all arithmetic of
+the hot path happens in libedge_b200.so.  Everything is CUDA-only and fp32-only: CPU tensors or
+other dtypes raise -- there is no fallback path.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import EEParams, EE_VARIANT_BPDA, EE_VARIANT_CANNY, EE_VARIANT_STEP125
+
+VARIANTS = {"step125": EE_VARIANT_STEP125, "canny": EE_VARIANT_CANNY, "bpda": EE_VARIANT_BPDA}
+
+_SOBEL_X = np.array([[-0.5, 0.0, 0.5], [-1.0, 0.0, 1.0], [-0.5, 0.0, 0.5]], dtype=np.float32)
+
+
+def make_params(variant, gauss, alpha=0.0, low=None, high=None, hysteresis=False, sobel=None):
+    """Build an EEParams from module state (3x3 fp32 kernels) + forward() arguments."""
+    p = EEParams()
+    p.variant = VARIANTS[variant] if isinstance(variant, str) else int(variant)
+    p.layout = _lib.EE_LAYOUT_NCHW
+    g = np.asarray(gauss, dtype=np.float32).reshape(-1)
+    s = (_SOBEL_X if sobel is None else np.asarray(sobel, dtype=np.float32)).reshape(-1)
+    if g.size != 9 or s.size != 9:
+        raise NotImplementedError("edge_b200 implements the 3x3 Gaussian / 3x3 Sobel of every reference config "
+                                  "(k_gaussian=3, k_sobel=3); got %d / %d taps" % (g.size, s.size))
+    for i in range(9):
+        p.gauss[i] = float(g[i])
+        p.sobel[i] = float(s[i])
+    p.alpha = float(alpha)
+    p.low_thr = 0.0 if low is None else float(low)
+    p.high_thr = 0.0 if high is None else float(high)
+    p.has_low = int(low is not None)
+    p.has_high = int(high is not None)
+    p.hysteresis = int(bool(hysteresis))
+    p.reserved = 0
+    return p
+
+
+def _chk(t, name, shape=None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("edge_b200: %s is on %s; the B200 kernels are CUDA-only and there is no CPU fallback"
+                           % (name, t.device))
+    if t.dtype != torch.float32:
+        raise TypeError("edge_b200: %s must be float32 (got %s)" % (name, t.dtype))
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError("edge_b200: %s has shape %s, expected %s" % (name, tuple(t.shape), tuple(shape)))
+    return t.contiguous()
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+# --------------------------------------------------------------------------------------------
+# raw ops (no autograd)
+# --------------------------------------------------------------------------------------------
+def edge_map(x, params):
+    """edge[B,1,H,W] = filter(x[B,C,H,W]) -- ee_edge_fwd_f32."""
+    x = _chk(x, "img")
+    if x.dim() != 4:
+        raise ValueError("img must be [B,C,H,W]")
+    B, C, H, W = x.shape
+    edge = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+    if x.numel() == 0:
+        return edge
+    with torch.cuda.device(x.device):
+        rc = _lib.load().ee_edge_fwd_f32(_ptr(x), _ptr(edge), B, C, H, W, ctypes.byref(params), _stream(x))
+    _lib.check(rc, "ee_edge_fwd_f32")
+    return edge
+
+
+def edge_map_backward(g_edge, x, params):
+    x = _chk(x, "img")
+    B, C, H, W = x.shape
+    g_edge = _chk(g_edge, "grad_edge", (B, 1, H, W))
+    g_x = torch.empty_like(x)
+    if x.numel() == 0:
+        return g_x
+    with torch.cuda.device(x.device):
+        rc = _lib.load().ee_edge_bwd_f32(_ptr(g_edge), _ptr(x), _ptr(g_x), B, C, H, W, ctypes.byref(params), _stream(x))
+    _lib.check(rc, "ee_edge_bwd_f32")
+    return g_x
+
+
+def edge_blend(x, base, params, w, want_edge=False):
+    """out = clamp(base + w*filter(x), 0, 1) in one pass -- ee_edge_blend_fwd_f32."""
+    x = _chk(x, "img")
+    if x.dim() != 4:
+        raise ValueError("img must be [B,C,H,W]")
+    B, C, H, W = x.shape
+    base = _chk(base, "base", x.shape)
+    out = torch.empty_like(x)
+    edge = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device) if want_edge else None
+    if x.numel():
+        with torch.cuda.device(x.device):
+            rc = _lib.load().ee_edge_blend_fwd_f32(_ptr(x), _ptr(base), _ptr(out), _ptr(edge), B, C, H, W,
+                                                   ctypes.byref(params), float(w), _stream(x))
+        _lib.check(rc, "ee_edge_blend_fwd_f32")
+    return (out, edge) if want_edge else out
+
+
+def edge_blend_backward(g_out, x, base, params, w, need_x=True, need_base=True):
+    x = _chk(x, "img")
+    B, C, H, W = x.shape
+    base = _chk(base, "base", x.shape)
+    g_out = _chk(g_out, "grad_out", x.shape)
+    g_x = torch.empty_like(x) if need_x else None
+    g_base = torch.empty_like(x) if need_base else None
+    if x.numel() and (need_x or need_base):
+        with torch.cuda.device(x.device):
+            rc = _lib.load().ee_edge_blend_bwd_f32(_ptr(g_out), _ptr(x), _ptr(base), _ptr(g_x), _ptr(g_base),
+                                                   B, C, H, W, ctypes.byref(params), float(w), _stream(x))
+        _lib.check(rc, "ee_edge_blend_bwd_f32")
+    return g_x, g_base
+
+
+def _same(*ts):
+    ref = ts[0]
+    out = []
+    for i, t in enumerate(ts):
+        t = _chk(t, "operand %d" % i)
+        if t.shape != ref.shape or t.device != ref.device:
+            raise ValueError("edge_b200: operand %d has shape/device %s/%s, expected %s/%s"
+                             % (i, tuple(t.shape), t.device, tuple(ref.shape), ref.device))
+        out.append(t)
+    return out
+
+
+def _out_like(x, out):
+    if out is None:
+        return torch.empty_like(x)
+    if not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.shape == x.shape):
+        raise ValueError("edge_b200: `out` must be a contiguous float32 CUDA tensor shaped like the input")
+    return out
+
+
+def pgd_linf_step(x, grad, x0, alpha_signed, eps, lo=0.0, hi=1.0, out=None):
+    """clamp(min(max(x + alpha_signed*sign(grad), x0-eps), x0+eps), lo, hi); `out` may be x."""
+    x, grad, x0 = _same(x, grad, x0)
+    out = _out_like(x, out)
+    if x.numel():
+        with torch.cuda.device(x.device):
+            rc = _lib.load().ee_pgd_linf_step_f32(_ptr(x), _ptr(grad), _ptr(x0), _ptr(out), x.numel(),
+                                                  float(alpha_signed), float(eps), float(lo), float(hi), _stream(x))
+        _lib.check(rc, "ee_pgd_linf_step_f32")
+    return out
+
+
+def fgsm_step(x, grad, alpha_signed, lo=0.0, hi=1.0, out=None):
+    x, grad = _same(x, grad)
+    out = _out_like(x, out)
+    if x.numel():
+        with torch.cuda.device(x.device):
+            rc = _lib.load().ee_fgsm_step_f32(_ptr(x), _ptr(grad), _ptr(out), x.numel(), float(alpha_signed),
+                                              float(lo), float(hi), _stream(x))
+        _lib.check(rc, "ee_fgsm_step_f32")
+    return out
+
+
+def free_at_step_(delta, grad, x0=None, alpha=0.0, eps=0.0, lo=0.0, hi=1.0, want_adv=True):
+    """In place: delta = clamp(delta + alpha*sign(grad), -eps, eps); returns x_adv = clamp(x0 + delta, lo, hi)
+    (or None when want_adv is False).  `delta` must be contiguous (it is updated in place)."""
+    if not (isinstance(delta, torch.Tensor) and delta.is_cuda and delta.dtype == torch.float32 and delta.is_contiguous()):
+        raise ValueError("edge_b200: delta must be a contiguous float32 CUDA tensor (updated in place)")
+    grad = _chk(grad, "grad", delta.shape)
+    x_adv = None
+    if want_adv:
+        x0 = _chk(x0, "x0", delta.shape)
+        x_adv = torch.empty_like(delta)
+    if delta.numel():
+        with torch.cuda.device(delta.device):
+            rc = _lib.load().ee_free_at_step_f32(_ptr(delta), _ptr(grad), _ptr(x0 if want_adv else None), _ptr(x_adv),
+                                                 delta.numel(), float(alpha), float(eps), float(lo), float(hi),
+                                                 _stream(delta))
+        _lib.check(rc, "ee_free_at_step_f32")
+    return x_adv
+
+
+def cw_linf_step(adv, grad, x, min_x, max_x, step, magnitude, out=None):
+    adv, grad, x, min_x, max_x = _same(adv, grad, x, min_x, max_x)
+    out = _out_like(adv, out)
+    if adv.numel():
+        with torch.cuda.device(adv.device):
+            rc = _lib.load().ee_cw_linf_step_f32(_ptr(adv), _ptr(grad), _ptr(x), _ptr(min_x), _ptr(max_x), _ptr(out),
+                                                 adv.numel(), float(step), float(magnitude), _stream(adv))
+        _lib.check(rc, "ee_cw_linf_step_f32")
+    return out
+
+
+def pgd_l2_step(x, grad, x0, step, eps):
+    """TRADES PGD-L2 update with per-sample RMS norms (first dim = batch)."""
+    x, grad, x0 = _same(x, grad, x0)
+    out = torch.empty_like(x)
+    if x.numel():
+        B = x.shape[0]
+        with torch.cuda.device(x.device):
+            rc = _lib.load().ee_pgd_l2_step_f32(_ptr(x), _ptr(grad), _ptr(x0), _ptr(out), B, x.numel() // B,
+                                                float(step), float(eps), _stream(x))
+        _lib.check(rc, "ee_pgd_l2_step_f32")
+    return out
+
+
+def _ew(name, args, n, ref, thr=None):
+    out = torch.empty_like(ref)
+    if n:
+        call = [_ptr(a) for a in args] + [_ptr(out), n]
+        if thr is not None:
+            call.append(float(thr))
+        call.append(_stream(ref))
+        with torch.cuda.device(ref.device):
+            rc = getattr(_lib.load(), name)(*call)
+        _lib.check(rc, name)
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# autograd Functions
+# --------------------------------------------------------------------------------------------
+class EdgeMapFn(torch.autograd.Function):
+    """edge = CannyFilter*(img); backward recomputes the forward intermediates from img."""
+
+    @staticmethod
+    def forward(ctx, img, params):
+        ctx.params = params
+        ctx.save_for_backward(img)
+        return edge_map(img, params)
+
+    @staticmethod
+    def backward(ctx, g_edge):
+        (img,) = ctx.saved_tensors
+        g = edge_map_backward(g_edge, img, ctx.params) if ctx.needs_input_grad[0] else None
+        return g, None
+
+
+class EdgeEnhanceFn(torch.autograd.Function):
+    """out = clamp(base + w * CannyFilter*(img), 0, 1), one HBM pass per direction."""
+
+    @staticmethod
+    def forward(ctx, img, base, params, w):
+        ctx.params = params
+        ctx.w = float(w)
+        ctx.save_for_backward(img, base)
+        return edge_blend(img, base, params, w)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        img, base = ctx.saved_tensors
+        need_x, need_base = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g_x, g_base = edge_blend_backward(g_out, img, base, ctx.params, ctx.w, need_x, need_base)
+        return g_x, g_base, None, None
+
+
+class ToCompareFn(torch.autograd.Function):
+    """utils/core.py:329-358."""
+
+    @staticmethod
+    def forward(ctx, input, threshold):
+        thr = float(threshold)
+        ctx.thr = thr
+        x = _chk(input, "input")
+        ctx.save_for_backward(x)
+        return _ew("ee_to_compare_fwd_f32", [x], x.numel(), x, thr)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = _chk(g, "grad", x.shape)
+        return _ew("ee_to_compare_bwd_f32", [g, x], x.numel(), x, ctx.thr), None
+
+
+class ToEqFn(torch.autograd.Function):
+    """utils/core.py:361-382."""
+
+    @staticmethod
+    def forward(ctx, input):
+        x = _chk(input, "input")
+        ctx.save_for_backward(x)
+        return _ew("ee_to_eq_fwd_f32", [x], x.numel(), x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = _chk(g, "grad", x.shape)
+        return _ew("ee_to_eq_bwd_f32", [g, x], x.numel(), x)
+
+
+class SafeSignFn(torch.autograd.Function):
+    """BinaryConnectDeterministic, utils/core.py:121-145."""
+
+    @staticmethod
+    def forward(ctx, input):
+        x = _chk(input, "input")
+        ctx.save_for_backward(x)
+        return _ew("ee_safe_sign_fwd_f32", [x], x.numel(), x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = _chk(g, "grad", x.shape)
+        return _ew("ee_safe_sign_bwd_f32", [g, x], x.numel(), x)
+
+
+def safe_sign(t):
+    """safeSign of utils/core.py:115-118 (no autograd)."""
+    x = _chk(t, "tensor")
+    return _ew("ee_safe_sign_fwd_f32", [x], x.numel(), x)

@@ -1,0 +1,148 @@
+/*
+ * edge_b200.h -- C ABI of libedge_b200.so: the B200 (sm_100a) implementation of the
+ * edge-enhancement transform and the PGD/FGSM inner-loop updates of Aiqz/Edge-Enhancement.
+ *
+ * This is the drop-in boundary.  The reference has no native code; what a maintainer binds
+ * instead of is a chain of PyTorch eager ops.  Each entry point names the reference lines it
+ * replaces (paths relative to the reference repo).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Contract (all entry points)
+ *   - plain pointers and sizes; no torch / C++ types; no exceptions cross the boundary;
+ *   - every pointer is a DEVICE pointer to fp32 data, dense NCHW (EE_LAYOUT_NCHW), owned by
+ *     the caller; the library never allocates, frees or retains device memory and keeps no
+ *     global device state, so every call is CUDA-graph capturable;
+ *   - work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*) of the
+ *     CURRENT device; no host synchronisation; re-entrant and thread-safe (DataParallel worker
+ *     threads, autograd engine threads);
+ *   - returns EE_OK (0) or a negative EE_ERR_* / positive cudaError_t; ee_last_error() gives a
+ *     thread-local message.  In-place use is allowed only where stated.
+ */
+#ifndef EDGE_B200_H_
+#define EDGE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EE_VERSION 100 /* 0.1.0 */
+
+enum {
+    EE_OK = 0,
+    EE_ERR_INVALID_ARG = -1, /* null pointer, non-positive size, bad enum             */
+    EE_ERR_UNSUPPORTED = -2, /* valid request this build does not implement            */
+    EE_ERR_TOO_LARGE = -3    /* a single image row strip does not fit in shared memory */
+};
+
+/* filter variants == the three reference modules */
+enum {
+    EE_VARIANT_STEP125 = 0, /* utils/core.py:509-585  CannyFilter_step125_1 */
+    EE_VARIANT_CANNY = 1,   /* utils/core.py:148-326  CannyFilter           */
+    EE_VARIANT_BPDA = 2     /* utils/core.py:386-505  CannyFilter_BPDA      */
+};
+
+enum { EE_LAYOUT_NCHW = 0 };
+
+/* Filter description, passed by value into kernel-parameter space (no device constants).
+ * Mirrors the module state + forward() arguments of the reference filters. */
+typedef struct EEParams {
+    int32_t variant;    /* EE_VARIANT_*                                                        */
+    int32_t layout;     /* EE_LAYOUT_NCHW                                                      */
+    float gauss[9];     /* weight_gaussian, row major (core.py:163-165).  Must have the         */
+                        /* corner/edge/centre symmetry every get_gaussian_kernel(3,mu,sigma) has */
+    float sobel[9];     /* weight_sobel_x, row major (core.py:175-178); must equal              */
+                        /* get_sobel_kernel(3); sobel_y is its transpose (core.py:180)          */
+    float alpha;        /* magnitude gate (core.py:264, :575); ignored by BPDA                  */
+    float low_thr;      /* forward(low_threshold=...), already /255 (resnet_EE.py:127)          */
+    float high_thr;     /* forward(high_threshold=...)                                          */
+    int32_t has_low;    /* low_threshold is not None                                            */
+    int32_t has_high;   /* high_threshold is not None (STEP125 requires it, core.py:578-583)    */
+    int32_t hysteresis; /* forward(hysteresis=...); ignored by STEP125                          */
+    int32_t reserved;   /* must be 0                                                            */
+} EEParams;
+
+/* ---- edge filter: module-level drop-in -------------------------------------------------- */
+
+/* edge[B,1,H,W] = CannyFilter*.forward(x[B,C,H,W], low, high, hysteresis)
+ * replaces utils/core.py:222-326, :426-505, :549-585. */
+int ee_edge_fwd_f32(const float* x, float* edge, int B, int C, int H, int W,
+                    const EEParams* p, void* stream);
+
+/* g_x[B,C,H,W] = d(edge)/d(x)^T g_edge[B,1,H,W]; replaces autograd through the above incl.
+ * To_compare/To_eq/BinaryConnectDeterministic.backward (core.py:138-145, :350-358, :375-382).
+ * Forward intermediates are recomputed from x (no saved tensors).  Sub-gradient of
+ * sqrt at 0 is 0 (the reference produces NaN there). */
+int ee_edge_bwd_f32(const float* g_edge, const float* x, float* g_x, int B, int C, int H, int W,
+                    const EEParams* p, void* stream);
+
+/* ---- edge filter fused with the blend: model-level drop-in ------------------------------- */
+
+/* out[B,C,H,W] = clamp(base + w * edge(x), 0, 1); optionally also writes edge[B,1,H,W].
+ * replaces core.py filter forward + e.g. Tiny_ImageNet/models_tinyimagenet/resnet_EE.py:182-191
+ * (gf=False).  One pass over HBM: reads x and base, writes out. */
+int ee_edge_blend_fwd_f32(const float* x, const float* base, float* out, float* edge_or_null,
+                          int B, int C, int H, int W, const EEParams* p, float w, void* stream);
+
+/* Adjoint of the above in one pass: reads g_out, x, base; writes
+ *   g_x    (edge path only; the caller's autograd adds HFS^T(g_base)), may be NULL
+ *   g_base = g_out * [0 <= base + w*edge <= 1],                        may be NULL */
+int ee_edge_blend_bwd_f32(const float* g_out, const float* x, const float* base, float* g_x_or_null,
+                          float* g_base_or_null, int B, int C, int H, int W, const EEParams* p,
+                          float w, void* stream);
+
+/* Workspace the edge entry points need from the caller: always 0 (recompute formulation). */
+size_t ee_aux_bytes(int B, int C, int H, int W, int variant);
+
+/* ---- attack inner-loop updates (elementwise, n = number of floats; out may alias x) ------ */
+
+/* out = clamp(min(max(x + alpha_signed*sign(g), x0-eps), x0+eps), lo, hi)
+ * replaces utils/attacks.py:25-27 and its copies :52-54 :82-84 :257-259 :298-300 :318-320
+ * :353-355 :414-416 :466-468 :505-507 (targeted ones pass alpha_signed = -step_size). */
+int ee_pgd_linf_step_f32(const float* x, const float* g, const float* x0, float* out, int64_t n,
+                         float alpha_signed, float eps, float lo, float hi, void* stream);
+
+/* out = clamp(x + alpha_signed*sign(g), lo, hi); replaces utils/attacks.py:121-126. */
+int ee_fgsm_step_f32(const float* x, const float* g, float* out, int64_t n, float alpha_signed,
+                     float lo, float hi, void* stream);
+
+/* delta = clamp(delta + alpha*sign(g), -eps, eps) in place; x_adv = clamp(x0 + delta, lo, hi)
+ * (x_adv may be NULL).  replaces ImageNet/free_imagenet/AT_hfs_canny_free_imagenet_ddp.py
+ * :330-332 + :314-315 and ImageNet/fgsm_imagenet/main_fast.py:233-235,:246-253. */
+int ee_free_at_step_f32(float* delta, const float* g, const float* x0, float* x_adv_or_null,
+                        int64_t n, float alpha, float eps, float lo, float hi, void* stream);
+
+/* CW L-inf inner update, replaces utils/attacks.py:213-222:
+ * t = adv + step*sign(g); t = max(min(t, x+magnitude), x-magnitude); t = clamp(t,0,1);
+ * out = max(min(t, max_x), min_x). */
+int ee_cw_linf_step_f32(const float* adv, const float* g, const float* x, const float* min_x,
+                        const float* max_x, float* out, int64_t n, float step, float magnitude,
+                        void* stream);
+
+/* TRADES PGD-L2 step with per-sample RMS norms, replaces utils/attacks.py:391-399 and
+ * l2_norm (:360-366).  One CTA per sample; out must NOT alias x. */
+int ee_pgd_l2_step_f32(const float* x, const float* g, const float* x0, float* out, int B,
+                       int64_t n_per_sample, float step, float eps, void* stream);
+
+/* ---- straight-through helper Functions (elementwise; out may alias g/in) ----------------- */
+int ee_to_compare_fwd_f32(const float* in, float* out, int64_t n, float thr, void* stream);                 /* core.py:338-347 */
+int ee_to_compare_bwd_f32(const float* g, const float* in, float* out, int64_t n, float thr, void* stream); /* core.py:350-358 */
+int ee_to_eq_fwd_f32(const float* in, float* out, int64_t n, void* stream);                                 /* core.py:364-372 */
+int ee_to_eq_bwd_f32(const float* g, const float* in, float* out, int64_t n, void* stream);                 /* core.py:375-382 */
+int ee_safe_sign_fwd_f32(const float* in, float* out, int64_t n, void* stream);                             /* core.py:115-118,:130-135 */
+int ee_safe_sign_bwd_f32(const float* g, const float* in, float* out, int64_t n, void* stream);             /* core.py:138-145 */
+
+/* ---- misc -------------------------------------------------------------------------------- */
+const char* ee_last_error(void); /* thread-local, never NULL */
+int ee_version(void);            /* EE_VERSION */
+
+/* Tuning knob for benchmarks/tests: force the row-strip height of the tiled edge kernels
+ * (0 = heuristic) and the staging path (0 = auto, 1 = vectorised LDG, 2 = TMA bulk copy).
+ * Process-wide; returns EE_OK.  Not needed for normal use. */
+int ee_set_tuning(int strip_rows_fwd, int strip_rows_bwd, int staging);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDGE_B200_H_ */
