@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py -- edge-enhanced PGD-10 hot-path throughput (images/s) on N B200s, with the HBM roofline
+of the dominant kernel and the CPU path timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # our CUDA path (default N=1)
+    python bench.py --impl reference ...                         # the CPU port of the reference path
+    torchrun --nproc-per-node N bench.py --gpus N ...            # one rank per GPU, batch sharded
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "C2"): Tiny-ImageNet edge-enhanced PGD-10,
+3x64x64 fp32, CannyFilter_step125_1 (high 76/255, w=1), eps 16/255, step 2/255
+(Tiny_ImageNet/configs_tinyimagenet/ee_at_bpda3_square.yml).  One STEP is the hot path of one
+PGD-10 adversarial-training iteration over the resident batch:
+    10 x [ edge+blend forward -> edge+blend backward -> PGD L-inf step ]  +  1 final forward
+i.e. 31 launches of our kernels.  The CNN forward/backward between them (cuDNN) and the FFT low-pass
+(cuFFT) are outside the product: `base` (x_hfs) and `g_out` (dL/d blended image) are resident
+synthetic tensors.  Per rank the step processes `--batch` images (default 16 Tiny batches of 256 =
+4096 images, 201 MB per tensor, so every launch streams from HBM rather than the 126 MB L2).
+
+Timing: W warm-up steps, then exactly K steps between barrier+synchronize, CUDA events on the
+launching stream, max over ranks.  `value` = images of all ranks / that time with inputs resident
+in HBM.  `e2e` = the same metric through the public Python API (attacks.PGD on a model whose front
+end is core.edge_enhance) with pinned HOST buffers: H2D of the batch and D2H of the adversarial
+examples inside the timed region.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# algorithmic bytes per pixel (C = 3, fp32), SURVEY.md section 8d / BASELINE.md section 2
+BYTES_FWD_PX = 36.0      # read x, base ; write out
+BYTES_BWD_PX = 60.0      # read g_out, x, base ; write g_x, g_base
+BYTES_PGD_ELT = 16.0     # read x, g, x0 ; write x'
+
+EPS, ALPHA, HIGH, LOW, W_BLEND = 16 / 255, 2 / 255, 76 / 255, 38 / 255, 1.0
+N_PGD = 10
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="images per rank per step")
+    ap.add_argument("--side", type=int, default=64)
+    ap.add_argument("--variant", default="step125", choices=["step125", "canny", "bpda"])
+    ap.add_argument("--cpu-images", type=int, default=2048, help="images in the bounded CPU sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--th-fwd", type=int, default=0)
+    ap.add_argument("--th-bwd", type=int, default=0)
+    ap.add_argument("--sweep", action="store_true", help="extra: kernel sweep table on stderr (configs[4])")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def shard_sizes(total, world):
+    """Contiguous batch shards, sizes differ by at most one (what DistributedSampler does)."""
+    base, rem = divmod(total, world)
+    return [base + (1 if r < rem else 0) for r in range(world)]
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampled DURING the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index, period=0.004):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._halt.wait(self.period)
+
+    def stop(self):
+        self._halt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU path (oracle port of the reference): the same PGD-10 hot path on a bounded sample
+# ---------------------------------------------------------------------------------------------
+def cpu_hot_path(images, side, variant, repeats=1):
+    """Returns (images/s, cores, seconds) of the oracle port running one PGD-10 hot-path step."""
+    from oracle import oracle as O
+    r = np.random.default_rng(1234)
+    shape = (images, 3, side, side)
+    x0 = r.random(shape, dtype=np.float32)
+    base = (r.random(shape, dtype=np.float32) * 1.1 - 0.1).astype(np.float32)
+    g_out = r.standard_normal(shape, dtype=np.float32)
+    p = O.make_params(variant, alpha=0.0, low=None if variant == "step125" else LOW, high=HIGH, hysteresis=True)
+    cores = os.cpu_count() or 1
+    best = None
+    for _ in range(repeats):
+        x = np.clip(x0 + (r.random(shape, dtype=np.float32) * 2 - 1) * np.float32(EPS), 0, 1).astype(np.float32)
+        t0 = time.perf_counter()
+        for _it in range(N_PGD):
+            O.edge_blend_fwd(x, base, p, W_BLEND)
+            g_x, _g_base = O.edge_blend_bwd(g_out, x, base, p, W_BLEND)
+            x = O.pgd_linf_step(x, g_x, x0, ALPHA, EPS)
+        O.edge_blend_fwd(x, base, p, W_BLEND)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return images / best, cores, best
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is Python
+    (torch eager) and cannot travel to the GPU box, so this is the C port under oracle/ (OpenMP, all
+    host threads), each step a bounded sample of the same workload."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    images = args.cpu_images
+    for _ in range(max(args.warmup, 0)):
+        cpu_hot_path(images, args.side, args.variant)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_hot_path(images, args.side, args.variant)
+    dt = time.perf_counter() - t0
+    value = images * args.steps / dt
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": "edge-enhanced PGD-10 hot-path images/sec", "value": value, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, images, 1, cpu=True),
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": "%d images of 3x%dx%d per step (one Tiny-ImageNet batch), full PGD-10 hot path"
+                                   % (images, args.side, args.side)},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, per_rank, world, cpu=False):
+    return {
+        "workload": "configs[1]: Tiny-ImageNet edge-enhanced PGD-10 hot path, 3x%dx%d fp32, %s, eps 16/255, step 2/255; "
+                    "one step = 10x(edge+blend fwd, edge+blend bwd, PGD L-inf step) + final fwd = 31 launches; "
+                    "CNN and FFT low-pass are outside the product (base, g_out resident synthetic tensors)"
+                    % (args.side, args.side, {"step125": "CannyFilter_step125_1", "canny": "CannyFilter", "bpda": "CannyFilter_BPDA"}[args.variant]),
+        "images_per_rank_per_step": per_rank,
+        "global_images_per_step": per_rank * world,
+        "tiny_batches_of_256_per_rank": per_rank / 256.0,
+        "l2": ("n/a (CPU)" if cpu else
+               "inputs larger than L2: %.0f MB per tensor, 7 tensors per rank, vs 126 MB L2" % (per_rank * 3 * args.side * args.side * 4 / 1e6)),
+        "parallelism": "batch sharded over %d rank(s), no data-path collective" % world,
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=dev)
+
+    import edge_enhancement_b200 as ee
+    from edge_enhancement_b200 import functional as F_ee, _lib, core, attacks
+
+    L = _lib.load()
+    L.ee_set_tuning(args.th_fwd, args.th_bwd, 0)
+    B, S = args.batch, args.side
+    shape = (B, 3, S, S)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x0 = torch.rand(shape, device=dev, generator=gen)
+    base = torch.rand(shape, device=dev, generator=gen) * 1.1 - 0.1
+    g_out = torch.randn(shape, device=dev, generator=gen)
+    g_out.view(-1)[::97] = 0.0
+    x_start = torch.clamp(x0 + (torch.rand(shape, device=dev, generator=gen) * 2 - 1) * EPS, 0, 1)
+    xa, xb = torch.empty_like(x0), torch.empty_like(x0)
+    out, g_x, g_base = torch.empty_like(x0), torch.empty_like(x0), torch.empty_like(x0)
+    filt = {"step125": core.CannyFilter_step125_1, "canny": core.CannyFilter, "bpda": core.CannyFilter_BPDA}[args.variant]
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        canny = filt(use_cuda=False, alpha=0.0)
+    p = canny.params(None if args.variant == "step125" else LOW, HIGH, True)
+
+    stream = torch.cuda.current_stream(dev)
+    ev_pool = []
+
+    def step(record=None):
+        """One PGD-10 hot-path step on resident tensors; 31 launches of our kernels."""
+        cur = x_start
+        nxt = xa
+        for _it in range(N_PGD):
+            if record is not None:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e2 = torch.cuda.Event(enable_timing=True); e3 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+            F_ee.edge_blend(cur, base, p, W_BLEND, out=out)
+            if record is not None:
+                e1.record(stream)
+            F_ee.edge_blend_backward(g_out, cur, base, p, W_BLEND, g_x=g_x, g_base=g_base)
+            if record is not None:
+                e2.record(stream)
+            F_ee.pgd_linf_step(cur, g_x, x0, ALPHA, EPS, out=nxt)
+            if record is not None:
+                e3.record(stream)
+                record.append((e0, e1, e2, e3))
+            cur, nxt = nxt, (xb if nxt is xa else xa)
+        F_ee.edge_blend(cur, base, p, W_BLEND, out=out)
+        return 3 * N_PGD + 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    records = []
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    barrier()
+    t_beg.record(stream)
+    for _ in range(args.steps):
+        launches += step(records)
+    t_end.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = t_beg.elapsed_time(t_end)
+    ms_t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_max = float(ms_t.item())
+    value = world * B * args.steps / (ms_max / 1e3)
+
+    # per-kernel durations inside the timed region
+    fwd_ms = float(np.mean([a.elapsed_time(b) for a, b, _, _ in records]))
+    bwd_ms = float(np.mean([b.elapsed_time(c) for _, b, c, _ in records]))
+    pgd_ms = float(np.mean([c.elapsed_time(d) for _, _, c, d in records]))
+    npx = B * S * S
+    peak, peak_src = load_peaks()
+    kern = {
+        "edge_blend_fwd": {"ms": fwd_ms, "gbs": BYTES_FWD_PX * npx / fwd_ms / 1e6, "bytes_per_px": BYTES_FWD_PX},
+        "edge_blend_bwd": {"ms": bwd_ms, "gbs": BYTES_BWD_PX * npx / bwd_ms / 1e6, "bytes_per_px": BYTES_BWD_PX},
+        "pgd_linf_step": {"ms": pgd_ms, "gbs": BYTES_PGD_ELT * 3 * npx / pgd_ms / 1e6, "bytes_per_elt": BYTES_PGD_ELT},
+    }
+    for k in kern.values():
+        k["frac_of_hbm_peak"] = k["gbs"] / peak
+    share = {"edge_blend_fwd": 11 * fwd_ms, "edge_blend_bwd": 10 * bwd_ms, "pgd_linf_step": 10 * pgd_ms}
+    dom = max(share, key=share.get)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": kern[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "share_of_step": share[dom] / sum(share.values())}
+
+    # ---- end to end through the public API with host buffers ---------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, torch, dist, dev, world, rank, core, attacks, canny, barrier)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, secs = cpu_hot_path(args.cpu_images, S, args.variant, repeats=2)
+        cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": "%d images of 3x%dx%d, one full PGD-10 hot-path step (best of 2, %.1f s each)" % (args.cpu_images, S, S, secs)}
+
+    if args.sweep and rank == 0:
+        run_sweep(torch, F_ee, canny, dev, peak)
+
+    if rank == 0:
+        line = {
+            "metric": "edge-enhanced PGD-10 hot-path images/sec", "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, B, world),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "kernels": kern, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, torch, dist, dev, world, rank, core, attacks, canny, barrier):
+    """attacks.PGD on a model whose front end is core.edge_enhance (base = x; the FFT low-pass is out of
+    scope) and whose head is a per-channel mean -> 3-way cross-entropy (stand-in for the CNN).  Every
+    step copies the batch from pinned host memory and reads the adversarial examples back."""
+    import torch.nn.functional as F
+    B, S = args.batch, args.side
+    shape = (B, 3, S, S)
+    host_in = torch.rand(shape).pin_memory()
+    host_out = torch.empty(shape).pin_memory()
+    targets = torch.randint(0, 3, (B,), device=dev)
+    low = None if args.variant == "step125" else LOW
+
+    def model(x):
+        z = core.edge_enhance(x, x, canny, W_BLEND, low, HIGH, True)
+        return z.flatten(2).mean(2) * 50.0
+
+    class A:
+        random = False
+        epsilon = EPS
+
+    def step():
+        x = host_in.to(dev, non_blocking=True)
+        x_adv = attacks.PGD(model, A, x, targets, N_PGD, ALPHA)
+        with torch.no_grad():
+            model(x_adv)                                   # the training forward on the adversarial batch
+        host_out.copy_(x_adv, non_blocking=True)
+        return 0
+
+    stream = torch.cuda.current_stream(dev)
+    for _ in range(3):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(3, min(args.steps, 10))
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    nbytes = B * 3 * S * S * 4
+    return {"value": world * B * steps / (float(ms.item()) / 1e3), "unit": "images/s",
+            "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": steps,
+            "api": "attacks.PGD(model=edge_enhance front end + mean/CE head, num_steps=10) + final forward"}
+
+
+def run_sweep(torch, F_ee, canny, dev, peak):
+    """configs[4]: standalone kernel sweep (batch x side), printed on stderr as a table."""
+    p = canny.params(None, HIGH, False)
+    print("sweep: B side | fwd GB/s (frac) | bwd GB/s (frac) | pgd GB/s (frac)", file=sys.stderr)
+    for side in (32, 64, 224):
+        for B in (64, 256, 1024, 4096):
+            shape = (B, 3, side, side)
+            x = torch.rand(shape, device=dev); base = torch.rand(shape, device=dev); g = torch.randn(shape, device=dev)
+            o1, o2, o3 = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+            res = []
+            for fn, nbytes in ((lambda: F_ee.edge_blend(x, base, p, 1.0, out=o1), 36.0),
+                               (lambda: F_ee.edge_blend_backward(g, x, base, p, 1.0, g_x=o2, g_base=o3), 60.0),
+                               (lambda: F_ee.pgd_linf_step(x, g, base, ALPHA, EPS, out=o1), 48.0)):
+                for _ in range(3):
+                    fn()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n = 20
+                e0.record()
+                for _ in range(n):
+                    fn()
+                e1.record(); torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / n
+                gbs = nbytes * B * side * side / ms / 1e6
+                res.append("%7.0f (%.2f) %6.1fus" % (gbs, gbs / peak, ms * 1e3))
+            print("sweep: %5d %4d | %s | %s | %s" % (B, side, res[0], res[1], res[2]), file=sys.stderr)
+            del x, base, g, o1, o2, o3
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -53,6 +53,14 @@ def _chk(t, name, shape=None):
     return t.contiguous()
 
 
+def _out_like(x, out):
+    if out is None:
+        return torch.empty_like(x)
+    if not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.shape == x.shape):
+        raise ValueError("edge_b200: `out` must be a contiguous float32 CUDA tensor shaped like the input")
+    return out
+
+
 def _stream(t):
     return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
@@ -92,14 +100,15 @@ def edge_map_backward(g_edge, x, params):
     return g_x
 
 
-def edge_blend(x, base, params, w, want_edge=False):
-    """out = clamp(base + w*filter(x), 0, 1) in one pass -- ee_edge_blend_fwd_f32."""
+def edge_blend(x, base, params, w, want_edge=False, out=None):
+    """out = clamp(base + w*filter(x), 0, 1) in one pass -- ee_edge_blend_fwd_f32.
+    `out` (optional) is a preallocated result buffer; it must not alias x or base."""
     x = _chk(x, "img")
     if x.dim() != 4:
         raise ValueError("img must be [B,C,H,W]")
     B, C, H, W = x.shape
     base = _chk(base, "base", x.shape)
-    out = torch.empty_like(x)
+    out = _out_like(x, out)
     edge = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device) if want_edge else None
     if x.numel():
         with torch.cuda.device(x.device):
@@ -109,13 +118,15 @@ def edge_blend(x, base, params, w, want_edge=False):
     return (out, edge) if want_edge else out
 
 
-def edge_blend_backward(g_out, x, base, params, w, need_x=True, need_base=True):
+def edge_blend_backward(g_out, x, base, params, w, need_x=True, need_base=True, g_x=None, g_base=None):
+    """(g_x, g_base) of edge_blend in one pass -- ee_edge_blend_bwd_f32.  g_x / g_base may be
+    preallocated buffers (not aliasing any input)."""
     x = _chk(x, "img")
     B, C, H, W = x.shape
     base = _chk(base, "base", x.shape)
     g_out = _chk(g_out, "grad_out", x.shape)
-    g_x = torch.empty_like(x) if need_x else None
-    g_base = torch.empty_like(x) if need_base else None
+    g_x = _out_like(x, g_x) if need_x else None
+    g_base = _out_like(x, g_base) if need_base else None
     if x.numel() and (need_x or need_base):
         with torch.cuda.device(x.device):
             rc = _lib.load().ee_edge_blend_bwd_f32(_ptr(g_out), _ptr(x), _ptr(base), _ptr(g_x), _ptr(g_base),
@@ -133,14 +144,6 @@ def _same(*ts):
             raise ValueError("edge_b200: operand %d has shape/device %s/%s, expected %s/%s"
                              % (i, tuple(t.shape), t.device, tuple(ref.shape), ref.device))
         out.append(t)
-    return out
-
-
-def _out_like(x, out):
-    if out is None:
-        return torch.empty_like(x)
-    if not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.shape == x.shape):
-        raise ValueError("edge_b200: `out` must be a contiguous float32 CUDA tensor shaped like the input")
     return out
 
 

@@ -1,0 +1,176 @@
+"""not gpu: host-side logic of the drop-in package and the C-ABI surface (no compute calls)."""
+import contextlib
+import ctypes
+import io
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import edge_enhancement_b200 as ee
+from edge_enhancement_b200 import _lib, attacks, core, functional as F_ee
+from oracle import oracle as O
+from oracle import ref_loader
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "edge_b200.h")).read()
+    declared = set(re.findall(r"\b(ee_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 19
+    L = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(L, name), "libedge_b200.so does not export %s" % name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert L.ee_version() == 100
+    assert L.ee_aux_bytes(256, 3, 64, 64, 0) == 0
+    assert L.ee_last_error() is not None
+
+
+def test_eeparams_layout_matches_header():
+    # 2 ints + 18 floats + 3 floats + 4 ints = 27 * 4 bytes, no padding
+    assert ctypes.sizeof(_lib.EEParams) == 27 * 4
+    p = F_ee.make_params("canny", O.gaussian3(), 0.3, 25 / 255, 51 / 255, True)
+    assert p.variant == 1 and p.has_low == 1 and p.has_high == 1 and p.hysteresis == 1
+    assert p.low_thr == np.float32(25 / 255) and p.high_thr == np.float32(51 / 255)
+    assert list(p.sobel) == [-0.5, 0.0, 0.5, -1.0, 0.0, 1.0, -0.5, 0.0, 0.5]
+    with pytest.raises(NotImplementedError):
+        F_ee.make_params("canny", np.ones((5, 5), np.float32))
+
+
+def test_argument_validation_without_a_gpu():
+    """Validation happens before any CUDA call, so it is testable on the CPU box."""
+    L = _lib.load()
+    p = F_ee.make_params("step125", O.gaussian3(), 0.0, None, 76 / 255, False)
+    assert L.ee_edge_fwd_f32(None, None, 1, 3, 8, 8, ctypes.byref(p), None) == -1          # EE_ERR_INVALID_ARG
+    assert b"null" in L.ee_last_error()
+    assert L.ee_edge_fwd_f32(None, None, 0, 3, 8, 8, ctypes.byref(p), None) == -1
+    p2 = F_ee.make_params("step125", O.gaussian3(), 0.0, None, None, False)
+    assert L.ee_edge_fwd_f32(None, None, 1, 3, 8, 8, ctypes.byref(p2), None) == -1
+    assert b"high_threshold" in L.ee_last_error()
+    bad = O.gaussian3().copy(); bad[0, 0] = 0.5
+    p3 = F_ee.make_params("canny", bad)
+    assert L.ee_edge_fwd_f32(None, None, 1, 3, 8, 8, ctypes.byref(p3), None) == -2         # EE_ERR_UNSUPPORTED
+    assert L.ee_pgd_linf_step_f32(None, None, None, None, 16, 0.1, 0.1, 0.0, 1.0, None) == -1
+    assert L.ee_pgd_linf_step_f32(None, None, None, None, 0, 0.1, 0.1, 0.0, 1.0, None) == 0  # empty input is fine
+
+
+def test_no_cpu_fallback():
+    f = quiet(core.CannyFilter_step125_1)
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        f(torch.rand(1, 3, 8, 8), high_threshold=0.3)
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        F_ee.pgd_linf_step(torch.rand(4), torch.rand(4), torch.rand(4), 0.1, 0.1)
+    with pytest.raises(UnboundLocalError):
+        f(torch.rand(1, 3, 8, 8))                       # reference behaviour, core.py:578-583
+    # the product must not import the oracle
+    for name, mod in list(sys.modules.items()):
+        if name.startswith("edge_enhancement_b200"):
+            src = getattr(mod, "__file__", None)
+            if src and os.path.exists(src):
+                assert "oracle" not in open(src).read().replace("oracle/", "").replace("the oracle", ""), name
+
+
+def test_kernel_builders_match_reference_constants():
+    g = core.get_gaussian_kernel(3, 0, 1)
+    assert np.allclose(g.sum(), 1.0)
+    assert np.array_equal(g.astype(np.float32), O.gaussian3())
+    assert np.array_equal(core.get_sobel_kernel(3), np.array([[-.5, 0, .5], [-1, 0, 1], [-.5, 0, .5]]))
+    thin = core.get_thin_kernels()
+    assert len(thin) == 8 and all(k[1, 1] == 1 and k.sum() == 0 for k in thin)
+    if ref_loader.available():
+        rc, _ = ref_loader.load()
+        for sigma in (0.5, 1.0, 2.0):
+            assert np.array_equal(core.get_gaussian_kernel(3, 0, sigma), rc.get_gaussian_kernel(3, 0, sigma))
+        assert np.array_equal(core.get_sobel_kernel(3), rc.get_sobel_kernel(3))
+        for a, b in zip(thin, rc.get_thin_kernels()):          # cv2-generated
+            assert np.array_equal(a, b)
+
+
+def test_module_surface_and_state_dict_layout():
+    f = quiet(core.CannyFilter, alpha=0.3)
+    assert list(f.state_dict()) == ["weight_gaussian", "weight_sobel_x", "weight_sobel_y",
+                                    "weight_directional", "weight_hysteresis"]
+    assert all(not p.requires_grad for p in f.parameters())
+    assert f.weight_directional.shape == (8, 1, 3, 3) and f.weight_hysteresis.flatten()[0] == 1.25
+    assert f.alpha == 0.3 and f.device == "cpu"
+    for cls in (core.CannyFilter_BPDA, core.CannyFilter_step125_1):
+        m = quiet(cls, alpha=0.1)
+        assert list(m.state_dict()) == []                        # plain tensors, core.py:403-424
+        assert isinstance(m.alpha, torch.Tensor) and m.weight_gaussian.shape == (1, 1, 3, 3)
+    with pytest.raises(NotImplementedError):
+        quiet(core.CannyFilter, k_gaussian=5)
+    if ref_loader.available():
+        rc, _ = ref_loader.load()
+        with ref_loader.quiet():
+            r = rc.CannyFilter(alpha=0.3)
+        for k, v in r.state_dict().items():
+            assert torch.equal(v, f.state_dict()[k]), k
+        f.load_state_dict(r.state_dict())
+    import inspect
+    assert str(inspect.signature(core.CannyFilter.__init__)) == \
+        "(self, k_gaussian=3, mu=0, sigma=1, k_sobel=3, use_cuda=False, alpha=0.0)"
+    assert str(inspect.signature(core.CannyFilter.forward)) == \
+        "(self, img, low_threshold=None, high_threshold=None, hysteresis=False)"
+
+
+def test_attack_surface_matches_reference_signatures():
+    import inspect
+    names = ["PGD", "targeted_PGD", "targeted_PGD_trick", "FGSM", "CWLinfAttack", "tar_alp_imagenet", "l2_norm",
+             "squared_l2_norm", "predict_from_logits", "compute_loss_and_error"]
+    classes = ["ALP", "targeted_ALP", "Trades", "AVmixup", "LabelSmoothLoss"]
+    for n in names + classes:
+        assert hasattr(attacks, n), n
+    if ref_loader.available():
+        _, ra = ref_loader.load()
+        for n in names:
+            assert str(inspect.signature(getattr(attacks, n))) == str(inspect.signature(getattr(ra, n))), n
+        for c in classes:
+            assert str(inspect.signature(getattr(attacks, c).__init__)) == str(inspect.signature(getattr(ra, c).__init__)), c
+        for c, ms in (("Trades", ["PGD_L2", "PGD_Linf", "loss", "reset_steps"]), ("AVmixup", ["perturb", "tar_perturb"]),
+                      ("targeted_ALP", ["PGD_Linf", "tarPGD_Linf", "loss"])):
+            for m in ms:
+                assert str(inspect.signature(getattr(getattr(attacks, c), m))) == \
+                    str(inspect.signature(getattr(getattr(ra, c), m))), (c, m)
+
+
+def test_install_aliases_utils_modules():
+    saved = {k: v for k, v in sys.modules.items() if k == "utils" or k.startswith("utils.")}
+    try:
+        for k in saved:
+            del sys.modules[k]
+        ee.install("utils")
+        from utils.core import CannyFilter, HighFreqSuppress, get_gaussian_kernel       # noqa: F401
+        from utils.attacks import PGD, Trades                                          # noqa: F401
+        assert CannyFilter is core.CannyFilter and PGD is attacks.PGD
+    finally:
+        for k in list(sys.modules):
+            if k == "utils" or k.startswith("utils."):
+                del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def test_high_freq_suppress_restatement():
+    """torch.fft restatement of utils/core.py:15-55: mask structure and basic behaviour (UNPINNED vs
+    the reference, whose torch.rfft call cannot run on torch >= 1.8)."""
+    h = core.HighFreqSuppress(28, 28, 4)
+    assert h.temp.shape == (1, 1, 28, 28, 1) and int(h.temp.sum()) == 64
+    x = torch.rand(2, 3, 28, 28)
+    y = h(x)
+    assert y.shape == x.shape and y.dtype == torch.float32
+    assert torch.allclose(y.mean((2, 3)), x.mean((2, 3)), atol=1e-5)       # DC passes
+    full = core.HighFreqSuppress(8, 8, 4)                                   # radius covers everything
+    z = torch.rand(1, 1, 8, 8)
+    assert torch.allclose(full(z), z, atol=1e-5)
+    if ref_loader.available():
+        rc, _ = ref_loader.load()
+        assert torch.equal(rc.HighFreqSuppress(64, 64, 8).temp, core.HighFreqSuppress(64, 64, 8).temp)
