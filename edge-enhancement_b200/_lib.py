@@ -60,7 +60,7 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
+    path = os.environ.get("EDGE_B200_LIB") or _build.LIB     # env override: A/B testing of kernel builds
     if not os.path.exists(path):
         path = _build.build()            # raises if nvcc is unavailable: no silent fallback
     L = ctypes.CDLL(path)

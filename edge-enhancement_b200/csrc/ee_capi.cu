@@ -3,6 +3,7 @@
 #include "../../include/edge_b200.h"
 #include "ee_attack.cuh"
 #include "ee_edge_canny.cuh"
+#include "ee_edge_fast.cuh"
 #include "ee_edge_step125.cuh"
 
 #include <atomic>
@@ -52,6 +53,112 @@ int check_params(const EEParams* p, float& c0, float& c1, float& c2) {
 }
 
 struct Launch { int vec, threads, GX, RY, TH, tiles; size_t smem; };
+
+// ---- exact threshold cut-offs in u = mag^2 space (sqrt_rn is monotonic) ----------------------
+float f_of(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
+// largest fp32 u >= 0 with pred(u) true, where pred is true at 0 and monotonically turns false
+template <typename P>
+float last_true(P pred) {
+    uint32_t lo = 0, hi = 0x7f800000u;          // +0 .. +inf
+    if (pred(f_of(hi))) return f_of(hi);
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (pred(f_of(mid))) lo = mid; else hi = mid;
+    }
+    return f_of(lo);
+}
+// mag > thr  <=>  u > cut
+float cut_gt(float thr) {
+    if (thr < 0.0f) return -1.0f;
+    return last_true([thr](float u) { return sqrtf(u) <= thr; });
+}
+// mag < alpha  <=>  u < cut
+float cut_lt(float alpha) {
+    if (!(alpha > 0.0f)) return 0.0f;
+    const float m = last_true([alpha](float u) { return sqrtf(u) < alpha; });
+    return nextafterf(m, INFINITY);
+}
+
+// Launch plan of the tuned (fast) kernels: padded plane rows, R rows per thread chunk.
+int plan_fast(int H, int W, int R, int rows_per_th, int rows_fixed, int max_halo_rows, int budget_bytes, int forced_th,
+              Launch& L) {
+    L.vec = 4;
+    const int G = W / 4;
+    const size_t row_bytes = (size_t)(W + ee::kPadW) * sizeof(float);
+    auto smem_of = [&](int th) { return (size_t)(rows_per_th * th + rows_fixed) * row_bytes; };
+    int th;
+    if (forced_th > 0) {
+        th = forced_th < H ? forced_th : H;
+    } else {
+        long fit = ((long)(budget_bytes / row_bytes) - rows_fixed) / rows_per_th;
+        th = (int)(fit < 4 ? 4 : (fit > H ? H : fit));
+        const int tiles = (H + th - 1) / th;
+        th = (H + tiles - 1) / tiles;
+    }
+    while (th > 1 && smem_of(th) > (size_t)kMaxSmem) --th;
+    if (smem_of(th) > (size_t)kMaxSmem) return fail(EE_ERR_TOO_LARGE, "row strip of width %d does not fit in shared memory", W);
+    L.TH = th;
+    L.tiles = (H + th - 1) / th;
+    L.smem = smem_of(th);
+    const int max_chunks = (th + max_halo_rows + R - 1) / R;
+    if (G >= kThreads) { L.GX = kThreads; L.RY = 1; }
+    else {
+        L.GX = G;
+        int ry = kThreads / G;
+        if (ry > max_chunks) ry = max_chunks;
+        if (ry < 1) ry = 1;
+        L.RY = ry;
+    }
+    L.threads = ((L.GX * L.RY + 31) / 32) * 32;
+    return EE_OK;
+}
+
+template <typename K>
+int launch_fast(K kernel, const Launch& L, int B, const ee::FastArgs& a, cudaStream_t s, const char* name) {
+    if (L.smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+    }
+    const long long grid = (long long)B * L.tiles;
+    if (grid > 0x7fffffffLL) return fail(EE_ERR_TOO_LARGE, "too many tiles");
+    kernel<<<(unsigned)grid, L.threads, L.smem, s>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, name);
+    return EE_OK;
+}
+
+// The tuned kernels keep full-width strips in shared memory; beyond ~128 columns the strips get so
+// thin (or the CTA count per SM so low) that the generic kernels win (measured at 224 px), so wide
+// images stay on the generic path unless forced (staging 4 / 8).
+bool fast_eligible(const ee::EdgeArgs& a, bool vec_ok) {
+    const int st = g_staging.load();
+    if (st == 1 || !vec_ok || a.W < 8 || a.H < 4) return false;
+    if (!(std::isfinite(a.high) && std::isfinite(a.alpha) && fabsf(a.high) < 1e18f && fabsf(a.alpha) < 1e18f)) return false;
+    return a.W <= 128 || st == 4 || st == 8;
+}
+
+void fill_fast(ee::FastArgs& f, const ee::EdgeArgs& a, const Launch& L) {
+    f.e = a;
+    f.e.TH = L.TH; f.e.tiles_per_img = L.tiles; f.e.GX = L.GX; f.e.RY = L.RY;
+    f.hi_cut = cut_gt(a.high);
+    f.w_cut = cut_gt(1.001f);
+    f.a_cut = cut_lt(a.alpha);
+    // u > hi_cut and u >= a_cut  <=>  u > max(hi_cut, nextbelow(a_cut))
+    f.e_cut = f.hi_cut;
+    if (f.a_cut > 0.0f) {
+        const float below = nextafterf(f.a_cut, -INFINITY);
+        if (below > f.e_cut) f.e_cut = below;
+    }
+    f.zero_val = (0.0f > a.high) ? 1.0f : 0.0f;
+    f.Wp = a.W + ee::kPadW;
+}
+
+#define EE_DISPATCH_FAST(KERNEL, BLEND, RR, L, B, f, s, name)                                     \
+    do {                                                                                          \
+        if ((f).e.C == 3) return launch_fast(KERNEL<3, BLEND, RR>, L, B, f, s, name);             \
+        if ((f).e.C == 1) return launch_fast(KERNEL<1, BLEND, RR>, L, B, f, s, name);             \
+        return launch_fast(KERNEL<0, BLEND, RR>, L, B, f, s, name);                               \
+    } while (0)
 
 // rows_fixed / rows_per_th: the kernel needs (rows_per_th*TH + rows_fixed) plane rows of W floats.
 int plan(int H, int W, bool vec_ok, int rows_per_th, int rows_fixed, int max_halo_rows, int budget_bytes,
@@ -139,6 +246,19 @@ int edge_forward(const float* x, const float* base, float* out, float* edge, int
     const bool vec_ok = (W % 4 == 0) && aligned16(x) && aligned16(base) && aligned16(out) && aligned16(edge);
     cudaStream_t s = (cudaStream_t)stream;
     Launch L;
+    if (p->variant == EE_VARIANT_STEP125 && fast_eligible(a, vec_ok)) {
+        const int R = (g_staging.load() == 8) ? 8 : 4;
+        rc = plan_fast(H, W, R, 2, 6, 4, 40 * 1024, g_th_fwd.load(), L);
+        if (rc) return rc;
+        ee::FastArgs f;
+        fill_fast(f, a, L);
+        if (R == 8) {
+            if (blend) EE_DISPATCH_FAST(ee::edge_fwd_step125_fast, true, 8, L, B, f, s, "edge_fwd_step125_fast");
+            else EE_DISPATCH_FAST(ee::edge_fwd_step125_fast, false, 8, L, B, f, s, "edge_fwd_step125_fast");
+        }
+        if (blend) EE_DISPATCH_FAST(ee::edge_fwd_step125_fast, true, 4, L, B, f, s, "edge_fwd_step125_fast");
+        else EE_DISPATCH_FAST(ee::edge_fwd_step125_fast, false, 4, L, B, f, s, "edge_fwd_step125_fast");
+    }
     if (p->variant == EE_VARIANT_STEP125) {
         rc = plan(H, W, vec_ok, 2, 6, 4, 44 * 1024, g_th_fwd.load(), L);
         if (rc) return rc;
@@ -166,6 +286,19 @@ int edge_backward(const float* g_in, const float* x, const float* base, float* g
     const bool vec_ok = (W % 4 == 0) && aligned16(x) && aligned16(base) && aligned16(g_in) && aligned16(g_x) && aligned16(g_base);
     cudaStream_t s = (cudaStream_t)stream;
     Launch L;
+    if (p->variant == EE_VARIANT_STEP125 && fast_eligible(a, vec_ok)) {
+        const int R = (g_staging.load() == 8) ? 8 : 4;
+        rc = plan_fast(H, W, R, 3, 18, 8, 62 * 1024, g_th_bwd.load(), L);
+        if (rc) return rc;
+        ee::FastArgs f;
+        fill_fast(f, a, L);
+        if (R == 8) {
+            if (blend) EE_DISPATCH_FAST(ee::edge_bwd_step125_fast, true, 8, L, B, f, s, "edge_bwd_step125_fast");
+            else EE_DISPATCH_FAST(ee::edge_bwd_step125_fast, false, 8, L, B, f, s, "edge_bwd_step125_fast");
+        }
+        if (blend) EE_DISPATCH_FAST(ee::edge_bwd_step125_fast, true, 4, L, B, f, s, "edge_bwd_step125_fast");
+        else EE_DISPATCH_FAST(ee::edge_bwd_step125_fast, false, 4, L, B, f, s, "edge_bwd_step125_fast");
+    }
     if (p->variant == EE_VARIANT_STEP125) {
         rc = plan(H, W, vec_ok, 3, 18, 8, 56 * 1024, g_th_bwd.load(), L);
         if (rc) return rc;

@@ -190,13 +190,14 @@ __device__ __forceinline__ int orient_bin(float gx1, float gy1) {
 }
 
 // dL/d(mag) -> (dL/dSgx, dL/dSgy):  mag = u^.5, u = gx1^2 + gy1^2 ; autograd evaluates
-// g*0.5*u^-.5, then *2*gx1, then /C.  Sub-gradient at mag == 0 is 0.
+// g*0.5*u^-.5, then *2*gx1, then /C (three divisions); canonical form: (g / (mag*C)) * gx1, one
+// division, equal up to ~2 ulp.  Sub-gradient at mag == 0 is 0.
 __device__ __forceinline__ void mag_backward(float gm, float mag, float gx1, float gy1, float fC,
                                              float& a, float& b) {
     if (gm == 0.0f || mag == 0.0f) { a = 0.0f; b = 0.0f; return; }
-    const float t = (gm * 0.5f) / mag;
-    a = (t * (2.0f * gx1)) / fC;
-    b = (t * (2.0f * gy1)) / fC;
+    const float t = gm / (mag * fC);
+    a = t * gx1;
+    b = t * gy1;
 }
 
 }  // namespace ee

@@ -1,0 +1,605 @@
+// ee_edge_fast.cuh -- tuned CannyFilter_step125_1 (+ blend) kernels for the 128-bit path.
+//
+// Same strip decomposition and the same canonical arithmetic as ee_edge_step125.cuh (the generic
+// kernels there stay as the any-shape fallback and as a second implementation to test against),
+// restructured because the round-1 profile (profiles/r1_*.md) showed the generic kernels are
+// ISSUE-bound, not HBM-bound: ~345 (bwd) / 142 (fwd) instructions per pixel, over half of them
+// integer / control, and every stencil row recomputed three times.  Changes:
+//
+//   * shared-memory planes carry one pad column on each side (row stride W+8 floats, data at +4,
+//     still 16-byte aligned): replicate / zero extension is materialised by the writer, so a
+//     window is always LDS.128 + 2 LDS.32 with no branch or clamp;
+//   * register sliding window down the rows: a thread owns one float4 column group and a chunk
+//     of R consecutive rows; the horizontal partial sums of each input row (P/Q, D/V, HA/HB) are
+//     computed once and reused by the three output rows that need them (3x fewer LDS and a third
+//     less FP work); the loop is fully unrolled so the 3-deep ring lives in registers;
+//   * x / 3 is evaluated as q = x*r, q' = fma(fma(-q,3,x), r, q) -- the correctly rounded quotient
+//     for every finite fp32 x (exhaustively verified), 3 instructions instead of ~10;
+//   * the threshold tests never take a square root: sqrt_rn is monotonic, so
+//     `sqrt(u) > thr` <=> `u > hi_cut` for a cut-off computed exactly on the host
+//     (ee_capi.cu: largest fp32 u with sqrtf(u) <= thr).  sqrt is only evaluated in the backward,
+//     on the ~5 % of pixels that carry gradient.
+#pragma once
+#include <type_traits>
+
+#include "ee_edge_step125.cuh"
+
+namespace ee {
+
+constexpr int kPadL = 4;      // floats of padding left of column 0 in every plane row (keeps 16B alignment)
+constexpr int kPadW = 8;      // total extra floats per plane row
+
+struct FastArgs {
+    EdgeArgs e;
+    float hi_cut;     // mag >  high   <=> u > hi_cut
+    float w_cut;      // mag <= 1.001f <=> u <= w_cut
+    float a_cut;      // mag <  alpha  <=> u < a_cut
+    float e_cut;      // (mag > high and not mag < alpha) <=> u > e_cut
+    float zero_val;   // To_compare's value for "not above": 1 if high < 0 else 0 (core.py:344-345)
+    int Wp;           // plane row stride in floats (W + 8)
+};
+
+// (sgx, sgy)[4] / C, value-identical to the IEEE division.  DIVM: 0 -> C == 1, 1 -> C == 3, 2 -> any C.
+// For C == 3: q = x*r, q' = fma(fma(-q,3,x), r, q) with r = RN(1/3) is the correctly rounded quotient
+// for EVERY finite fp32 x including denormals (verified exhaustively over all 2^31 bit patterns
+// against x/3.0f; the only difference is the sign of a zero result for x = -0).
+template <int DIVM>
+__device__ __forceinline__ void div_channels8(const float (&sx)[4], const float (&sy)[4], float fC, float (&gx)[4], float (&gy)[4]) {
+    if constexpr (DIVM == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { gx[k] = sx[k]; gy[k] = sy[k]; }
+    } else if constexpr (DIVM == 1) {
+        const float r = 0.333333343f;                 // RN(1/3) = 0x3eaaaaab
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float qx = sx[k] * r, qy = sy[k] * r;
+            gx[k] = fmaf(fmaf(-qx, 3.0f, sx[k]), r, qx);
+            gy[k] = fmaf(fmaf(-qy, 3.0f, sy[k]), r, qy);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { gx[k] = sx[k] / fC; gy[k] = sy[k] / fC; }
+    }
+}
+
+// edge value from u = gx1^2 + gy1^2 (no sqrt): to_compare(gate(mag), high).  e_cut folds the
+// threshold and the alpha gate into one comparison (ee_capi.cu); NaN stays NaN like To_compare.
+__device__ __forceinline__ float edge_from_u(const FastArgs& a, float u) {
+    return (u > a.e_cut) ? 1.0f : ((u != u) ? u : a.zero_val);
+}
+
+// torch.clamp(v, 0, 1) with NaN propagation in two instructions (FMNMX.NAN)
+__device__ __forceinline__ float clamp01_fast(float v) {
+    float r;
+    asm("max.NaN.f32 %0, %1, 0f00000000;\n\tmin.NaN.f32 %0, %0, 0f3F800000;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// Duplicating every chunk body into a guard-free FULL variant was measured SLOWER on B200 (code
+// size / registers: 3.4 vs 5.7 TB/s forward), so it is off by default; kept for experiments.
+#ifndef EE_USE_FULL
+#define EE_USE_FULL 0
+#endif
+
+#define EE_FOR_CHUNKS(row_lo, row_hi)                                                         \
+    for (int ch = ty, n_ch = ((row_hi) - (row_lo) + R - 1) / R; ch < n_ch; ch += a.e.RY)      \
+        for (int g = tx; g < G; g += a.e.GX)
+
+// Every chunk body exists twice: FULL (all R rows present, no image border inside the chunk: no
+// guards, no clamps) and the guarded general version.  `full_t` / `part_t` select them.
+using full_t = std::integral_constant<bool, true>;
+using part_t = std::integral_constant<bool, false>;
+
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// write 4 values + the pad column a border group owns
+__device__ __forceinline__ void st_plane(float* q, const float (&o)[4], bool left, bool right, float lpad, float rpad) {
+    *reinterpret_cast<float4*>(q) = make_float4(o[0], o[1], o[2], o[3]);
+    if (left) q[-1] = lpad;
+    if (right) q[4] = rpad;
+}
+
+// ---- stage S: channel sum of x rows [lo,hi) into a replicate-padded plane -------------------
+template <int NC, int R>
+__device__ __forceinline__ void fast_stage_sum(const FastArgs& a, const float* __restrict__ xb, float* S, int lo, int hi,
+                                               int G, int tx, int ty) {
+    const int W = a.e.W, Wp = a.Wp;
+    const int C = NC ? NC : a.e.C;
+    const size_t hw = (size_t)a.e.H * W;
+    EE_FOR_CHUNKS(lo, hi) {
+        const int col = g * 4, ra = lo + ch * R;
+        const float* px = xb + (size_t)ra * W + col;
+        float* ps = S + (size_t)(ra - lo) * Wp + kPadL + col;
+        auto body = [&](auto tag) {
+            constexpr bool FULL = decltype(tag)::value;
+            float4 acc[R];
+            if (NC == 3) {
+                float4 v1[R], v2[R];
+#pragma unroll
+                for (int i = 0; i < R; ++i)
+                    if (FULL || ra + i < hi) {
+                        acc[i] = __ldg(reinterpret_cast<const float4*>(px + i * W));
+                        v1[i] = __ldg(reinterpret_cast<const float4*>(px + i * W + hw));
+                        v2[i] = __ldg(reinterpret_cast<const float4*>(px + i * W + 2 * hw));
+                    }
+#pragma unroll
+                for (int i = 0; i < R; ++i)
+                    if (FULL || ra + i < hi) acc[i] = f4add(f4add(acc[i], v1[i]), v2[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < R; ++i)
+                    if (FULL || ra + i < hi) acc[i] = __ldg(reinterpret_cast<const float4*>(px + i * W));
+                for (int c = 1; c < C; ++c) {
+#pragma unroll
+                    for (int i = 0; i < R; ++i)
+                        if (FULL || ra + i < hi) acc[i] = f4add(acc[i], __ldg(reinterpret_cast<const float4*>(px + i * W + (size_t)c * hw)));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+                if (FULL || ra + i < hi) {
+                    const float o[4] = {acc[i].x, acc[i].y, acc[i].z, acc[i].w};
+                    st_plane(ps + i * Wp, o, col == 0, col + 4 == W, o[0], o[3]);
+                }
+        };
+        if (EE_USE_FULL && ra + R <= hi) body(full_t{}); else body(part_t{});
+    }
+}
+
+// window of one plane row: l | m[4] | r
+struct Win { float l, m0, m1, m2, m3, r; };
+__device__ __forceinline__ Win ld_win(const float* p) {
+    const float4 m = *reinterpret_cast<const float4*>(p);
+    Win w; w.l = p[-1]; w.m0 = m.x; w.m1 = m.y; w.m2 = m.z; w.m3 = m.w; w.r = p[4];
+    return w;
+}
+
+// Gaussian horizontal partials of one row: P (outer rows) and Q (centre row)
+__device__ __forceinline__ void gauss_partials(const Win& w, float c0, float c1, float c2, float (&P)[4], float (&Q)[4]) {
+    const float e0 = w.l + w.m1, e1 = w.m0 + w.m2, e2 = w.m1 + w.m3, e3 = w.m2 + w.r;
+    P[0] = fmaf(c1, w.m0, c0 * e0); P[1] = fmaf(c1, w.m1, c0 * e1); P[2] = fmaf(c1, w.m2, c0 * e2); P[3] = fmaf(c1, w.m3, c0 * e3);
+    Q[0] = fmaf(c2, w.m0, c1 * e0); Q[1] = fmaf(c2, w.m1, c1 * e1); Q[2] = fmaf(c2, w.m2, c1 * e2); Q[3] = fmaf(c2, w.m3, c1 * e3);
+}
+
+// Forward sliding chunks: output rows [ra, rb), inputs ra-1 .. rb with the row index clamped to the
+// image (replicate padding).  A chunk is FULL when it has R rows and touches neither image border.
+
+#define EE_FWD_CHUNK_IS_FULL(ra, rb, H) (EE_USE_FULL && (rb) - (ra) == R && (ra) > 0 && (rb) < (H))
+
+// ---- stage blur: Bl rows [lo,hi) from S ------------------------------------------------------
+template <int R>
+__device__ __forceinline__ void fast_stage_blur(const FastArgs& a, const float* S, int s_lo, float* Bl, int lo, int hi,
+                                                int G, int tx, int ty) {
+    const int W = a.e.W, H = a.e.H, Wp = a.Wp;
+    const float c0 = a.e.c0, c1 = a.e.c1, c2 = a.e.c2;
+    EE_FOR_CHUNKS(lo, hi) {
+        const int col = g * 4, ra = lo + ch * R, rb = min(ra + R, hi);
+        const float* ps = S + kPadL + col;                 // row r at ps + (r - s_lo) * Wp
+        float* pb = Bl + (size_t)(ra - lo) * Wp + kPadL + col;
+        auto body = [&](auto tag) {
+            constexpr bool FULL = decltype(tag)::value;
+            float P[3][4], Q[3][4];
+#pragma unroll
+            for (int i = 0; i < R + 2; ++i) {
+                const int rin = ra - 1 + i;
+                if (FULL || rin <= rb) {
+                    const int rc = FULL ? rin : min(max(rin, 0), H - 1);
+                    gauss_partials(ld_win(ps + (rc - s_lo) * Wp), c0, c1, c2, P[i % 3], Q[i % 3]);
+                }
+                if (i >= 2 && (FULL || ra + i - 2 < rb)) {
+                    float o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) o[k] = (P[(i - 2) % 3][k] + Q[(i - 1) % 3][k]) + P[i % 3][k];
+                    st_plane(pb + (i - 2) * Wp, o, col == 0, col + 4 == W, o[0], o[3]);
+                }
+            }
+        };
+        if (EE_FWD_CHUNK_IS_FULL(ra, rb, H)) body(full_t{}); else body(part_t{});
+    }
+}
+
+// Sobel horizontal partials of one blurred row: D = right - left, V = fma(.5, left + right, mid)
+__device__ __forceinline__ void sobel_partials(const Win& w, float (&D)[4], float (&V)[4]) {
+    D[0] = w.m1 - w.l; D[1] = w.m2 - w.m0; D[2] = w.m3 - w.m1; D[3] = w.r - w.m2;
+    V[0] = fmaf(0.5f, w.l + w.m1, w.m0); V[1] = fmaf(0.5f, w.m0 + w.m2, w.m1);
+    V[2] = fmaf(0.5f, w.m1 + w.m3, w.m2); V[3] = fmaf(0.5f, w.m2 + w.r, w.m3);
+}
+
+// -------------------------------------------------------------------------------------------
+// forward:  planes S (TH+4 rows) and Bl (TH+2 rows), both with stride Wp
+// -------------------------------------------------------------------------------------------
+template <int NC, bool BLEND, int R>
+#ifndef EE_MINB_FWD
+#define EE_MINB_FWD 3
+#endif
+#ifndef EE_MINB_BWD
+#define EE_MINB_BWD 3
+#endif
+__global__ void __launch_bounds__(256, EE_MINB_FWD) edge_fwd_step125_fast(const FastArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int DIVM = (NC == 1) ? 0 : (NC == 3 ? 1 : 2);
+    const int b = blockIdx.x / a.e.tiles_per_img;
+    const int ti = blockIdx.x - b * a.e.tiles_per_img;
+    const int H = a.e.H, W = a.e.W, Wp = a.Wp;
+    const int C = NC ? NC : a.e.C;
+    const int r0 = ti * a.e.TH, r1 = min(r0 + a.e.TH, H);
+    const int G = W >> 2;
+    const int tx = threadIdx.x % a.e.GX, ty = threadIdx.x / a.e.GX;
+    const size_t hw = (size_t)H * W;
+
+    const int s_lo = max(r0 - 2, 0), s_hi = min(r1 + 2, H);
+    const int b_lo = max(r0 - 1, 0), b_hi = min(r1 + 1, H);
+    float* S = smem;
+    float* Bl = smem + (size_t)(a.e.TH + 4) * Wp;
+
+    if (ty < a.e.RY) fast_stage_sum<NC, R>(a, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, G, tx, ty);
+    __syncthreads();
+    if (ty < a.e.RY) fast_stage_blur<R>(a, S, s_lo, Bl, b_lo, b_hi, G, tx, ty);
+    __syncthreads();
+    if (ty >= a.e.RY) return;
+
+    const float fC = a.e.fC, wgt = a.e.w;
+    const float* base_b = a.e.base + (size_t)b * C * hw;
+    float* out_b = a.e.out + (size_t)b * C * hw;
+    EE_FOR_CHUNKS(r0, r1) {
+        const int col = g * 4, ra = r0 + ch * R, rb = min(ra + R, r1);
+        const float* pbl = Bl + kPadL + col;
+        auto body = [&](auto tag) {
+            constexpr bool FULL = decltype(tag)::value;
+            float D[3][4], V[3][4];
+#pragma unroll
+            for (int i = 0; i < R + 2; ++i) {
+                const int rin = ra - 1 + i;
+                if (FULL || rin <= rb) {
+                    const int rc = FULL ? rin : min(max(rin, 0), H - 1);
+                    sobel_partials(ld_win(pbl + (rc - b_lo) * Wp), D[i % 3], V[i % 3]);
+                }
+                if (i >= 2 && (FULL || ra + i - 2 < rb)) {
+                    const int pix = (ra + i - 2) * W + col;
+                    float4 bs[NC ? NC : 1];
+                    if (BLEND && NC) {
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) bs[c] = __ldg(reinterpret_cast<const float4*>(base_b + c * hw + pix));
+                    }
+                    float e[4], sgx[4], sgy[4], gx1[4], gy1[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        sgx[k] = fmaf(0.5f, D[(i - 2) % 3][k] + D[i % 3][k], D[(i - 1) % 3][k]);
+                        sgy[k] = V[i % 3][k] - V[(i - 2) % 3][k];
+                    }
+                    div_channels8<DIVM>(sgx, sgy, fC, gx1, gy1);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) e[k] = edge_from_u(a, gx1[k] * gx1[k] + gy1[k] * gy1[k]);
+                    if (a.e.edge) __stcs(reinterpret_cast<float4*>(a.e.edge + (size_t)b * hw + pix), make_float4(e[0], e[1], e[2], e[3]));
+                    if (BLEND) {
+                        const float w0 = wgt * e[0], w1 = wgt * e[1], w2 = wgt * e[2], w3 = wgt * e[3];
+                        if (NC) {
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) {
+                                const float4 o = make_float4(clamp01_fast(bs[c].x + w0), clamp01_fast(bs[c].y + w1),
+                                                             clamp01_fast(bs[c].z + w2), clamp01_fast(bs[c].w + w3));
+                                __stcs(reinterpret_cast<float4*>(out_b + c * hw + pix), o);
+                            }
+                        } else {
+                            for (int c = 0; c < C; ++c) {
+                                const float4 t = __ldg(reinterpret_cast<const float4*>(base_b + c * hw + pix));
+                                const float4 o = make_float4(clamp01_fast(t.x + w0), clamp01_fast(t.y + w1),
+                                                             clamp01_fast(t.z + w2), clamp01_fast(t.w + w3));
+                                __stcs(reinterpret_cast<float4*>(out_b + c * hw + pix), o);
+                            }
+                        }
+                    }
+                }
+            }
+        };
+        if (EE_FWD_CHUNK_IS_FULL(ra, rb, H)) body(full_t{}); else body(part_t{});
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// adjoint sliding stages.  Output rows p run over [pa, pb) in padded-frame coordinates: the chunk
+// that owns image row 0 also produces ring row -1 and folds it into row 0; the chunk that owns row
+// H-1 also produces ring row H and folds it into row H-1.  Ring columns -1 / W are produced by the
+// border groups (one scalar per row) and folded into columns 0 / W-1.  Zero extension: input rows
+// outside the image contribute zero partials.  A chunk is FULL when it has R rows and touches
+// neither image border: then there are no ring rows and no bounds checks.
+// -------------------------------------------------------------------------------------------
+struct AdjBorder { bool left, right; };
+
+// Sobel-adjoint partials of input row (a-row wa, b-row wb): HA = a(q-1) - a(q+1), HB = fma(.5, b(q-1)+b(q+1), b(q)),
+// plus the ring column partials for a border group.
+__device__ __forceinline__ void sobel_adj_partials(const Win& wa, const Win& wb, AdjBorder bd, float (&HA)[4], float (&HB)[4],
+                                                   float& HAr, float& HBr) {
+    HA[0] = wa.l - wa.m1; HA[1] = wa.m0 - wa.m2; HA[2] = wa.m1 - wa.m3; HA[3] = wa.m2 - wa.r;
+    HB[0] = fmaf(0.5f, wb.l + wb.m1, wb.m0); HB[1] = fmaf(0.5f, wb.m0 + wb.m2, wb.m1);
+    HB[2] = fmaf(0.5f, wb.m1 + wb.m3, wb.m2); HB[3] = fmaf(0.5f, wb.m2 + wb.r, wb.m3);
+    // ring column: left  q=-1: HA = 0 - a(0),   HB = fma(.5, 0 + b(0), 0)
+    //              right q=W : HA = a(W-1) - 0, HB = fma(.5, b(W-1) + 0, 0)
+    const float alo = bd.left ? 0.0f : wa.m3, ahi = bd.left ? wa.m0 : 0.0f;
+    HAr = alo - ahi;
+    HBr = fmaf(0.5f, 0.0f + (bd.left ? wb.m0 : wb.m3), 0.0f);
+}
+
+__device__ __forceinline__ void gauss_adj_partials(const Win& w, AdjBorder bd, float c0, float c1, float c2, float (&P)[4],
+                                                   float (&Q)[4], float& Pr, float& Qr) {
+    gauss_partials(w, c0, c1, c2, P, Q);
+    // ring column: e = g(q-1) + g(q+1) with one of them 0 and m = g(q) = 0
+    const float er = 0.0f + (bd.left ? w.m0 : w.m3);
+    Pr = fmaf(c1, 0.0f, c0 * er);
+    Qr = fmaf(c2, 0.0f, c1 * er);
+}
+
+// Generic adjoint sliding chunk.  LOADP(i, rin, valid) fills partial slot i%3 (zeros when !valid),
+// COMBINE(i, o) combines slots (i-2, i-1, i) into o[4] incl. the ring column, STORE(row, o) emits.
+template <int R, bool FULL, typename LoadP, typename Combine, typename Store>
+__device__ __forceinline__ void adj_chunk(int ra, int rb, int H, LoadP loadp, Combine combine, Store store) {
+    if constexpr (FULL) {
+#pragma unroll
+        for (int i = 0; i < R + 2; ++i) {
+            loadp(i, ra - 1 + i, true);
+            if (i >= 2) {
+                float o[4];
+                combine(i, o);
+                store(ra + i - 2, o);
+            }
+        }
+    } else {
+        const int pa = ra - (ra == 0 ? 1 : 0), pb = rb + (rb == H ? 1 : 0);      // output rows incl. ring rows
+        float hold[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int i = 0; i < R + 4; ++i) {
+            const int rin = ra - 2 + i;
+            if (rin >= pa - 1 && rin <= pb) loadp(i, rin, rin >= 0 && rin < H);
+            if (i >= 2) {
+                const int p = ra - 3 + i;                     // centre of the last three inputs
+                if (p >= pa && p < pb) {
+                    float o[4];
+                    combine(i, o);
+                    if (p == -1) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) hold[k] = o[k];                       // ring row above, folded into row 0
+                    } else if (p == H) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) o[k] = hold[k] + o[k];                // row H-1 + ring row below
+                        store(H - 1, o);
+                    } else {
+                        if (p == 0) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) o[k] = o[k] + hold[k];
+                        }
+                        if (p == H - 1) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) hold[k] = o[k];                   // wait for ring row H
+                        } else {
+                            store(p, o);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// backward.  smem regions (stride Wp): R1 = S then A (TH+8 rows), R2 = Bl then GB (TH+6), R3 = Bv (TH+4)
+// -------------------------------------------------------------------------------------------
+template <int NC, bool BLEND, int R>
+__global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const FastArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int DIVM = (NC == 1) ? 0 : (NC == 3 ? 1 : 2);
+    const int b = blockIdx.x / a.e.tiles_per_img;
+    const int ti = blockIdx.x - b * a.e.tiles_per_img;
+    const int H = a.e.H, W = a.e.W, Wp = a.Wp;
+    const int C = NC ? NC : a.e.C;
+    const int r0 = ti * a.e.TH, r1 = min(r0 + a.e.TH, H);
+    const int G = W >> 2;
+    const int tx = threadIdx.x % a.e.GX, ty = threadIdx.x / a.e.GX;
+    const size_t hw = (size_t)H * W;
+    const bool active = ty < a.e.RY;
+
+    float* R1 = smem;
+    float* R2 = R1 + (size_t)(a.e.TH + 8) * Wp;
+    float* R3 = R2 + (size_t)(a.e.TH + 6) * Wp;
+
+    const bool want_gx = (a.e.g_x != nullptr);
+    const int s_lo = max(r0 - 4, 0), s_hi = min(r1 + 4, H);
+    const int b_lo = max(r0 - 3, 0), b_hi = min(r1 + 3, H);
+    const int ab_lo = want_gx ? max(r0 - 2, 0) : r0, ab_hi = want_gx ? min(r1 + 2, H) : r1;
+    const int gb_lo = max(r0 - 1, 0), gb_hi = min(r1 + 1, H);
+    const float fC = a.e.fC, wgt = a.e.w;
+    const float c0 = a.e.c0, c1 = a.e.c1, c2 = a.e.c2;
+
+    float* S = R1; float* Bl = R2;
+    if (active) fast_stage_sum<NC, R>(a, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, G, tx, ty);
+    __syncthreads();
+    if (active) fast_stage_blur<R>(a, S, s_lo, Bl, b_lo, b_hi, G, tx, ty);
+    __syncthreads();
+
+    // ---- A / Bv = dL/dSgx, dL/dSgy on rows [ab_lo, ab_hi), zero pad columns ---------------------
+    float* A = R1; float* Bv = R3;
+    if (active) {
+        const float* base_b = a.e.base + (size_t)b * C * hw;
+        const float* gin_b = a.e.g_in + (size_t)b * (BLEND ? C : 1) * hw;
+        float* gbase_b = a.e.g_base ? a.e.g_base + (size_t)b * C * hw : nullptr;
+        EE_FOR_CHUNKS(ab_lo, ab_hi) {
+            const int col = g * 4, ra = ab_lo + ch * R, rb = min(ra + R, ab_hi);
+            const float* pbl = Bl + kPadL + col;
+            auto body = [&](auto tag) {
+                constexpr bool FULL = decltype(tag)::value;
+                float D[3][4], V[3][4];
+#pragma unroll
+                for (int i = 0; i < R + 2; ++i) {
+                    const int rin = ra - 1 + i;
+                    if (FULL || rin <= rb) {
+                        const int rc = FULL ? rin : min(max(rin, 0), H - 1);
+                        sobel_partials(ld_win(pbl + (rc - b_lo) * Wp), D[i % 3], V[i % 3]);
+                    }
+                    if (i >= 2 && (FULL || ra + i - 2 < rb)) {
+                        const int rout = ra + i - 2;
+                        const int pix = rout * W + col;
+                        float gx1[4], gy1[4], u[4], ge[4], sgx[4], sgy[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            sgx[k] = fmaf(0.5f, D[(i - 2) % 3][k] + D[i % 3][k], D[(i - 1) % 3][k]);
+                            sgy[k] = V[i % 3][k] - V[(i - 2) % 3][k];
+                        }
+                        div_channels8<DIVM>(sgx, sgy, fC, gx1, gy1);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) u[k] = gx1[k] * gx1[k] + gy1[k] * gy1[k];
+                        if (BLEND) {
+                            float we[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) we[k] = wgt * edge_from_u(a, u[k]);
+                            const bool interior = (rout >= r0 && rout < r1);
+                            float4 bs[NC ? NC : 1], go[NC ? NC : 1];
+                            if (NC) {
+#pragma unroll
+                                for (int c = 0; c < NC; ++c) {
+                                    bs[c] = __ldg(reinterpret_cast<const float4*>(base_b + c * hw + pix));
+                                    go[c] = __ldg(reinterpret_cast<const float4*>(gin_b + c * hw + pix));
+                                }
+                            }
+#pragma unroll 3
+                            for (int c = 0; c < C; ++c) {
+                                float4 bsc, goc;
+                                if (NC) { bsc = bs[NC ? c : 0]; goc = go[NC ? c : 0]; }
+                                else {
+                                    bsc = __ldg(reinterpret_cast<const float4*>(base_b + c * hw + pix));
+                                    goc = __ldg(reinterpret_cast<const float4*>(gin_b + c * hw + pix));
+                                }
+                                const float bsv[4] = {bsc.x, bsc.y, bsc.z, bsc.w}, gov[4] = {goc.x, goc.y, goc.z, goc.w};
+                                float gp[4];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const float pre = bsv[k] + we[k];
+                                    gp[k] = (pre >= 0.0f && pre <= 1.0f) ? gov[k] : 0.0f;
+                                    ge[k] = (c == 0) ? gp[k] * wgt : fmaf(gp[k], wgt, ge[k]);
+                                }
+                                if (gbase_b && interior)
+                                    __stcs(reinterpret_cast<float4*>(gbase_b + c * hw + pix), make_float4(gp[0], gp[1], gp[2], gp[3]));
+                            }
+                        } else {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(gin_b + pix));
+                            ge[0] = t.x; ge[1] = t.y; ge[2] = t.z; ge[3] = t.w;
+                        }
+                        if (want_gx) {
+                            float av[4], bv[4];
+                            bool any = false;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float win = (u[k] > a.hi_cut && u[k] <= a.w_cut) ? 1.0f : 0.0f;   // To_compare.backward
+                                float gm = ge[k] * win;
+                                if (u[k] < a.a_cut) gm = 0.0f;                                            // torch.where backward
+                                ge[k] = gm;
+                                av[k] = 0.0f; bv[k] = 0.0f;
+                                any = any || (gm != 0.0f && u[k] != 0.0f);
+                            }
+                            if (any) {          // ~5 % of pixels carry gradient: one branch per 4 pixels
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    if (ge[k] != 0.0f && u[k] != 0.0f) {
+                                        const float t = ge[k] / (sqrtf(u[k]) * fC);
+                                        av[k] = t * gx1[k];
+                                        bv[k] = t * gy1[k];
+                                    }
+                                }
+                            }
+                            const int q = (rout - ab_lo) * Wp + kPadL + col;
+                            st_plane(A + q, av, col == 0, col + 4 == W, 0.0f, 0.0f);
+                            st_plane(Bv + q, bv, col == 0, col + 4 == W, 0.0f, 0.0f);
+                        }
+                    }
+                }
+            };
+            if (EE_FWD_CHUNK_IS_FULL(ra, rb, H)) body(full_t{}); else body(part_t{});
+        }
+    }
+    if (!want_gx) return;
+    __syncthreads();
+
+    // ---- GB = fold(Sobel^T(A, Bv)) on rows [gb_lo, gb_hi), zero pad columns ---------------------
+    float* GB = R2;
+    if (active) {
+        EE_FOR_CHUNKS(gb_lo, gb_hi) {
+            const int col = g * 4, ra = gb_lo + ch * R, rb = min(ra + R, gb_hi);
+            const AdjBorder bd = {col == 0, col + 4 == W};
+            const bool ring = bd.left || bd.right;
+            float HA[3][4], HB[3][4], HAr[3], HBr[3];
+            const float* pA = A + kPadL + col;
+            const float* pB = Bv + kPadL + col;
+            auto loadp = [&](int i, int rin, bool valid) {
+                if (valid) {
+                    const int q = (rin - ab_lo) * Wp;
+                    sobel_adj_partials(ld_win(pA + q), ld_win(pB + q), bd, HA[i % 3], HB[i % 3], HAr[i % 3], HBr[i % 3]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { HA[i % 3][k] = 0.0f; HB[i % 3][k] = 0.0f; }
+                    HAr[i % 3] = 0.0f; HBr[i % 3] = 0.0f;
+                }
+            };
+            auto combine = [&](int i, float (&o)[4]) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float xa = fmaf(0.5f, HA[(i - 2) % 3][k] + HA[i % 3][k], HA[(i - 1) % 3][k]);
+                    const float yb = HB[(i - 2) % 3][k] - HB[i % 3][k];
+                    o[k] = xa + yb;
+                }
+                if (ring) {
+                    const float xa = fmaf(0.5f, HAr[(i - 2) % 3] + HAr[i % 3], HAr[(i - 1) % 3]);
+                    const float yb = HBr[(i - 2) % 3] - HBr[i % 3];
+                    const float t = xa + yb;
+                    if (bd.left) o[0] = o[0] + t; else o[3] = o[3] + t;
+                }
+            };
+            auto store = [&](int row, const float (&o)[4]) {
+                st_plane(GB + (row - gb_lo) * Wp + kPadL + col, o, bd.left, bd.right, 0.0f, 0.0f);
+            };
+            if (EE_FWD_CHUNK_IS_FULL(ra, rb, H)) adj_chunk<R, true>(ra, rb, H, loadp, combine, store);
+            else adj_chunk<R, false>(ra, rb, H, loadp, combine, store);
+        }
+    }
+    __syncthreads();
+
+    // ---- g_s rows [r0, r1) = fold(Gauss^T(GB)) -> g_x of every channel ---------------------------
+    if (active) {
+        float* gx_b = a.e.g_x + (size_t)b * C * hw;
+        EE_FOR_CHUNKS(r0, r1) {
+            const int col = g * 4, ra = r0 + ch * R, rb = min(ra + R, r1);
+            const AdjBorder bd = {col == 0, col + 4 == W};
+            const bool ring = bd.left || bd.right;
+            float P[3][4], Q[3][4], Pr[3], Qr[3];
+            const float* pG = GB + kPadL + col;
+            auto loadp = [&](int i, int rin, bool valid) {
+                if (valid) {
+                    gauss_adj_partials(ld_win(pG + (rin - gb_lo) * Wp), bd, c0, c1, c2, P[i % 3], Q[i % 3], Pr[i % 3], Qr[i % 3]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { P[i % 3][k] = 0.0f; Q[i % 3][k] = 0.0f; }
+                    Pr[i % 3] = 0.0f; Qr[i % 3] = 0.0f;
+                }
+            };
+            auto combine = [&](int i, float (&o)[4]) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) o[k] = (P[(i - 2) % 3][k] + Q[(i - 1) % 3][k]) + P[i % 3][k];
+                if (ring) {
+                    const float t = (Pr[(i - 2) % 3] + Qr[(i - 1) % 3]) + Pr[i % 3];
+                    if (bd.left) o[0] = o[0] + t; else o[3] = o[3] + t;
+                }
+            };
+            auto store = [&](int row, const float (&o)[4]) {
+                const float4 v = make_float4(o[0], o[1], o[2], o[3]);
+                float* pg = gx_b + row * W + col;
+                if (NC) {
+#pragma unroll
+                    for (int c = 0; c < (NC ? NC : 1); ++c) __stcs(reinterpret_cast<float4*>(pg + c * hw), v);
+                } else {
+                    for (int c = 0; c < C; ++c) __stcs(reinterpret_cast<float4*>(pg + c * hw), v);
+                }
+            };
+            if (EE_FWD_CHUNK_IS_FULL(ra, rb, H)) adj_chunk<R, true>(ra, rb, H, loadp, combine, store);
+            else adj_chunk<R, false>(ra, rb, H, loadp, combine, store);
+        }
+    }
+}
+
+}  // namespace ee

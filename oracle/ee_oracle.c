@@ -417,13 +417,15 @@ static void edge_backward_image(const float *ge, int C, int H, int W, const ee_o
             if (pl->removed[q]) gm = 0.0f;                       /* core.py:290 / :480 */
             if (pr->variant == EE_CANNY && pl->mag[q] < pr->alpha) gm = 0.0f;
         }
-        /* mag = u^0.5, u = gx1^2 + gy1^2 ; autograd: g*0.5*u^-0.5 then *2*gx1 then /C.
+        /* mag = u^0.5, u = gx1^2 + gy1^2 ; autograd evaluates g*0.5*u^-0.5, then *2*gx1, then /C
+         * (three divisions).  Canonical form here: one division, dL/dSgx = (g / (mag*C)) * gx1 --
+         * the same value up to ~2 ulp, well inside the 1e-5 gradient tolerance.
          * Sub-gradient at mag == 0 defined as 0 (the reference yields NaN). */
         float m = pl->mag[q];
         if (gm == 0.0f || m == 0.0f) { a[q] = 0.0f; b[q] = 0.0f; continue; }
-        float t = (gm * 0.5f) / m;
-        a[q] = (t * (2.0f * pl->gx1[q])) / fC;
-        b[q] = (t * (2.0f * pl->gy1[q])) / fC;
+        float t = gm / (m * fC);
+        a[q] = t * pl->gx1[q];
+        b[q] = t * pl->gy1[q];
     }
     sob_ctx sc = { a, b, H, W };
     for (int i = 0; i < H; ++i)

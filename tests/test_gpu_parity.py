@@ -53,20 +53,26 @@ SHAPES = [
     # B, C, H, W      (W % 4 == 0 -> 128-bit path, otherwise scalar path)
     (2, 3, 64, 64), (3, 1, 28, 28), (2, 3, 32, 32), (1, 3, 224, 224), (2, 3, 17, 23), (2, 2, 9, 12),
     (3, 1, 1, 1), (2, 3, 1, 8), (2, 3, 8, 1), (1, 4, 2, 2), (1, 3, 5, 4), (1, 3, 40, 300),
+    (2, 3, 4, 8), (1, 5, 13, 16), (1, 3, 9, 1028),
 ]
 VARIANT_MODES = [("step125", "hyst")] + [(v, m) for v in ("canny", "bpda") for m in ("hyst", "mix", "low", "raw")]
 
 
+# staging knob of ee_set_tuning: 0 = auto (tuned kernels where eligible, 4 rows per thread), 1 = generic
+# kernels only, 8 = tuned kernels with 8 rows per thread
+@pytest.mark.parametrize("staging", [0, 1, 8])
 @pytest.mark.parametrize("strip", [0, 1, 3, 7])
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("variant,mode", VARIANT_MODES)
-def test_edge_filter_fwd_bwd(variant, mode, shape, strip):
+def test_edge_filter_fwd_bwd(variant, mode, shape, strip, staging):
+    if staging != 0 and variant != "step125":
+        pytest.skip("only CannyFilter_step125_1 has a tuned kernel")
     B, C, H, W = shape
     low, high, hyst = T.MODES[mode]
     alpha = 0.05 if variant != "bpda" else 0.0
     pc, po = both_params(variant, alpha, low, high, hyst)
     x, base, g_out, g_edge = T.make_inputs(hash((variant, mode, shape)) % 10000, B, C, H, W)
-    _lib.load().ee_set_tuning(strip, strip, 0)
+    _lib.load().ee_set_tuning(strip, strip, staging)
     # module-level forward / backward
     assert_same("edge", F_ee.edge_map(cu(x), pc), O.edge_fwd(x, po))
     assert_same("g_x(edge)", F_ee.edge_map_backward(cu(g_edge), cu(x), pc), O.edge_bwd(g_edge, x, po))
