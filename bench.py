@@ -26,7 +26,6 @@ import argparse
 import json
 import os
 import sys
-import threading
 import time
 
 import numpy as np
@@ -88,54 +87,69 @@ def load_peaks():
 # ---------------------------------------------------------------------------------------------
 # clocks sampled DURING the timed region
 # ---------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    def __init__(self, index, period=0.004):
-        super().__init__(daemon=True)
-        self.index, self.period = index, period
-        self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._halt = threading.Event()
-        self.ok = False
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            self.ok = True
-        except Exception:
-            self.ok = False
+class ClockSampler:
+    """Samples SM clock and throttle reasons with a separate `nvidia-smi -lms` process (a Python thread is
+    starved by the launch loop) and keeps the samples whose timestamps fall inside the timed region."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
 
-    def run(self):
-        if not self.ok:
-            return
-        nv = self.nv
-        names = {
-            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
-            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
-            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
-            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
-            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
-        }
-        while not self._halt.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            self._halt.wait(self.period)
+    def __init__(self, index, period_ms=20):
+        import subprocess
+        import tempfile
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        self.t0 = self.t1 = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", str(period_ms)],
+                                         stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
 
     def stop(self):
-        self._halt.set()
-        if self.is_alive():
-            self.join(timeout=2)
-        med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        import datetime
+        time.sleep(0.05)
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        rows = []
+        try:
+            self.tmp.flush()
+            with open(self.tmp.name) as f:
+                for line in f:
+                    parts = [p.strip() for p in line.split(",")]
+                    if len(parts) < 7:
+                        continue
+                    try:
+                        ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                        rows.append((ts, float(parts[1]), float(parts[2]), parts[3:7]))
+                    except ValueError:
+                        continue
+            os.unlink(self.tmp.name)
+        except OSError:
+            pass
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "nvidia-smi unavailable"}
+        inside = [r for r in rows if self.t0 is not None and self.t0 <= r[0] <= self.t1]
+        note = "inside the timed region"
+        if not inside:          # region shorter than the sampling period: take the samples closest to it
+            mid = 0.5 * ((self.t0 or rows[-1][0]) + (self.t1 or rows[-1][0]))
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+            note = "nearest samples (timed region shorter than the sampling period)"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in inside for n, v in zip(names, r[3]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_max_mhz": inside[0][2], "reasons": reasons,
+                "samples": len(inside), "source": "nvidia-smi -lms 20, " + note}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -279,16 +293,19 @@ def run_ours(args):
         step()
     barrier()
     sampler = ClockSampler(local)
-    sampler.start()
+    for _ in range(2):          # keep the GPU under load while nvidia-smi starts up
+        step()
     records = []
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
     barrier()
+    sampler.begin()
     t_beg.record(stream)
     for _ in range(args.steps):
         launches += step(records)
     t_end.record(stream)
     barrier()
+    sampler.end()
     clocks = sampler.stop()
     ms = t_beg.elapsed_time(t_end)
     ms_t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -347,14 +364,20 @@ def run_ours(args):
 def run_e2e(args, torch, dist, dev, world, rank, core, attacks, canny, barrier):
     """attacks.PGD on a model whose front end is core.edge_enhance (base = x; the FFT low-pass is out of
     scope) and whose head is a per-channel mean -> 3-way cross-entropy (stand-in for the CNN).  Every
-    step copies the batch from pinned host memory and reads the adversarial examples back."""
-    import torch.nn.functional as F
+    step copies the batch from pinned host memory and reads the adversarial examples back; the batch
+    is cut into `E2E_CHUNKS` chunks issued round-robin on three CUDA streams (the library enqueues on
+    the caller's current stream), so H2D of one chunk, the kernels of another and D2H of a third overlap."""
+    E2E_CHUNKS, N_STREAMS = 8, 3
     B, S = args.batch, args.side
     shape = (B, 3, S, S)
     host_in = torch.rand(shape).pin_memory()
     host_out = torch.empty(shape).pin_memory()
     targets = torch.randint(0, 3, (B,), device=dev)
     low = None if args.variant == "step125" else LOW
+    bounds = [(i * B // E2E_CHUNKS, (i + 1) * B // E2E_CHUNKS) for i in range(E2E_CHUNKS)]
+    bounds = [(lo, hi) for lo, hi in bounds if hi > lo]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(N_STREAMS)]
+    main = torch.cuda.current_stream(dev)
 
     def model(x):
         z = core.edge_enhance(x, x, canny, W_BLEND, low, HIGH, True)
@@ -365,23 +388,32 @@ def run_e2e(args, torch, dist, dev, world, rank, core, attacks, canny, barrier):
         epsilon = EPS
 
     def step():
-        x = host_in.to(dev, non_blocking=True)
-        x_adv = attacks.PGD(model, A, x, targets, N_PGD, ALPHA)
-        with torch.no_grad():
-            model(x_adv)                                   # the training forward on the adversarial batch
-        host_out.copy_(x_adv, non_blocking=True)
-        return 0
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for i, (lo, hi) in enumerate(bounds):
+            st = streams[i % N_STREAMS]
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                x = host_in[lo:hi].to(dev, non_blocking=True)
+                x_adv = attacks.PGD(model, A, x, targets[lo:hi], N_PGD, ALPHA)
+                with torch.no_grad():
+                    model(x_adv)                               # the training forward on the adversarial batch
+                host_out[lo:hi].copy_(x_adv, non_blocking=True)
+                x.record_stream(st); x_adv.record_stream(st)
+        for st in streams:
+            join = torch.cuda.Event()
+            join.record(st)
+            main.wait_event(join)
 
-    stream = torch.cuda.current_stream(dev)
     for _ in range(3):
         step()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     steps = max(3, min(args.steps, 10))
-    e0.record(stream)
+    e0.record(main)
     for _ in range(steps):
         step()
-    e1.record(stream)
+    e1.record(main)
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -389,7 +421,8 @@ def run_e2e(args, torch, dist, dev, world, rank, core, attacks, canny, barrier):
     nbytes = B * 3 * S * S * 4
     return {"value": world * B * steps / (float(ms.item()) / 1e3), "unit": "images/s",
             "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": steps,
-            "api": "attacks.PGD(model=edge_enhance front end + mean/CE head, num_steps=10) + final forward"}
+            "api": "attacks.PGD(model=edge_enhance front end + mean/CE head, num_steps=10) + final forward; "
+                   "%d chunks on %d streams, pinned host buffers" % (len(bounds), N_STREAMS)}
 
 
 def run_sweep(torch, F_ee, canny, dev, peak):

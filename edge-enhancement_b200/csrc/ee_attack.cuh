@@ -14,9 +14,9 @@
 namespace ee {
 
 __device__ __forceinline__ float sgnf(float g) { return (float)((g > 0.0f) - (g < 0.0f)); }
-// torch.max / torch.min (binary): NaN in either operand wins
-__device__ __forceinline__ float maxn(float a, float b) { return (a != a) ? a : ((b != b) ? b : fmaxf(a, b)); }
-__device__ __forceinline__ float minn(float a, float b) { return (a != a) ? a : ((b != b) ? b : fminf(a, b)); }
+// torch.max / torch.min (binary): NaN in either operand wins -> one FMNMX.NAN each
+__device__ __forceinline__ float maxn(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float minn(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 
 // Generic elementwise driver: NIN inputs, one output, 128-bit path when everything is 16-byte
 // aligned.  Each thread keeps UNROLL independent 128-bit loads per input in flight.

@@ -129,12 +129,12 @@ int launch_fast(K kernel, const Launch& L, int B, const ee::FastArgs& a, cudaStr
 
 // The tuned kernels keep full-width strips in shared memory; beyond ~128 columns the strips get so
 // thin (or the CTA count per SM so low) that the generic kernels win (measured at 224 px), so wide
-// images stay on the generic path unless forced (staging 4 / 8).
+// images stay on the generic path unless forced (staging 4).
 bool fast_eligible(const ee::EdgeArgs& a, bool vec_ok) {
     const int st = g_staging.load();
     if (st == 1 || !vec_ok || a.W < 8 || a.H < 4) return false;
     if (!(std::isfinite(a.high) && std::isfinite(a.alpha) && fabsf(a.high) < 1e18f && fabsf(a.alpha) < 1e18f)) return false;
-    return a.W <= 128 || st == 4 || st == 8;
+    return a.W <= 128 || st == 4;
 }
 
 void fill_fast(ee::FastArgs& f, const ee::EdgeArgs& a, const Launch& L) {
@@ -153,11 +153,22 @@ void fill_fast(ee::FastArgs& f, const ee::EdgeArgs& a, const Launch& L) {
     f.Wp = a.W + ee::kPadW;
 }
 
-#define EE_DISPATCH_FAST(KERNEL, BLEND, RR, L, B, f, s, name)                                     \
+// Width-specialised instantiations for the hot shapes (Tiny-ImageNet 64, CIFAR 32, MNIST 28); any
+// other width uses the runtime-W instantiation (WT = 0) of the same kernel.
+#define EE_DISPATCH_FAST(KERNEL, BLEND, L, B, f, s, name)                                         \
     do {                                                                                          \
-        if ((f).e.C == 3) return launch_fast(KERNEL<3, BLEND, RR>, L, B, f, s, name);             \
-        if ((f).e.C == 1) return launch_fast(KERNEL<1, BLEND, RR>, L, B, f, s, name);             \
-        return launch_fast(KERNEL<0, BLEND, RR>, L, B, f, s, name);                               \
+        const int W_ = (f).e.W, C_ = (f).e.C;                                                     \
+        if (C_ == 3) {                                                                            \
+            if (W_ == 64) return launch_fast(KERNEL<3, BLEND, 4, 64>, L, B, f, s, name);          \
+            if (W_ == 32) return launch_fast(KERNEL<3, BLEND, 4, 32>, L, B, f, s, name);          \
+            return launch_fast(KERNEL<3, BLEND, 4, 0>, L, B, f, s, name);                         \
+        }                                                                                         \
+        if (C_ == 1) {                                                                            \
+            if (W_ == 28) return launch_fast(KERNEL<1, BLEND, 4, 28>, L, B, f, s, name);          \
+            if (W_ == 32) return launch_fast(KERNEL<1, BLEND, 4, 32>, L, B, f, s, name);          \
+            return launch_fast(KERNEL<1, BLEND, 4, 0>, L, B, f, s, name);                         \
+        }                                                                                         \
+        return launch_fast(KERNEL<0, BLEND, 4, 0>, L, B, f, s, name);                             \
     } while (0)
 
 // rows_fixed / rows_per_th: the kernel needs (rows_per_th*TH + rows_fixed) plane rows of W floats.
@@ -247,17 +258,12 @@ int edge_forward(const float* x, const float* base, float* out, float* edge, int
     cudaStream_t s = (cudaStream_t)stream;
     Launch L;
     if (p->variant == EE_VARIANT_STEP125 && fast_eligible(a, vec_ok)) {
-        const int R = (g_staging.load() == 8) ? 8 : 4;
-        rc = plan_fast(H, W, R, 2, 6, 4, 40 * 1024, g_th_fwd.load(), L);
+        rc = plan_fast(H, W, 4, 2, 6, 4, 40 * 1024, g_th_fwd.load(), L);
         if (rc) return rc;
         ee::FastArgs f;
         fill_fast(f, a, L);
-        if (R == 8) {
-            if (blend) EE_DISPATCH_FAST(ee::edge_fwd_step125_fast, true, 8, L, B, f, s, "edge_fwd_step125_fast");
-            else EE_DISPATCH_FAST(ee::edge_fwd_step125_fast, false, 8, L, B, f, s, "edge_fwd_step125_fast");
-        }
-        if (blend) EE_DISPATCH_FAST(ee::edge_fwd_step125_fast, true, 4, L, B, f, s, "edge_fwd_step125_fast");
-        else EE_DISPATCH_FAST(ee::edge_fwd_step125_fast, false, 4, L, B, f, s, "edge_fwd_step125_fast");
+        if (blend) EE_DISPATCH_FAST(ee::edge_fwd_step125_fast, true, L, B, f, s, "edge_fwd_step125_fast");
+        else EE_DISPATCH_FAST(ee::edge_fwd_step125_fast, false, L, B, f, s, "edge_fwd_step125_fast");
     }
     if (p->variant == EE_VARIANT_STEP125) {
         rc = plan(H, W, vec_ok, 2, 6, 4, 44 * 1024, g_th_fwd.load(), L);
@@ -287,17 +293,12 @@ int edge_backward(const float* g_in, const float* x, const float* base, float* g
     cudaStream_t s = (cudaStream_t)stream;
     Launch L;
     if (p->variant == EE_VARIANT_STEP125 && fast_eligible(a, vec_ok)) {
-        const int R = (g_staging.load() == 8) ? 8 : 4;
-        rc = plan_fast(H, W, R, 3, 18, 8, 62 * 1024, g_th_bwd.load(), L);
+        rc = plan_fast(H, W, 4, 3, 18, 8, 62 * 1024, g_th_bwd.load(), L);
         if (rc) return rc;
         ee::FastArgs f;
         fill_fast(f, a, L);
-        if (R == 8) {
-            if (blend) EE_DISPATCH_FAST(ee::edge_bwd_step125_fast, true, 8, L, B, f, s, "edge_bwd_step125_fast");
-            else EE_DISPATCH_FAST(ee::edge_bwd_step125_fast, false, 8, L, B, f, s, "edge_bwd_step125_fast");
-        }
-        if (blend) EE_DISPATCH_FAST(ee::edge_bwd_step125_fast, true, 4, L, B, f, s, "edge_bwd_step125_fast");
-        else EE_DISPATCH_FAST(ee::edge_bwd_step125_fast, false, 4, L, B, f, s, "edge_bwd_step125_fast");
+        if (blend) EE_DISPATCH_FAST(ee::edge_bwd_step125_fast, true, L, B, f, s, "edge_bwd_step125_fast");
+        else EE_DISPATCH_FAST(ee::edge_bwd_step125_fast, false, L, B, f, s, "edge_bwd_step125_fast");
     }
     if (p->variant == EE_VARIANT_STEP125) {
         rc = plan(H, W, vec_ok, 3, 18, 8, 56 * 1024, g_th_bwd.load(), L);

@@ -164,8 +164,9 @@ __device__ __forceinline__ float to_compare(float v, float thr) {
 // (safeSign(v - thr) + 1) / 2, utils/core.py:115-118,:299-310
 __device__ __forceinline__ float sign_step(float v, float thr) { return (v - thr > 0.0f) ? 1.0f : 0.0f; }
 // backward windows: To_compare.backward (core.py:350-358), BinaryConnectDeterministic.backward (:138-145)
-__device__ __forceinline__ float ste_window(float v, float thr) { return (v > thr && v <= 1.001f) ? 1.0f : 0.0f; }
-__device__ __forceinline__ float bcd_window(float v, float thr) { return (fabsf(v - thr) > 1.001f) ? 0.0f : 1.0f; }
+// (masked assignments grad_input[mask] = 0, i.e. a select: a non-finite gradient outside the window is 0)
+__device__ __forceinline__ float ste_sel(float g, float v, float thr) { return (v > thr && v <= 1.001f) ? g : 0.0f; }
+__device__ __forceinline__ float bcd_sel(float g, float v, float thr) { return (fabsf(v - thr) > 1.001f) ? 0.0f : g; }
 
 // torch.clamp(v, 0, 1): NaN propagates (fminf/fmaxf would drop it)
 __device__ __forceinline__ float clamp01_nan(float v) {

@@ -219,22 +219,22 @@ __global__ void __launch_bounds__(256) edge_fwd_canny_kernel(const EdgeArgs a) {
 __device__ __forceinline__ float g_thin_of(const EdgeArgs& a, int mode, float ge, float thin, int wih) {
     if (mode == MODE_RAW) return ge;
     if (a.variant == 1) {   // CannyFilter: (sign(.)+1)/2 with the BinaryConnect STE window
-        if (mode == MODE_LOW) return (0.5f * ge) * bcd_window(thin, a.low);
+        if (mode == MODE_LOW) return bcd_sel(0.5f * ge, thin, a.low);
         if (mode == MODE_MIX) {
             const float h = 0.5f * ge;
-            return (0.5f * h) * bcd_window(thin, a.low) + (0.5f * h) * bcd_window(thin, a.high);
+            return bcd_sel(0.5f * h, thin, a.low) + bcd_sel(0.5f * h, thin, a.high);
         }
-        return (0.5f * ge) * bcd_window(thin, a.high);   // hysteresis: only `high` is differentiable
+        return bcd_sel(0.5f * ge, thin, a.high);   // hysteresis: only `high` is differentiable
     }
     // CannyFilter_BPDA: To_compare / To_eq windows
     if (mode == MODE_MIX) {
         const float h = 0.5f * ge;
-        return h * ste_window(thin, a.low) + h * ste_window(thin, a.high);
+        return ste_sel(h, thin, a.low) + ste_sel(h, thin, a.high);
     }
     const float gt = ge * (float)wih;
     const float g_low = 0.5f * gt;
     const float g_high = ge + 0.5f * gt;
-    return g_low * ste_window(thin, a.low) + g_high * ste_window(thin, a.high);
+    return ste_sel(g_low, thin, a.low) + ste_sel(g_high, thin, a.high);
 }
 
 // -------------------------------------------------------------------------------------------

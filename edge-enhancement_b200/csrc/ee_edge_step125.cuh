@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(256) edge_bwd_step125_kernel(const EdgeArgs a)
             float av[VEC], bv[VEC];
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
-                float gm = ge[k] * ste_window(magm[k], a.high);          // To_compare.backward
+                float gm = ste_sel(ge[k], magm[k], a.high);              // To_compare.backward
                 if (mag[k] < a.alpha) gm = 0.0f;                         // torch.where backward
                 mag_backward(gm, mag[k], gx1[k], gy1[k], a.fC, av[k], bv[k]);
             }

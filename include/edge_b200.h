@@ -138,7 +138,7 @@ const char* ee_last_error(void); /* thread-local, never NULL */
 int ee_version(void);            /* EE_VERSION */
 
 /* Tuning knob for benchmarks/tests: force the row-strip height of the tiled edge kernels
- * (0 = heuristic) and the staging path (0 = auto, 1 = vectorised LDG, 2 = TMA bulk copy).
+ * (0 = heuristic) and the staging path (0 = auto, 1 = generic kernels only, 4 = tuned kernels even for wide images).
  * Process-wide; returns EE_OK.  Not needed for normal use. */
 int ee_set_tuning(int strip_rows_fwd, int strip_rows_bwd, int staging);
 

@@ -309,33 +309,35 @@ int ee_oracle_edge_blend_fwd(const float *x, const float *base, float *out, floa
  *            (core.py:319-321: weak / weak_is_high are integer tensors).
  *   BPDA   : To_compare / To_eq (core.py:482-503); closed form in SURVEY.md A.3.
  * ---------------------------------------------------------------------------------- */
-static inline float ste_window(float v, float thr) { return (v > thr && v <= 1.001f) ? 1.0f : 0.0f; }
-static inline float bcd_window(float v, float thr) { return (fabsf(v - thr) > 1.001f) ? 0.0f : 1.0f; }
+/* masked assignments of the reference (grad_input[mask] = 0): a SELECT, so a non-finite upstream
+ * gradient outside the window becomes 0, not NaN */
+static inline float ste_sel(float g, float v, float thr) { return (v > thr && v <= 1.001f) ? g : 0.0f; }
+static inline float bcd_sel(float g, float v, float thr) { return (fabsf(v - thr) > 1.001f) ? 0.0f : g; }
 
 static float g_thin_of(const ee_oracle_params *pr, const planes_t *pl, size_t q, float ge)
 {
     float th = pl->thin[q];
     if (!pr->has_low) return ge;
     if (pr->variant == EE_CANNY) {
-        if (!pr->has_high) return (0.5f * ge) * bcd_window(th, pr->low_thr);
+        if (!pr->has_high) return bcd_sel(0.5f * ge, th, pr->low_thr);
         if (!pr->hysteresis) {
             float h = 0.5f * ge;   /* d(low*.5 + high*.5) */
-            return (0.5f * h) * bcd_window(th, pr->low_thr) + (0.5f * h) * bcd_window(th, pr->high_thr);
+            return bcd_sel(0.5f * h, th, pr->low_thr) + bcd_sel(0.5f * h, th, pr->high_thr);
         }
-        return (0.5f * ge) * bcd_window(th, pr->high_thr);
+        return bcd_sel(0.5f * ge, th, pr->high_thr);
     }
     /* BPDA */
     if (!pr->has_high) return ge;           /* raw thinned magnitude is returned, see forward */
     if (!pr->hysteresis) {
         float h = 0.5f * ge;
-        return h * ste_window(th, pr->low_thr) + h * ste_window(th, pr->high_thr);
+        return ste_sel(h, th, pr->low_thr) + ste_sel(h, th, pr->high_thr);
     }
     {
         float wih = pl->wih[q] ? 1.0f : 0.0f;
         float gt = ge * wih;                        /* through To_eq(t) * weak_1 */
         float g_low = 0.5f * gt;
         float g_high = ge + 0.5f * gt;
-        return g_low * ste_window(th, pr->low_thr) + g_high * ste_window(th, pr->high_thr);
+        return ste_sel(g_low, th, pr->low_thr) + ste_sel(g_high, th, pr->high_thr);
     }
 }
 
@@ -410,7 +412,7 @@ static void edge_backward_image(const float *ge, int C, int H, int W, const ee_o
     for (size_t q = 0; q < hw; ++q) {
         float gm;
         if (pr->variant == EE_STEP125) {
-            gm = ge[q] * ste_window(pl->magm[q], pr->high_thr);
+            gm = ste_sel(ge[q], pl->magm[q], pr->high_thr);
             if (pl->mag[q] < pr->alpha) gm = 0.0f;              /* torch.where backward */
         } else {
             gm = g_thin_of(pr, pl, q, ge[q]);

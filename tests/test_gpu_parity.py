@@ -58,9 +58,9 @@ SHAPES = [
 VARIANT_MODES = [("step125", "hyst")] + [(v, m) for v in ("canny", "bpda") for m in ("hyst", "mix", "low", "raw")]
 
 
-# staging knob of ee_set_tuning: 0 = auto (tuned kernels where eligible, 4 rows per thread), 1 = generic
-# kernels only, 8 = tuned kernels with 8 rows per thread
-@pytest.mark.parametrize("staging", [0, 1, 8])
+# staging knob of ee_set_tuning: 0 = auto (tuned kernels for W <= 128), 1 = generic kernels only,
+# 4 = tuned kernels also for wide images
+@pytest.mark.parametrize("staging", [0, 1, 4])
 @pytest.mark.parametrize("strip", [0, 1, 3, 7])
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("variant,mode", VARIANT_MODES)
