@@ -46,7 +46,7 @@ N_PGD = 10
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="images per rank per step")
@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--variant", default="step125", choices=["step125", "canny", "bpda"])
     ap.add_argument("--cpu-images", type=int, default=2048, help="images in the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=3, help="chunks the e2e batch is pipelined in (3 streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--th-fwd", type=int, default=0)
     ap.add_argument("--th-bwd", type=int, default=0)
@@ -150,6 +151,36 @@ class ClockSampler:
         reasons = sorted({n for r in inside for n, v in zip(names, r[3]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median([r[1] for r in inside])), "sm_max_mhz": inside[0][2], "reasons": reasons,
                 "samples": len(inside), "source": "nvidia-smi -lms 20, " + note}
+
+
+def sample_clocks_until(index, done_event, period=0.002):
+    """NVML clock / throttle-reason samples taken by the launching thread while the already enqueued
+    timed steps are still executing (launches run far ahead of the GPU), i.e. under load."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+    except Exception:
+        return None
+    names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+             0x80: "hw_power_brake"}
+    samples, reasons = [], set()
+    while not done_event.query():
+        try:
+            samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            try:
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            reasons |= {n for bit, n in names.items() if mask & bit}
+        except Exception:
+            break
+        time.sleep(period)
+    if not samples:
+        return None
+    return {"sm_mhz": float(np.median(samples)), "sm_max_mhz": float(mx), "reasons": sorted(reasons),
+            "samples": len(samples), "source": "NVML polled by the launching thread while the timed steps execute"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -304,9 +335,12 @@ def run_ours(args):
     for _ in range(args.steps):
         launches += step(records)
     t_end.record(stream)
+    nvml_samples = sample_clocks_until(local, t_end)      # the GPU is still draining the queued launches
     barrier()
     sampler.end()
     clocks = sampler.stop()
+    if nvml_samples is not None and nvml_samples["samples"] > clocks.get("samples", 0):
+        clocks = nvml_samples
     ms = t_beg.elapsed_time(t_end)
     ms_t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -367,7 +401,7 @@ def run_e2e(args, torch, dist, dev, world, rank, core, attacks, canny, barrier):
     step copies the batch from pinned host memory and reads the adversarial examples back; the batch
     is cut into `E2E_CHUNKS` chunks issued round-robin on three CUDA streams (the library enqueues on
     the caller's current stream), so H2D of one chunk, the kernels of another and D2H of a third overlap."""
-    E2E_CHUNKS, N_STREAMS = 8, 3
+    E2E_CHUNKS, N_STREAMS = max(1, args.e2e_chunks), 3
     B, S = args.batch, args.side
     shape = (B, 3, S, S)
     host_in = torch.rand(shape).pin_memory()

@@ -61,8 +61,30 @@ def _out_like(x, out):
     return out
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream(t):
+    """cudaStream_t of the CURRENT stream of t's device (what autograd / DataParallel threads expect)."""
+    if _raw_stream is not None:
+        return ctypes.c_void_p(_raw_stream(t.device.index))
     return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+class _on_device:
+    """`with torch.cuda.device(t.device)` costs ~5 us per call; skip it when t's device is already current."""
+    __slots__ = ("guard",)
+
+    def __init__(self, t):
+        self.guard = None if t.device.index == torch.cuda.current_device() else torch.cuda.device(t.device)
+
+    def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            self.guard.__exit__(*exc)
 
 
 def _ptr(t):
@@ -81,7 +103,7 @@ def edge_map(x, params):
     edge = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
     if x.numel() == 0:
         return edge
-    with torch.cuda.device(x.device):
+    with _on_device(x):
         rc = _lib.load().ee_edge_fwd_f32(_ptr(x), _ptr(edge), B, C, H, W, ctypes.byref(params), _stream(x))
     _lib.check(rc, "ee_edge_fwd_f32")
     return edge
@@ -94,7 +116,7 @@ def edge_map_backward(g_edge, x, params):
     g_x = torch.empty_like(x)
     if x.numel() == 0:
         return g_x
-    with torch.cuda.device(x.device):
+    with _on_device(x):
         rc = _lib.load().ee_edge_bwd_f32(_ptr(g_edge), _ptr(x), _ptr(g_x), B, C, H, W, ctypes.byref(params), _stream(x))
     _lib.check(rc, "ee_edge_bwd_f32")
     return g_x
@@ -111,7 +133,7 @@ def edge_blend(x, base, params, w, want_edge=False, out=None):
     out = _out_like(x, out)
     edge = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device) if want_edge else None
     if x.numel():
-        with torch.cuda.device(x.device):
+        with _on_device(x):
             rc = _lib.load().ee_edge_blend_fwd_f32(_ptr(x), _ptr(base), _ptr(out), _ptr(edge), B, C, H, W,
                                                    ctypes.byref(params), float(w), _stream(x))
         _lib.check(rc, "ee_edge_blend_fwd_f32")
@@ -128,7 +150,7 @@ def edge_blend_backward(g_out, x, base, params, w, need_x=True, need_base=True, 
     g_x = _out_like(x, g_x) if need_x else None
     g_base = _out_like(x, g_base) if need_base else None
     if x.numel() and (need_x or need_base):
-        with torch.cuda.device(x.device):
+        with _on_device(x):
             rc = _lib.load().ee_edge_blend_bwd_f32(_ptr(g_out), _ptr(x), _ptr(base), _ptr(g_x), _ptr(g_base),
                                                    B, C, H, W, ctypes.byref(params), float(w), _stream(x))
         _lib.check(rc, "ee_edge_blend_bwd_f32")
@@ -152,7 +174,7 @@ def pgd_linf_step(x, grad, x0, alpha_signed, eps, lo=0.0, hi=1.0, out=None):
     x, grad, x0 = _same(x, grad, x0)
     out = _out_like(x, out)
     if x.numel():
-        with torch.cuda.device(x.device):
+        with _on_device(x):
             rc = _lib.load().ee_pgd_linf_step_f32(_ptr(x), _ptr(grad), _ptr(x0), _ptr(out), x.numel(),
                                                   float(alpha_signed), float(eps), float(lo), float(hi), _stream(x))
         _lib.check(rc, "ee_pgd_linf_step_f32")
@@ -163,7 +185,7 @@ def fgsm_step(x, grad, alpha_signed, lo=0.0, hi=1.0, out=None):
     x, grad = _same(x, grad)
     out = _out_like(x, out)
     if x.numel():
-        with torch.cuda.device(x.device):
+        with _on_device(x):
             rc = _lib.load().ee_fgsm_step_f32(_ptr(x), _ptr(grad), _ptr(out), x.numel(), float(alpha_signed),
                                               float(lo), float(hi), _stream(x))
         _lib.check(rc, "ee_fgsm_step_f32")
@@ -181,7 +203,7 @@ def free_at_step_(delta, grad, x0=None, alpha=0.0, eps=0.0, lo=0.0, hi=1.0, want
         x0 = _chk(x0, "x0", delta.shape)
         x_adv = torch.empty_like(delta)
     if delta.numel():
-        with torch.cuda.device(delta.device):
+        with _on_device(delta):
             rc = _lib.load().ee_free_at_step_f32(_ptr(delta), _ptr(grad), _ptr(x0 if want_adv else None), _ptr(x_adv),
                                                  delta.numel(), float(alpha), float(eps), float(lo), float(hi),
                                                  _stream(delta))
@@ -193,7 +215,7 @@ def cw_linf_step(adv, grad, x, min_x, max_x, step, magnitude, out=None):
     adv, grad, x, min_x, max_x = _same(adv, grad, x, min_x, max_x)
     out = _out_like(adv, out)
     if adv.numel():
-        with torch.cuda.device(adv.device):
+        with _on_device(adv):
             rc = _lib.load().ee_cw_linf_step_f32(_ptr(adv), _ptr(grad), _ptr(x), _ptr(min_x), _ptr(max_x), _ptr(out),
                                                  adv.numel(), float(step), float(magnitude), _stream(adv))
         _lib.check(rc, "ee_cw_linf_step_f32")
@@ -206,7 +228,7 @@ def pgd_l2_step(x, grad, x0, step, eps):
     out = torch.empty_like(x)
     if x.numel():
         B = x.shape[0]
-        with torch.cuda.device(x.device):
+        with _on_device(x):
             rc = _lib.load().ee_pgd_l2_step_f32(_ptr(x), _ptr(grad), _ptr(x0), _ptr(out), B, x.numel() // B,
                                                 float(step), float(eps), _stream(x))
         _lib.check(rc, "ee_pgd_l2_step_f32")
@@ -220,7 +242,7 @@ def _ew(name, args, n, ref, thr=None):
         if thr is not None:
             call.append(float(thr))
         call.append(_stream(ref))
-        with torch.cuda.device(ref.device):
+        with _on_device(ref):
             rc = getattr(_lib.load(), name)(*call)
         _lib.check(rc, name)
     return out

@@ -1,0 +1,120 @@
+"""-m gpu: BASELINE.json's full sizes.  Where the oracle finishes in seconds the comparison is direct
+(bit-exact); at sweep sizes it goes through size-independent properties: strip / kernel-choice
+invariance, batch-permutation equivariance, channel-identical gradients, mask consistency of g_base,
+range / idempotence of the projection."""
+import numpy as np
+import pytest
+import torch
+
+from tests import common as T
+
+pytestmark = pytest.mark.gpu
+
+from edge_enhancement_b200 import functional as F_ee, _lib   # noqa: E402
+from oracle import oracle as O                               # noqa: E402
+
+DEV = "cuda:0"
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.fixture(autouse=True)
+def _reset():
+    _lib.load().ee_set_tuning(0, 0, 0)
+    yield
+    _lib.load().ee_set_tuning(0, 0, 0)
+
+
+FULL = [
+    # config, variant, shape, alpha, low, high
+    ("M: MNIST 128x1x28x28 full Canny (ee_at_training.yml)", "canny", (128, 1, 28, 28), 0.3, 25 / 255, 51 / 255),
+    ("M: MNIST 128x1x28x28 step125", "step125", (128, 1, 28, 28), 0.0, None, 51 / 255),
+    ("T: Tiny 256x3x64x64 step125 (ee_at_bpda3_square.yml)", "step125", (256, 3, 64, 64), 0.0, None, 76 / 255),
+    ("T: Tiny 256x3x64x64 full Canny (ee_at_training.yml)", "canny", (256, 3, 64, 64), 0.0, 38 / 255, 76 / 255),
+    ("T: Tiny 256x3x64x64 BPDA", "bpda", (256, 3, 64, 64), 0.0, 38 / 255, 76 / 255),
+    ("I: ImageNet per-GPU 32x3x224x224 step125 (at_ee_training.yml)", "step125", (32, 3, 224, 224), 0.0, None, 76 / 255),
+]
+
+
+@pytest.mark.parametrize("cfg", FULL, ids=lambda c: c[0].split(":")[0] + "-" + c[1])
+def test_full_size_configs_bit_exact(cfg):
+    _, variant, shape, alpha, low, high = cfg
+    kind = "sparse" if shape[1] == 1 else "uniform"
+    x, base, g_out, _ = T.make_inputs(42, *shape, kind=kind)
+    g = O.gaussian3()
+    pc = F_ee.make_params(variant, g, alpha, low, high, True)
+    po = O.make_params(variant, alpha=alpha, low=low, high=high, hysteresis=True)
+    out = F_ee.edge_blend(cu(x), cu(base), pc, 1.0)
+    g_x, g_base = F_ee.edge_blend_backward(cu(g_out), cu(x), cu(base), pc, 1.0)
+    o_out = O.edge_blend_fwd(x, base, po, 1.0)
+    o_gx, o_gb = O.edge_blend_bwd(g_out, x, base, po, 1.0)
+    assert np.array_equal(out.cpu().numpy(), o_out)
+    assert np.array_equal(g_base.cpu().numpy(), o_gb)
+    assert np.array_equal(g_x.cpu().numpy(), o_gx)
+
+
+@pytest.mark.parametrize("variant", ["step125", "canny"])
+@pytest.mark.parametrize("shape", [(1024, 3, 64, 64), (192, 3, 224, 224), (2048, 3, 32, 32)], ids=str)
+def test_sweep_size_properties(variant, shape):
+    B, C, H, W = shape
+    gen = torch.Generator(device=DEV).manual_seed(7)
+    x = torch.rand(shape, device=DEV, generator=gen)
+    base = torch.rand(shape, device=DEV, generator=gen) * 1.1 - 0.1
+    g_out = torch.randn(shape, device=DEV, generator=gen)
+    low = None if variant == "step125" else T.LOW
+    p = F_ee.make_params(variant, O.gaussian3(), 0.0, low, T.HIGH, True)
+    L = _lib.load()
+
+    def run():
+        out, edge = F_ee.edge_blend(x, base, p, 1.0, want_edge=True)
+        g_x, g_base = F_ee.edge_blend_backward(g_out, x, base, p, 1.0)
+        return out, edge, g_x, g_base
+
+    ref = run()
+    # (1) the result does not depend on the strip height nor on which kernel family runs
+    for th, staging in ((5, 0), (16, 1), (11, 4)):
+        L.ee_set_tuning(th, th, staging)
+        for a, b in zip(ref, run()):
+            assert torch.equal(a, b), (th, staging)
+    L.ee_set_tuning(0, 0, 0)
+    out, edge, g_x, g_base = ref
+    # (2) images are independent: permuting the batch permutes the result
+    perm = torch.randperm(B, device=DEV, generator=gen)
+    out_p = F_ee.edge_blend(x[perm].contiguous(), base[perm].contiguous(), p, 1.0)
+    assert torch.equal(out_p, out[perm])
+    # (3) masks are binary, the blend is in range, every channel receives the same edge gradient
+    assert bool(((edge == 0) | (edge == 1)).all()) and 0.02 < float(edge.mean()) < 0.6
+    assert float(out.min()) >= 0 and float(out.max()) <= 1
+    assert torch.equal(out, torch.clamp(base + 1.0 * edge, 0, 1))              # blend identity, bit-exact
+    for c in range(1, C):
+        assert torch.equal(g_x[:, 0], g_x[:, c])
+    assert bool(torch.isfinite(g_x).all())
+    # (4) g_base is g_out under the inclusive clamp mask
+    pre = base + 1.0 * edge
+    mask = (pre >= 0) & (pre <= 1)
+    assert torch.equal(g_base, torch.where(mask, g_out, torch.zeros_like(g_out)))
+    # (5) linearity of the adjoint in the upstream gradient (exact for a power-of-two scale)
+    g_x2, g_base2 = F_ee.edge_blend_backward(2.0 * g_out, x, base, p, 1.0)
+    assert torch.equal(g_x2, 2.0 * g_x) and torch.equal(g_base2, 2.0 * g_base)
+
+
+@pytest.mark.parametrize("n", [4096 * 3 * 64 * 64, 1024 * 3 * 224 * 224 + 3])
+def test_pgd_step_properties_at_sweep_size(n):
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    eps, a = 16 / 255, 2 / 255
+    x0 = torch.rand(n, device=DEV, generator=gen)
+    x = torch.clamp(x0 + (torch.rand(n, device=DEV, generator=gen) * 2 - 1) * eps, 0, 1)
+    g = torch.randn(n, device=DEV, generator=gen)
+    g[::101] = 0
+    y = F_ee.pgd_linf_step(x, g, x0, a, eps)
+    ref = torch.clamp(torch.min(torch.max(x + a * torch.sign(g), x0 - eps), x0 + eps), 0, 1)   # attacks.py:25-27
+    assert torch.equal(y, ref)
+    assert float(y.min()) >= 0 and float(y.max()) <= 1
+    assert float((y - x0).abs().max()) <= eps + 2.5e-7          # x0 +- eps is rounded to fp32 before the compare
+    assert torch.equal(F_ee.pgd_linf_step(y, g, x0, 0.0, eps), y)               # projection is idempotent
+    assert torch.equal(y[::101], x[::101])                                      # sign(0) = 0
+    d = (x - x0).contiguous()
+    adv = F_ee.free_at_step_(d, g, x0, a, eps)
+    assert float(d.abs().max()) <= np.float32(eps) and torch.equal(adv, torch.clamp(x0 + d, 0, 1))
