@@ -3,6 +3,7 @@
 #include "../../include/edge_b200.h"
 #include "ee_attack.cuh"
 #include "ee_edge_canny.cuh"
+#include "ee_edge_canny_fast.cuh"
 #include "ee_edge_fast.cuh"
 #include "ee_edge_step125.cuh"
 
@@ -133,7 +134,8 @@ int launch_fast(K kernel, const Launch& L, int B, const ee::FastArgs& a, cudaStr
 bool fast_eligible(const ee::EdgeArgs& a, bool vec_ok) {
     const int st = g_staging.load();
     if (st == 1 || !vec_ok || a.W < 8 || a.H < 4) return false;
-    if (!(std::isfinite(a.high) && std::isfinite(a.alpha) && fabsf(a.high) < 1e18f && fabsf(a.alpha) < 1e18f)) return false;
+    if (!(std::isfinite(a.high) && std::isfinite(a.alpha) && std::isfinite(a.low) && fabsf(a.high) < 1e18f &&
+          fabsf(a.alpha) < 1e18f)) return false;
     return a.W <= 128 || st == 4;
 }
 
@@ -272,6 +274,14 @@ int edge_forward(const float* x, const float* base, float* out, float* edge, int
         if (blend) EE_DISPATCH(ee::edge_fwd_step125_kernel, true, L, B, a, s, "edge_fwd_step125");
         else EE_DISPATCH(ee::edge_fwd_step125_kernel, false, L, B, a, s, "edge_fwd_step125");
     }
+    if (fast_eligible(a, vec_ok)) {
+        rc = plan_fast(H, W, 4, ee::kCannyFastFwdRowsPerTH, ee::kCannyFastFwdRowsFixed, 8, 62 * 1024, g_th_fwd.load(), L);
+        if (rc) return rc;
+        ee::FastArgs f;
+        fill_fast(f, a, L);
+        if (blend) EE_DISPATCH_FAST(ee::edge_fwd_canny_fast, true, L, B, f, s, "edge_fwd_canny_fast");
+        else EE_DISPATCH_FAST(ee::edge_fwd_canny_fast, false, L, B, f, s, "edge_fwd_canny_fast");
+    }
     rc = plan(H, W, vec_ok, ee::kCannyFwdRowsPerTH, ee::kCannyFwdRowsFixed, 8, 64 * 1024, g_th_fwd.load(), L);
     if (rc) return rc;
     a.TH = L.TH; a.tiles_per_img = L.tiles; a.GX = L.GX; a.RY = L.RY;
@@ -306,6 +316,14 @@ int edge_backward(const float* g_in, const float* x, const float* base, float* g
         a.TH = L.TH; a.tiles_per_img = L.tiles; a.GX = L.GX; a.RY = L.RY;
         if (blend) EE_DISPATCH(ee::edge_bwd_step125_kernel, true, L, B, a, s, "edge_bwd_step125");
         else EE_DISPATCH(ee::edge_bwd_step125_kernel, false, L, B, a, s, "edge_bwd_step125");
+    }
+    if (fast_eligible(a, vec_ok)) {
+        rc = plan_fast(H, W, 4, ee::kCannyFastBwdRowsPerTH, ee::kCannyFastBwdRowsFixed, 12, 84 * 1024, g_th_bwd.load(), L);
+        if (rc) return rc;
+        ee::FastArgs f;
+        fill_fast(f, a, L);
+        if (blend) EE_DISPATCH_FAST(ee::edge_bwd_canny_fast, true, L, B, f, s, "edge_bwd_canny_fast");
+        else EE_DISPATCH_FAST(ee::edge_bwd_canny_fast, false, L, B, f, s, "edge_bwd_canny_fast");
     }
     rc = plan(H, W, vec_ok, ee::kCannyBwdRowsPerTH, ee::kCannyBwdRowsFixed, 12, 80 * 1024, g_th_bwd.load(), L);
     if (rc) return rc;

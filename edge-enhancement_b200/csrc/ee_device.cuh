@@ -173,21 +173,19 @@ __device__ __forceinline__ float clamp01_nan(float v) {
     return (v != v) ? v : fminf(fmaxf(v, 0.0f), 1.0f);
 }
 
-// Orientation bin of utils/core.py:258-260,:270 without atan: bin = round(atan(r)*8/pi + 4) mod 8,
-// whose boundaries are r = tan((k - 3.5) pi / 8); count the boundaries below r.  NaN (0/0) -> -1.
-__device__ __forceinline__ int orient_bin(float gx1, float gy1) {
-    const float r = gy1 / gx1;
-    if (r != r) return -1;
-    int k = 0;
-    k += (r > -5.02733949212584810451f);
-    k += (r > -1.49660576266548901760f);
-    k += (r > -0.66817863791929891999f);
-    k += (r > -0.19891236737965800691f);
-    k += (r > 0.19891236737965800691f);
-    k += (r > 0.66817863791929891999f);
-    k += (r > 1.49660576266548901760f);
-    k += (r > 5.02733949212584810451f);
-    return k & 7;
+// Direction pair used by non-maximum suppression (utils/core.py:258-260,:270,:275-281), evaluated without
+// atan or division: bin boundaries are |gy/gx| = t_i = tan((2i+1)pi/16); with a = |gx|, s = sign(gx)*gy,
+// m = #{i : |s| > t_i*a} and dir = (s > 0) ? m mod 4 : (4 - m) mod 4   (see oracle orient_dir).
+__device__ __forceinline__ int orient_dir(float gx1, float gy1) {
+    const float a = fabsf(gx1);
+    const float s = (gx1 < 0.0f) ? -gy1 : gy1;
+    const float as = fabsf(s);
+    int m = 0;
+    m += (as > 0.19891236737965800691f * a);
+    m += (as > 0.66817863791929891999f * a);
+    m += (as > 1.49660576266548901760f * a);
+    m += (as > 5.02733949212584810451f * a);
+    return (s > 0.0f) ? (m & 3) : ((4 - m) & 3);
 }
 
 // dL/d(mag) -> (dL/dSgx, dL/dSgy):  mag = u^.5, u = gx1^2 + gy1^2 ; autograd evaluates

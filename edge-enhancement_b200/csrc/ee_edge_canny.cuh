@@ -8,7 +8,7 @@
 //   S -> Bl -> (M = gated magnitude, META = orientation bin) -> NMS + double threshold (META gets
 //   low+high / high / removed bits) -> hysteresis (3x3 sum of low+high, zero padded) -> edge.
 // META is one 32-bit word per pixel:
-//   bits 0-3 : orientation bin + 1 (0 = undefined, gx = gy = 0)       core.py:258-260,:270
+//   bits 0-3 : NMS direction pair (orientation bin mod 4) + 1         core.py:258-260,:270
 //   bits 4-5 : low + high  (2*t of core.py:315)                        core.py:300-315 / :486-492
 //   bit  6   : high
 //   bit  7   : removed by non-maximum suppression                      core.py:275-290 / :463-480
@@ -52,7 +52,7 @@ __device__ __forceinline__ void stage_mag_bin(const EdgeArgs& a, const float* Bl
         for (int k = 0; k < VEC; ++k) {
             const float mag = magnitude(gx1[k], gy1[k]);
             mm[k] = (gate && mag < a.alpha) ? 0.0f : mag;
-            mt[k] = __int_as_float(orient_bin(gx1[k], gy1[k]) + 1);
+            mt[k] = __int_as_float(orient_dir(gx1[k], gy1[k]) + 1);
         }
         st_vec<VEC>(M + (size_t)(row - lo) * W + col, mm);
         st_vec<VEC>(META + (size_t)(row - lo) * W + col, mt);
@@ -74,11 +74,10 @@ __device__ __forceinline__ void nms_threshold(const EdgeArgs& a, const float* M,
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
         int w = __float_as_int(mt[k]) & 15;
-        const int bin = w - 1;
+        const int dir = w - 1;
         const float mc = m[k + 1];
         int removed = 0;
-        if (bin >= 0) {
-            const int dir = bin & 3;
+        {
             // -1 tap offsets (row,col): 0:(0,+1) 1:(-1,+1) 2:(-1,0) 3:(-1,-1) | 4:(0,-1) 5:(+1,-1) 6:(+1,0) 7:(+1,+1)
             const float n1 = (dir == 0) ? m[k + 2] : (dir == 1) ? u[k + 2] : (dir == 2) ? u[k + 1] : u[k];
             const float n2 = (dir == 0) ? m[k] : (dir == 1) ? d[k] : (dir == 2) ? d[k + 1] : d[k + 2];

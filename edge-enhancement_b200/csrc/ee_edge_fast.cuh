@@ -424,6 +424,96 @@ __device__ __forceinline__ void adj_chunk(int ra, int rb, int H, LoadP loadp, Co
     }
 }
 
+// GB rows [gb_lo, gb_hi) = fold(Sobel^T(A, Bv)), zero pad columns.  A / Bv planes start at row ab_lo.
+template <int R>
+__device__ __forceinline__ void fast_stage_sobel_adjoint(const Geo geo, const float* A, const float* Bv, int ab_lo,
+                                                         float* GB, int gb_lo, int gb_hi, int tx, int ty) {
+    const int W = geo.W, H = geo.H, Wp = geo.Wp;
+    EE_FOR_CHUNKS(gb_lo, gb_hi) {
+        const int col = g * 4, ra = gb_lo + ch * R, rb = min(ra + R, gb_hi);
+        const AdjBorder bd = {col == 0, col + 4 == W};
+        const bool ring = bd.left || bd.right;
+        float HA[3][4], HB[3][4], HAr[3], HBr[3];
+        const float* pA = A + kPadL + col;
+        const float* pB = Bv + kPadL + col;
+        auto loadp = [&](int i, int rin, bool valid) {
+            if (valid) {
+                const int q = (rin - ab_lo) * Wp;
+                sobel_adj_partials(ld_win(pA + q), ld_win(pB + q), bd, HA[i % 3], HB[i % 3], HAr[i % 3], HBr[i % 3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { HA[i % 3][k] = 0.0f; HB[i % 3][k] = 0.0f; }
+                HAr[i % 3] = 0.0f; HBr[i % 3] = 0.0f;
+            }
+        };
+        auto combine = [&](int i, float (&o)[4]) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float xa = fmaf(0.5f, HA[(i - 2) % 3][k] + HA[i % 3][k], HA[(i - 1) % 3][k]);
+                const float yb = HB[(i - 2) % 3][k] - HB[i % 3][k];
+                o[k] = xa + yb;
+            }
+            if (ring) {
+                const float xa = fmaf(0.5f, HAr[(i - 2) % 3] + HAr[i % 3], HAr[(i - 1) % 3]);
+                const float yb = HBr[(i - 2) % 3] - HBr[i % 3];
+                const float t = xa + yb;
+                if (bd.left) o[0] = o[0] + t; else o[3] = o[3] + t;
+            }
+        };
+        auto store = [&](int row, const float (&o)[4]) {
+            st_plane(GB + (row - gb_lo) * Wp + kPadL + col, o, bd.left, bd.right, 0.0f, 0.0f);
+        };
+        if (EE_FWD_CHUNK_IS_FULL(ra, rb, H)) adj_chunk<R, true>(ra, rb, H, loadp, combine, store);
+        else adj_chunk<R, false>(ra, rb, H, loadp, combine, store);
+    }
+}
+
+// g_s rows [r0, r1) = fold(Gauss^T(GB)), written to every channel of g_x (gx_b = image base pointer)
+template <int NC, int R>
+__device__ __forceinline__ void fast_stage_gauss_adjoint_store(const FastArgs& a, const Geo geo, const float* GB, int gb_lo,
+                                                               float* gx_b, int r0, int r1, int tx, int ty) {
+    const int W = geo.W, H = geo.H, Wp = geo.Wp;
+    const int C = NC ? NC : a.e.C;
+    const size_t hw = (size_t)H * W;
+    const float c0 = a.e.c0, c1 = a.e.c1, c2 = a.e.c2;
+    EE_FOR_CHUNKS(r0, r1) {
+        const int col = g * 4, ra = r0 + ch * R, rb = min(ra + R, r1);
+        const AdjBorder bd = {col == 0, col + 4 == W};
+        const bool ring = bd.left || bd.right;
+        float P[3][4], Q[3][4], Pr[3], Qr[3];
+        const float* pG = GB + kPadL + col;
+        auto loadp = [&](int i, int rin, bool valid) {
+            if (valid) {
+                gauss_adj_partials(ld_win(pG + (rin - gb_lo) * Wp), bd, c0, c1, c2, P[i % 3], Q[i % 3], Pr[i % 3], Qr[i % 3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { P[i % 3][k] = 0.0f; Q[i % 3][k] = 0.0f; }
+                Pr[i % 3] = 0.0f; Qr[i % 3] = 0.0f;
+            }
+        };
+        auto combine = [&](int i, float (&o)[4]) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = (P[(i - 2) % 3][k] + Q[(i - 1) % 3][k]) + P[i % 3][k];
+            if (ring) {
+                const float t = (Pr[(i - 2) % 3] + Qr[(i - 1) % 3]) + Pr[i % 3];
+                if (bd.left) o[0] = o[0] + t; else o[3] = o[3] + t;
+            }
+        };
+        auto store = [&](int row, const float (&o)[4]) {
+            const float4 v = make_float4(o[0], o[1], o[2], o[3]);
+            float* pg = gx_b + row * W + col;
+            if (NC) {
+#pragma unroll
+                for (int c = 0; c < (NC ? NC : 1); ++c) __stcs(reinterpret_cast<float4*>(pg + c * hw), v);
+            } else {
+                for (int c = 0; c < C; ++c) __stcs(reinterpret_cast<float4*>(pg + c * hw), v);
+            }
+        };
+        if (EE_FWD_CHUNK_IS_FULL(ra, rb, H)) adj_chunk<R, true>(ra, rb, H, loadp, combine, store);
+        else adj_chunk<R, false>(ra, rb, H, loadp, combine, store);
+    }
+}
+
 // -------------------------------------------------------------------------------------------
 // backward.  smem regions (stride Wp): R1 = S then A (TH+8 rows), R2 = Bl then GB (TH+6), R3 = Bv (TH+4)
 // -------------------------------------------------------------------------------------------
@@ -571,89 +661,11 @@ __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const 
     if (!want_gx) return;
     __syncthreads();
 
-    // ---- GB = fold(Sobel^T(A, Bv)) on rows [gb_lo, gb_hi), zero pad columns ---------------------
+    // ---- GB = fold(Sobel^T(A, Bv)) on rows [gb_lo, gb_hi) ; g_s rows [r0, r1) = fold(Gauss^T(GB)) -> g_x -------
     float* GB = R2;
-    if (active) {
-        EE_FOR_CHUNKS(gb_lo, gb_hi) {
-            const int col = g * 4, ra = gb_lo + ch * R, rb = min(ra + R, gb_hi);
-            const AdjBorder bd = {col == 0, col + 4 == W};
-            const bool ring = bd.left || bd.right;
-            float HA[3][4], HB[3][4], HAr[3], HBr[3];
-            const float* pA = A + kPadL + col;
-            const float* pB = Bv + kPadL + col;
-            auto loadp = [&](int i, int rin, bool valid) {
-                if (valid) {
-                    const int q = (rin - ab_lo) * Wp;
-                    sobel_adj_partials(ld_win(pA + q), ld_win(pB + q), bd, HA[i % 3], HB[i % 3], HAr[i % 3], HBr[i % 3]);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { HA[i % 3][k] = 0.0f; HB[i % 3][k] = 0.0f; }
-                    HAr[i % 3] = 0.0f; HBr[i % 3] = 0.0f;
-                }
-            };
-            auto combine = [&](int i, float (&o)[4]) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float xa = fmaf(0.5f, HA[(i - 2) % 3][k] + HA[i % 3][k], HA[(i - 1) % 3][k]);
-                    const float yb = HB[(i - 2) % 3][k] - HB[i % 3][k];
-                    o[k] = xa + yb;
-                }
-                if (ring) {
-                    const float xa = fmaf(0.5f, HAr[(i - 2) % 3] + HAr[i % 3], HAr[(i - 1) % 3]);
-                    const float yb = HBr[(i - 2) % 3] - HBr[i % 3];
-                    const float t = xa + yb;
-                    if (bd.left) o[0] = o[0] + t; else o[3] = o[3] + t;
-                }
-            };
-            auto store = [&](int row, const float (&o)[4]) {
-                st_plane(GB + (row - gb_lo) * Wp + kPadL + col, o, bd.left, bd.right, 0.0f, 0.0f);
-            };
-            if (EE_FWD_CHUNK_IS_FULL(ra, rb, H)) adj_chunk<R, true>(ra, rb, H, loadp, combine, store);
-            else adj_chunk<R, false>(ra, rb, H, loadp, combine, store);
-        }
-    }
+    if (active) fast_stage_sobel_adjoint<R>(geo, A, Bv, ab_lo, GB, gb_lo, gb_hi, tx, ty);
     __syncthreads();
-
-    // ---- g_s rows [r0, r1) = fold(Gauss^T(GB)) -> g_x of every channel ---------------------------
-    if (active) {
-        float* gx_b = a.e.g_x + (size_t)b * C * hw;
-        EE_FOR_CHUNKS(r0, r1) {
-            const int col = g * 4, ra = r0 + ch * R, rb = min(ra + R, r1);
-            const AdjBorder bd = {col == 0, col + 4 == W};
-            const bool ring = bd.left || bd.right;
-            float P[3][4], Q[3][4], Pr[3], Qr[3];
-            const float* pG = GB + kPadL + col;
-            auto loadp = [&](int i, int rin, bool valid) {
-                if (valid) {
-                    gauss_adj_partials(ld_win(pG + (rin - gb_lo) * Wp), bd, c0, c1, c2, P[i % 3], Q[i % 3], Pr[i % 3], Qr[i % 3]);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { P[i % 3][k] = 0.0f; Q[i % 3][k] = 0.0f; }
-                    Pr[i % 3] = 0.0f; Qr[i % 3] = 0.0f;
-                }
-            };
-            auto combine = [&](int i, float (&o)[4]) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) o[k] = (P[(i - 2) % 3][k] + Q[(i - 1) % 3][k]) + P[i % 3][k];
-                if (ring) {
-                    const float t = (Pr[(i - 2) % 3] + Qr[(i - 1) % 3]) + Pr[i % 3];
-                    if (bd.left) o[0] = o[0] + t; else o[3] = o[3] + t;
-                }
-            };
-            auto store = [&](int row, const float (&o)[4]) {
-                const float4 v = make_float4(o[0], o[1], o[2], o[3]);
-                float* pg = gx_b + row * W + col;
-                if (NC) {
-#pragma unroll
-                    for (int c = 0; c < (NC ? NC : 1); ++c) __stcs(reinterpret_cast<float4*>(pg + c * hw), v);
-                } else {
-                    for (int c = 0; c < C; ++c) __stcs(reinterpret_cast<float4*>(pg + c * hw), v);
-                }
-            };
-            if (EE_FWD_CHUNK_IS_FULL(ra, rb, H)) adj_chunk<R, true>(ra, rb, H, loadp, combine, store);
-            else adj_chunk<R, false>(ra, rb, H, loadp, combine, store);
-        }
-    }
+    if (active) fast_stage_gauss_adjoint_store<NC, R>(a, geo, GB, gb_lo, a.e.g_x + (size_t)b * C * hw, r0, r1, tx, ty);
 }
 
 }  // namespace ee

@@ -126,22 +126,24 @@ static void sobel3_replicate(const float *b, int H, int W, int C, float *D, floa
     }
 }
 
-/* Orientation bin of core.py:258-260,270:  atan(gy/gx)*(360/pi)+180 -> round(/45)*45 -> (/45)%8.
- * v = atan(r)*8/pi + 4 in [0,8]; bin = round(v) mod 8; the boundaries v = k+.5 are at
- * r = tan((k-3.5)*pi/8).  Canonical form: count the boundaries below r (no atan; see
- * DESIGN.md).  0/0 = NaN matches no direction (-1). */
-static const float EE_TAN_BOUNDS[8] = {
-    -5.02733949212584810451f, -1.49660576266548901760f, -0.66817863791929891999f,
-    -0.19891236737965800691f,  0.19891236737965800691f,  0.66817863791929891999f,
-     1.49660576266548901760f,  5.02733949212584810451f };
+/* Orientation of core.py:258-260,270:  atan(gy/gx)*(360/pi)+180 -> round(/45)*45 -> (/45)%8, of which
+ * NMS only uses the direction pair `bin mod 4` (core.py:275-281).  With v = atan(r)*8/pi + 4, r = gy/gx,
+ * bin = round(v) mod 8 and the bin boundaries are at |r| = t_i = tan((2i+1)*pi/16), i = 0..3:
+ *     m = #{ i : |r| > t_i } ;  dir = (r > 0) ? m mod 4 : (4 - m) mod 4
+ * Canonical form (no atan, no division): with a = |gx|, s = sign(gx)*gy,  |r| > t_i  <=>  |s| > t_i*a.
+ * gx = 0, gy != 0 gives r = +-inf -> dir 0, as in the reference (atan(+-inf) -> bin 0 or 8).  gx = gy = 0
+ * (the reference's NaN orientation, no direction) has magnitude 0, so its direction is immaterial. */
+static const float EE_TAN_T[4] = { 0.19891236737965800691f, 0.66817863791929891999f,
+                                   1.49660576266548901760f, 5.02733949212584810451f };
 
-static inline int orient_bin(float gx1, float gy1)
+static inline int orient_dir(float gx1, float gy1)
 {
-    float r = gy1 / gx1;
-    if (r != r) return -1;
-    int k = 0;
-    for (int t = 0; t < 8; ++t) k += (r > EE_TAN_BOUNDS[t]);
-    return k & 7;
+    const float a = fabsf(gx1);
+    const float s = (gx1 < 0.0f) ? -gy1 : gy1;
+    const float as = fabsf(s);
+    int m = 0;
+    for (int i = 0; i < 4; ++i) m += (as > EE_TAN_T[i] * a);
+    return (s > 0.0f) ? (m & 3) : ((4 - m) & 3);
 }
 
 /* (row, col) offset of the -1 tap of directional kernel k (core.py:87-112; cv2 output). */
@@ -192,10 +194,9 @@ static void edge_forward_image(const float *x, int C, int H, int W, const ee_ora
     for (int i = 0; i < H; ++i)
         for (int j = 0; j < W; ++j) {
             size_t q = (size_t)i * W + j;
-            int bin = orient_bin(pl->gx1[q], pl->gy1[q]);
             int rem = 0;
-            if (bin >= 0) {
-                int k = bin & 3;
+            {
+                int k = orient_dir(pl->gx1[q], pl->gy1[q]);
                 float m = pl->magm[q];
                 int i1 = i + EE_DIR_DR[k], j1 = j + EE_DIR_DC[k];
                 int i2 = i + EE_DIR_DR[k + 4], j2 = j + EE_DIR_DC[k + 4];

@@ -118,3 +118,41 @@ def test_pgd_step_properties_at_sweep_size(n):
     d = (x - x0).contiguous()
     adv = F_ee.free_at_step_(d, g, x0, a, eps)
     assert float(d.abs().max()) <= np.float32(eps) and torch.equal(adv, torch.clamp(x0 + d, 0, 1))
+
+
+def test_cuda_graph_capture_of_one_pgd_iteration():
+    """The library allocates nothing and never synchronises, so a whole hot-path iteration (fused forward,
+    fused backward, PGD step) can be captured in a CUDA graph and replayed with identical results."""
+    shape = (256, 3, 64, 64)                      # BASELINE configs[1] batch
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    x0 = torch.rand(shape, device=DEV, generator=gen)
+    x = torch.clamp(x0 + (torch.rand(shape, device=DEV, generator=gen) * 2 - 1) * (16 / 255), 0, 1)
+    base = torch.rand(shape, device=DEV, generator=gen) * 1.1 - 0.1
+    g_out = torch.randn(shape, device=DEV, generator=gen)
+    p = F_ee.make_params("step125", O.gaussian3(), 0.0, None, T.HIGH, False)
+    out, g_x, g_base, x_new = (torch.empty_like(x) for _ in range(4))
+
+    def iteration():
+        F_ee.edge_blend(x, base, p, 1.0, out=out)
+        F_ee.edge_blend_backward(g_out, x, base, p, 1.0, g_x=g_x, g_base=g_base)
+        F_ee.pgd_linf_step(x, g_x, x0, 2 / 255, 16 / 255, out=x_new)
+
+    iteration()
+    torch.cuda.synchronize()
+    want = [t.clone() for t in (out, g_x, g_base, x_new)]
+    for t in (out, g_x, g_base, x_new):
+        t.zero_()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        iteration()                                # warm-up on the capture stream
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        iteration()
+    for t in (out, g_x, g_base, x_new):
+        t.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    for got, ref in zip((out, g_x, g_base, x_new), want):
+        assert torch.equal(got, ref)
