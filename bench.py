@@ -75,6 +75,18 @@ def shard_sizes(total, world):
     return [base + (1 if r < rem else 0) for r in range(world)]
 
 
+def ncu_traffic(kernel, shape, variant):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture, if it was taken on this shape."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        if list(t["shape"]) == list(shape) and t["variant"] == variant:
+            return t[kernel]["dram_read_bytes"] + t[kernel]["dram_write_bytes"]
+    except Exception:
+        pass
+    return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -364,8 +376,11 @@ def run_ours(args):
     share = {"edge_blend_fwd": 11 * fwd_ms, "edge_blend_bwd": 10 * bwd_ms, "pgd_linf_step": 10 * pgd_ms}
     dom = max(share, key=share.get)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
-                "share_of_step": share[dom] / sum(share.values())}
+                "frac": kern[dom]["gbs"] / peak, "traffic": ncu_traffic(dom, [B, 3, S, S], args.variant),
+                "traffic_unit": "bytes per launch (dram read + write, ncu --set full capture in profiles/)",
+                "algorithmic_bytes_per_launch": {"edge_blend_fwd": BYTES_FWD_PX, "edge_blend_bwd": BYTES_BWD_PX,
+                                                 "pgd_linf_step": BYTES_PGD_ELT * 3}[dom] * npx,
+                "peak_source": peak_src, "share_of_step": share[dom] / sum(share.values())}
 
     # ---- end to end through the public API with host buffers ---------------------------------
     e2e = None

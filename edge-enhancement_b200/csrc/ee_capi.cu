@@ -53,7 +53,7 @@ int check_params(const EEParams* p, float& c0, float& c1, float& c2) {
     return EE_OK;
 }
 
-struct Launch { int vec, threads, GX, RY, TH, tiles; size_t smem; };
+struct Launch { int vec, threads, GX, RY, TH, tiles; size_t smem; int TW, tiles_x, planeW, halo; };
 
 // ---- exact threshold cut-offs in u = mag^2 space (sqrt_rn is monotonic) ----------------------
 float f_of(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
@@ -80,12 +80,23 @@ float cut_lt(float alpha) {
     return nextafterf(m, INFINITY);
 }
 
-// Launch plan of the tuned (fast) kernels: padded plane rows, R rows per thread chunk.
+// Launch plan of the tuned (fast) kernels: tiles of TH rows x TW columns; planes are (TW + 8 halo) columns
+// wide with 8 floats of padding per row; R rows per thread chunk.  Images up to 128 columns use one
+// column tile (full-width strips); wider ones are cut into ~64-column tiles.
 int plan_fast(int H, int W, int R, int rows_per_th, int rows_fixed, int max_halo_rows, int budget_bytes, int forced_th,
-              Launch& L) {
+              Launch& L, int halo_cols = 4) {
     L.vec = 4;
-    const int G = W / 4;
-    const size_t row_bytes = (size_t)(W + ee::kPadW) * sizeof(float);
+    L.halo = halo_cols;
+    if (W <= 128) { L.tiles_x = 1; L.TW = W; L.planeW = W; }
+    else {
+        L.tiles_x = (W + 63) / 64;
+        int tw = (W + L.tiles_x - 1) / L.tiles_x;
+        L.TW = (tw + 3) & ~3;
+        L.tiles_x = (W + L.TW - 1) / L.TW;
+        L.planeW = L.TW + 2 * halo_cols;
+    }
+    const int G = L.planeW / 4;
+    const size_t row_bytes = (size_t)(L.planeW + ee::kPadW) * sizeof(float);
     auto smem_of = [&](int th) { return (size_t)(rows_per_th * th + rows_fixed) * row_bytes; };
     int th;
     if (forced_th > 0) {
@@ -97,9 +108,9 @@ int plan_fast(int H, int W, int R, int rows_per_th, int rows_fixed, int max_halo
         th = (H + tiles - 1) / tiles;
     }
     while (th > 1 && smem_of(th) > (size_t)kMaxSmem) --th;
-    if (smem_of(th) > (size_t)kMaxSmem) return fail(EE_ERR_TOO_LARGE, "row strip of width %d does not fit in shared memory", W);
+    if (smem_of(th) > (size_t)kMaxSmem) return fail(EE_ERR_TOO_LARGE, "tile of %d columns does not fit in shared memory", L.planeW);
     L.TH = th;
-    L.tiles = (H + th - 1) / th;
+    L.tiles = ((H + th - 1) / th) * L.tiles_x;
     L.smem = smem_of(th);
     const int max_chunks = (th + max_halo_rows + R - 1) / R;
     if (G >= kThreads) { L.GX = kThreads; L.RY = 1; }
@@ -128,15 +139,10 @@ int launch_fast(K kernel, const Launch& L, int B, const ee::FastArgs& a, cudaStr
     return EE_OK;
 }
 
-// The tuned kernels keep full-width strips in shared memory; beyond ~128 columns the strips get so
-// thin (or the CTA count per SM so low) that the generic kernels win (measured at 224 px), so wide
-// images stay on the generic path unless forced (staging 4).
 bool fast_eligible(const ee::EdgeArgs& a, bool vec_ok) {
-    const int st = g_staging.load();
-    if (st == 1 || !vec_ok || a.W < 8 || a.H < 4) return false;
-    if (!(std::isfinite(a.high) && std::isfinite(a.alpha) && std::isfinite(a.low) && fabsf(a.high) < 1e18f &&
-          fabsf(a.alpha) < 1e18f)) return false;
-    return a.W <= 128 || st == 4;
+    if (g_staging.load() == 1 || !vec_ok || a.W < 8 || a.H < 4) return false;
+    return std::isfinite(a.high) && std::isfinite(a.alpha) && std::isfinite(a.low) && fabsf(a.high) < 1e18f &&
+           fabsf(a.alpha) < 1e18f;
 }
 
 void fill_fast(ee::FastArgs& f, const ee::EdgeArgs& a, const Launch& L) {
@@ -152,25 +158,29 @@ void fill_fast(ee::FastArgs& f, const ee::EdgeArgs& a, const Launch& L) {
         if (below > f.e_cut) f.e_cut = below;
     }
     f.zero_val = (0.0f > a.high) ? 1.0f : 0.0f;
-    f.Wp = a.W + ee::kPadW;
+    f.Wp = L.planeW + ee::kPadW;
+    f.TW = L.TW;
+    f.tiles_x = L.tiles_x;
+    f.halo = L.halo;
 }
 
-// Width-specialised instantiations for the hot shapes (Tiny-ImageNet 64, CIFAR 32, MNIST 28); any
-// other width uses the runtime-W instantiation (WT = 0) of the same kernel.
+// Specialised instantiations <NC, BLEND, rows/thread, plane width WT, global width WG> for the hot shapes
+// (Tiny-ImageNet 64, CIFAR 32, MNIST 28 as single column tiles; 64-wide planes of column-tiled 224 px
+// images); everything else runs the runtime-width instantiation <.., 0, 0> of the same kernel.
 #define EE_DISPATCH_FAST(KERNEL, BLEND, L, B, f, s, name)                                         \
     do {                                                                                          \
         const int W_ = (f).e.W, C_ = (f).e.C;                                                     \
-        if (C_ == 3) {                                                                            \
-            if (W_ == 64) return launch_fast(KERNEL<3, BLEND, 4, 64>, L, B, f, s, name);          \
-            if (W_ == 32) return launch_fast(KERNEL<3, BLEND, 4, 32>, L, B, f, s, name);          \
-            return launch_fast(KERNEL<3, BLEND, 4, 0>, L, B, f, s, name);                         \
+        if ((L).tiles_x == 1) {                                                                   \
+            if (C_ == 3 && W_ == 64) return launch_fast(KERNEL<3, BLEND, 4, 64, 64>, L, B, f, s, name); \
+            if (C_ == 3 && W_ == 32) return launch_fast(KERNEL<3, BLEND, 4, 32, 32>, L, B, f, s, name); \
+            if (C_ == 1 && W_ == 28) return launch_fast(KERNEL<1, BLEND, 4, 28, 28>, L, B, f, s, name); \
+            if (C_ == 1 && W_ == 32) return launch_fast(KERNEL<1, BLEND, 4, 32, 32>, L, B, f, s, name); \
+        } else if (C_ == 3 && (L).planeW == 64) {                                                 \
+            return launch_fast(KERNEL<3, BLEND, 4, 64, 0>, L, B, f, s, name);                     \
         }                                                                                         \
-        if (C_ == 1) {                                                                            \
-            if (W_ == 28) return launch_fast(KERNEL<1, BLEND, 4, 28>, L, B, f, s, name);          \
-            if (W_ == 32) return launch_fast(KERNEL<1, BLEND, 4, 32>, L, B, f, s, name);          \
-            return launch_fast(KERNEL<1, BLEND, 4, 0>, L, B, f, s, name);                         \
-        }                                                                                         \
-        return launch_fast(KERNEL<0, BLEND, 4, 0>, L, B, f, s, name);                             \
+        if (C_ == 3) return launch_fast(KERNEL<3, BLEND, 4, 0, 0>, L, B, f, s, name);             \
+        if (C_ == 1) return launch_fast(KERNEL<1, BLEND, 4, 0, 0>, L, B, f, s, name);             \
+        return launch_fast(KERNEL<0, BLEND, 4, 0, 0>, L, B, f, s, name);                          \
     } while (0)
 
 // rows_fixed / rows_per_th: the kernel needs (rows_per_th*TH + rows_fixed) plane rows of W floats.
@@ -318,7 +328,7 @@ int edge_backward(const float* g_in, const float* x, const float* base, float* g
         else EE_DISPATCH(ee::edge_bwd_step125_kernel, false, L, B, a, s, "edge_bwd_step125");
     }
     if (fast_eligible(a, vec_ok)) {
-        rc = plan_fast(H, W, 4, ee::kCannyFastBwdRowsPerTH, ee::kCannyFastBwdRowsFixed, 12, 84 * 1024, g_th_bwd.load(), L);
+        rc = plan_fast(H, W, 4, ee::kCannyFastBwdRowsPerTH, ee::kCannyFastBwdRowsFixed, 12, 84 * 1024, g_th_bwd.load(), L, 8);
         if (rc) return rc;
         ee::FastArgs f;
         fill_fast(f, a, L);

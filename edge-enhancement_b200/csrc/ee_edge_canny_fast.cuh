@@ -34,8 +34,8 @@ __device__ __forceinline__ void cfast_stage_mag_dir(const FastArgs& a, const Geo
     const float fC = a.e.fC;
     const bool gate = (a.e.variant == 1);            // only CannyFilter applies alpha (core.py:263-264)
     EE_FOR_CHUNKS(lo, hi) {
-        const int col = g * 4, ra = lo + ch * R, rb = min(ra + R, hi);
-        const float* pbl = Bl + kPadL + col;
+        const int lc = g * 4, col = geo.cs + lc, ra = lo + ch * R, rb = min(ra + R, hi);
+        const float* pbl = Bl + kPadL + lc;
         float D[3][4], V[3][4];
 #pragma unroll
         for (int i = 0; i < R + 2; ++i) {
@@ -58,7 +58,7 @@ __device__ __forceinline__ void cfast_stage_mag_dir(const FastArgs& a, const Geo
                     mm[k] = (gate && mag < a.e.alpha) ? 0.0f : mag;
                     mt[k] = __int_as_float(orient_dir(gx1[k], gy1[k]) + 1);
                 }
-                const int q = (ra + i - 2 - lo) * Wp + kPadL + col;
+                const int q = (ra + i - 2 - lo) * Wp + kPadL + lc;
                 st_plane(M + q, mm, col == 0, col + 4 == W, 0.0f, 0.0f);
                 st_plane(META + q, mt, col == 0, col + 4 == W, 0.0f, 0.0f);
             }
@@ -140,8 +140,9 @@ __device__ __forceinline__ void cfast_stage_nms(const FastArgs& a, const Geo geo
                                                 int lo, int hi, int b, int mode, int tx, int ty) {
     const int W = geo.W, H = geo.H, Wp = geo.Wp;
     EE_FOR_CHUNKS(lo, hi) {
-        const int col = g * 4, ra = lo + ch * R, rb = min(ra + R, hi);
-        const float* pm = M + kPadL + col;
+        const int lc = g * 4, col = geo.cs + lc, ra = lo + ch * R, rb = min(ra + R, hi);
+        if (EMIT && (col < geo.c0 || col >= geo.c1)) continue;   // halo groups produce no output
+        const float* pm = M + kPadL + lc;
         Win wm[3];
 #pragma unroll
         for (int i = 0; i < R + 2; ++i) {
@@ -149,7 +150,7 @@ __device__ __forceinline__ void cfast_stage_nms(const FastArgs& a, const Geo geo
             if (rin <= rb) wm[i % 3] = (rin >= 0 && rin < H) ? ld_win(pm + (rin - m_lo) * Wp) : zero_win();
             if (i >= 2 && ra + i - 2 < rb) {
                 const int p = ra + i - 2;
-                float* pmeta = META + (p - m_lo) * Wp + kPadL + col;
+                float* pmeta = META + (p - m_lo) * Wp + kPadL + lc;
                 const float4 mt = *reinterpret_cast<const float4*>(pmeta);
                 float thin[4];
                 int meta[4];
@@ -171,13 +172,14 @@ __device__ __forceinline__ void cfast_stage_nms(const FastArgs& a, const Geo geo
 // -------------------------------------------------------------------------------------------
 // forward
 // -------------------------------------------------------------------------------------------
-template <int NC, bool BLEND, int R, int WT>
+template <int NC, bool BLEND, int R, int WT, int WG>
 __global__ void __launch_bounds__(256, 3) edge_fwd_canny_fast(const FastArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int DIVM = (NC == 1) ? 0 : (NC == 3 ? 1 : 2);
-    const Geo geo = make_geo<WT>(a);
     const int b = blockIdx.x / a.e.tiles_per_img;
-    const int ti = blockIdx.x - b * a.e.tiles_per_img;
+    const int tq = blockIdx.x - b * a.e.tiles_per_img;
+    const int ti = tq / a.tiles_x;                                   // row-strip index; column tile = tq % tiles_x
+    const Geo geo = make_geo<WT, WG>(a, tq - ti * a.tiles_x);
     const int H = geo.H, W = geo.W, Wp = geo.Wp;
     const int C = NC ? NC : a.e.C;
     const int r0 = ti * a.e.TH, r1 = min(r0 + a.e.TH, H);
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(256, 3) edge_fwd_canny_fast(const FastArgs a) 
     const int m_lo = max(r0 - 1 - hc, 0), m_hi = min(r1 + 1 + hc, H);
 
 #if EE_L2_PREFETCH
-    if (BLEND && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
+    if (BLEND && a.tiles_x == 1 && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
 #endif
     float* S = R1; float* Bl = R2;
     if (active) fast_stage_sum<NC, R>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
@@ -216,8 +218,9 @@ __global__ void __launch_bounds__(256, 3) edge_fwd_canny_fast(const FastArgs a) 
     // hysteresis (core.py:317-321 / :494-503): weak = (low+high == 1), kept if the zero-padded 3x3 sum of
     // (low+high) is >= 2; edge = high + weak_is_high
     EE_FOR_CHUNKS(r0, r1) {
-        const int col = g * 4, ra = r0 + ch * R, rb = min(ra + R, r1);
-        const float* pmt = META + kPadL + col;
+        const int lc = g * 4, col = geo.cs + lc, ra = r0 + ch * R, rb = min(ra + R, r1);
+        if (col < geo.c0 || col >= geo.c1) continue;             // halo groups produce no output
+        const float* pmt = META + kPadL + lc;
         int hs[3][4], cw[3][4];
 #pragma unroll
         for (int i = 0; i < R + 2; ++i) {
@@ -241,13 +244,14 @@ __global__ void __launch_bounds__(256, 3) edge_fwd_canny_fast(const FastArgs a) 
 // -------------------------------------------------------------------------------------------
 // backward
 // -------------------------------------------------------------------------------------------
-template <int NC, bool BLEND, int R, int WT>
+template <int NC, bool BLEND, int R, int WT, int WG>
 __global__ void __launch_bounds__(256, 2) edge_bwd_canny_fast(const FastArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int DIVM = (NC == 1) ? 0 : (NC == 3 ? 1 : 2);
-    const Geo geo = make_geo<WT>(a);
     const int b = blockIdx.x / a.e.tiles_per_img;
-    const int ti = blockIdx.x - b * a.e.tiles_per_img;
+    const int tq = blockIdx.x - b * a.e.tiles_per_img;
+    const int ti = tq / a.tiles_x;                                   // row-strip index; column tile = tq % tiles_x
+    const Geo geo = make_geo<WT, WG>(a, tq - ti * a.tiles_x);
     const int H = geo.H, W = geo.W, Wp = geo.Wp;
     const int C = NC ? NC : a.e.C;
     const int r0 = ti * a.e.TH, r1 = min(r0 + a.e.TH, H);
@@ -296,9 +300,9 @@ __global__ void __launch_bounds__(256, 2) edge_bwd_canny_fast(const FastArgs a) 
         float* gbase_b = a.e.g_base ? a.e.g_base + (size_t)b * C * hw : nullptr;
         const bool gate = (a.e.variant == 1);
         EE_FOR_CHUNKS(ab_lo, ab_hi) {
-            const int col = g * 4, ra = ab_lo + ch * R, rb = min(ra + R, ab_hi);
-            const float* pbl = Bl + kPadL + col;
-            const float* pmt = META + kPadL + col;
+            const int lc = g * 4, col = geo.cs + lc, ra = ab_lo + ch * R, rb = min(ra + R, ab_hi);
+            const float* pbl = Bl + kPadL + lc;
+            const float* pmt = META + kPadL + lc;
             float D[3][4], V[3][4];
             int hs[3][4], cw[3][4];
 #pragma unroll
@@ -346,7 +350,7 @@ __global__ void __launch_bounds__(256, 2) edge_bwd_canny_fast(const FastArgs a) 
                                                                 : edge_value_simple(mode, thin[k], meta[k]);
                             we[k] = wgt * e;
                         }
-                        const bool interior = (rout >= r0 && rout < r1);
+                        const bool interior = (rout >= r0 && rout < r1 && col >= geo.c0 && col < geo.c1);
                         for (int c = 0; c < C; ++c) {
                             const float4 bsc = __ldg(reinterpret_cast<const float4*>(base_b + c * hw + pix));
                             const float4 goc = __ldg(reinterpret_cast<const float4*>(gin_b + c * hw + pix));
@@ -374,7 +378,7 @@ __global__ void __launch_bounds__(256, 2) edge_bwd_canny_fast(const FastArgs a) 
                             if (gate && mag[k] < a.e.alpha) gm = 0.0f;                // torch.where backward
                             mag_backward(gm, mag[k], gx1[k], gy1[k], fC, av[k], bv[k]);
                         }
-                        const int q = (rout - ab_lo) * Wp + kPadL + col;
+                        const int q = (rout - ab_lo) * Wp + kPadL + lc;
                         st_plane(A + q, av, col == 0, col + 4 == W, 0.0f, 0.0f);
                         st_plane(Bv + q, bv, col == 0, col + 4 == W, 0.0f, 0.0f);
                     }

@@ -36,7 +36,10 @@ struct FastArgs {
     float a_cut;      // mag <  alpha  <=> u < a_cut
     float e_cut;      // (mag > high and not mag < alpha) <=> u > e_cut
     float zero_val;   // To_compare's value for "not above": 1 if high < 0 else 0 (core.py:344-345)
-    int Wp;           // plane row stride in floats (W + 8)
+    int Wp;           // plane row stride in floats (plane width + 8)
+    int TW;           // columns per tile (multiple of 4; == W for a single column tile)
+    int tiles_x;      // column tiles per image
+    int halo;         // plane halo columns on each side of a column tile (4, or 8 for the Canny backward)
 };
 
 // (sgx, sgy)[4] / C, value-identical to the IEEE division.  DIVM: 0 -> C == 1, 1 -> C == 3, 2 -> any C.
@@ -109,22 +112,32 @@ __device__ __forceinline__ float clamp01_fast(float v) {
 // Tile geometry.  When the kernel is specialised on the image width (WT != 0) W, Wp, G and GX are
 // compile-time constants, so every row stride becomes an immediate offset and the integer address
 // arithmetic (a quarter of the executed instructions in the round-1 profile) disappears.
-struct Geo { int W, Wp, H, G, GX, RY; };
-template <int WT>
-__device__ __forceinline__ Geo make_geo(const FastArgs& a) {
+// A tile is rows [r0,r1) x columns [c0,c1) of one image; its planes cover columns [cs,ce) = the tile plus
+// `halo` columns on each side (one float4 group; two for the Canny backward, whose dependency cone is 6
+// columns), clipped to the image.  Images up to 128 columns wide use a
+// single column tile (cs = 0, ce = W: exactly the full-width strips of round 1); wider images are cut into
+// column tiles so that the planes stay small enough for 3 CTAs per SM.
+struct Geo { int W, Wp, H, GX, RY, cs, ce, c0, c1, Gt; };
+template <int WT, int WG>
+__device__ __forceinline__ Geo make_geo(const FastArgs& a, int tile_x) {
     Geo q;
-    q.W = WT ? WT : a.e.W;
-    q.Wp = WT ? WT + kPadW : a.Wp;
+    q.W = WG ? WG : a.e.W;                     // global row stride
+    q.Wp = WT ? WT + kPadW : a.Wp;             // plane row stride (WT = plane width incl. halo groups)
     q.H = a.e.H;
-    q.G = q.W >> 2;
-    q.GX = WT ? (WT >> 2) : a.e.GX;          // host guarantees GX == G whenever G <= 256
+    q.GX = WT ? (WT >> 2) : a.e.GX;            // host guarantees GX == plane groups whenever that is <= 256
     q.RY = a.e.RY;
+    q.c0 = tile_x * a.TW;
+    q.c1 = min(q.c0 + a.TW, q.W);
+    q.cs = max(q.c0 - a.halo, 0);
+    q.ce = min(q.c1 + a.halo, q.W);
+    if (WG && WG == WT) { q.c0 = 0; q.c1 = WG; q.cs = 0; q.ce = WG; }     // single column tile, all constant
+    q.Gt = (q.ce - q.cs) >> 2;
     return q;
 }
 
 #define EE_FOR_CHUNKS(row_lo, row_hi)                                                         \
     for (int ch = ty, n_ch = ((row_hi) - (row_lo) + R - 1) / R; ch < n_ch; ch += geo.RY)      \
-        for (int g = tx; g < geo.G; g += geo.GX)
+        for (int g = tx; g < geo.Gt; g += geo.GX)
 
 // Every chunk body exists twice: FULL (all R rows present, no image border inside the chunk: no
 // guards, no clamps) and the guarded general version.  `full_t` / `part_t` select them.
@@ -148,9 +161,9 @@ __device__ __forceinline__ void fast_stage_sum(const FastArgs& a, const Geo geo,
     const int C = NC ? NC : a.e.C;
     const size_t hw = (size_t)geo.H * W;
     EE_FOR_CHUNKS(lo, hi) {
-        const int col = g * 4, ra = lo + ch * R;
+        const int lc = g * 4, col = geo.cs + lc, ra = lo + ch * R;
         const float* px = xb + (size_t)ra * W + col;
-        float* ps = S + (size_t)(ra - lo) * Wp + kPadL + col;
+        float* ps = S + (size_t)(ra - lo) * Wp + kPadL + lc;
         auto body = [&](auto tag) {
             constexpr bool FULL = decltype(tag)::value;
             float4 acc[R];
@@ -214,9 +227,9 @@ __device__ __forceinline__ void fast_stage_blur(const FastArgs& a, const Geo geo
     const int W = geo.W, H = geo.H, Wp = geo.Wp;
     const float c0 = a.e.c0, c1 = a.e.c1, c2 = a.e.c2;
     EE_FOR_CHUNKS(lo, hi) {
-        const int col = g * 4, ra = lo + ch * R, rb = min(ra + R, hi);
-        const float* ps = S + kPadL + col;                 // row r at ps + (r - s_lo) * Wp
-        float* pb = Bl + (size_t)(ra - lo) * Wp + kPadL + col;
+        const int lc = g * 4, col = geo.cs + lc, ra = lo + ch * R, rb = min(ra + R, hi);
+        const float* ps = S + kPadL + lc;                 // row r at ps + (r - s_lo) * Wp
+        float* pb = Bl + (size_t)(ra - lo) * Wp + kPadL + lc;
         auto body = [&](auto tag) {
             constexpr bool FULL = decltype(tag)::value;
             float P[3][4], Q[3][4];
@@ -249,7 +262,7 @@ __device__ __forceinline__ void sobel_partials(const Win& w, float (&D)[4], floa
 // -------------------------------------------------------------------------------------------
 // forward:  planes S (TH+4 rows) and Bl (TH+2 rows), both with stride Wp
 // -------------------------------------------------------------------------------------------
-template <int NC, bool BLEND, int R, int WT>
+template <int NC, bool BLEND, int R, int WT, int WG>
 #ifndef EE_MINB_FWD
 #define EE_MINB_FWD 3
 #endif
@@ -259,9 +272,10 @@ template <int NC, bool BLEND, int R, int WT>
 __global__ void __launch_bounds__(256, EE_MINB_FWD) edge_fwd_step125_fast(const FastArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int DIVM = (NC == 1) ? 0 : (NC == 3 ? 1 : 2);
-    const Geo geo = make_geo<WT>(a);
     const int b = blockIdx.x / a.e.tiles_per_img;
-    const int ti = blockIdx.x - b * a.e.tiles_per_img;
+    const int tq = blockIdx.x - b * a.e.tiles_per_img;
+    const int ti = tq / a.tiles_x;                                   // row-strip index; column tile = tq % tiles_x
+    const Geo geo = make_geo<WT, WG>(a, tq - ti * a.tiles_x);
     const int H = geo.H, W = geo.W, Wp = geo.Wp;
     const int C = NC ? NC : a.e.C;
     const int r0 = ti * a.e.TH, r1 = min(r0 + a.e.TH, H);
@@ -274,7 +288,7 @@ __global__ void __launch_bounds__(256, EE_MINB_FWD) edge_fwd_step125_fast(const 
     float* Bl = smem + (size_t)(a.e.TH + 4) * Wp;
 
 #if EE_L2_PREFETCH
-    if (BLEND && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
+    if (BLEND && a.tiles_x == 1 && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
 #endif
     if (ty < geo.RY) fast_stage_sum<NC, R>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
     __syncthreads();
@@ -286,8 +300,9 @@ __global__ void __launch_bounds__(256, EE_MINB_FWD) edge_fwd_step125_fast(const 
     const float* base_b = a.e.base + (size_t)b * C * hw;
     float* out_b = a.e.out + (size_t)b * C * hw;
     EE_FOR_CHUNKS(r0, r1) {
-        const int col = g * 4, ra = r0 + ch * R, rb = min(ra + R, r1);
-        const float* pbl = Bl + kPadL + col;
+        const int lc = g * 4, col = geo.cs + lc, ra = r0 + ch * R, rb = min(ra + R, r1);
+        if (col < geo.c0 || col >= geo.c1) continue;             // halo groups produce no output
+        const float* pbl = Bl + kPadL + lc;
         auto body = [&](auto tag) {
             constexpr bool FULL = decltype(tag)::value;
             float D[3][4], V[3][4];
@@ -430,12 +445,12 @@ __device__ __forceinline__ void fast_stage_sobel_adjoint(const Geo geo, const fl
                                                          float* GB, int gb_lo, int gb_hi, int tx, int ty) {
     const int W = geo.W, H = geo.H, Wp = geo.Wp;
     EE_FOR_CHUNKS(gb_lo, gb_hi) {
-        const int col = g * 4, ra = gb_lo + ch * R, rb = min(ra + R, gb_hi);
+        const int lc = g * 4, col = geo.cs + lc, ra = gb_lo + ch * R, rb = min(ra + R, gb_hi);
         const AdjBorder bd = {col == 0, col + 4 == W};
         const bool ring = bd.left || bd.right;
         float HA[3][4], HB[3][4], HAr[3], HBr[3];
-        const float* pA = A + kPadL + col;
-        const float* pB = Bv + kPadL + col;
+        const float* pA = A + kPadL + lc;
+        const float* pB = Bv + kPadL + lc;
         auto loadp = [&](int i, int rin, bool valid) {
             if (valid) {
                 const int q = (rin - ab_lo) * Wp;
@@ -461,7 +476,7 @@ __device__ __forceinline__ void fast_stage_sobel_adjoint(const Geo geo, const fl
             }
         };
         auto store = [&](int row, const float (&o)[4]) {
-            st_plane(GB + (row - gb_lo) * Wp + kPadL + col, o, bd.left, bd.right, 0.0f, 0.0f);
+            st_plane(GB + (row - gb_lo) * Wp + kPadL + lc, o, bd.left, bd.right, 0.0f, 0.0f);
         };
         if (EE_FWD_CHUNK_IS_FULL(ra, rb, H)) adj_chunk<R, true>(ra, rb, H, loadp, combine, store);
         else adj_chunk<R, false>(ra, rb, H, loadp, combine, store);
@@ -477,11 +492,12 @@ __device__ __forceinline__ void fast_stage_gauss_adjoint_store(const FastArgs& a
     const size_t hw = (size_t)H * W;
     const float c0 = a.e.c0, c1 = a.e.c1, c2 = a.e.c2;
     EE_FOR_CHUNKS(r0, r1) {
-        const int col = g * 4, ra = r0 + ch * R, rb = min(ra + R, r1);
+        const int lc = g * 4, col = geo.cs + lc, ra = r0 + ch * R, rb = min(ra + R, r1);
+        if (col < geo.c0 || col >= geo.c1) continue;             // halo groups produce no output
         const AdjBorder bd = {col == 0, col + 4 == W};
         const bool ring = bd.left || bd.right;
         float P[3][4], Q[3][4], Pr[3], Qr[3];
-        const float* pG = GB + kPadL + col;
+        const float* pG = GB + kPadL + lc;
         auto loadp = [&](int i, int rin, bool valid) {
             if (valid) {
                 gauss_adj_partials(ld_win(pG + (rin - gb_lo) * Wp), bd, c0, c1, c2, P[i % 3], Q[i % 3], Pr[i % 3], Qr[i % 3]);
@@ -517,13 +533,14 @@ __device__ __forceinline__ void fast_stage_gauss_adjoint_store(const FastArgs& a
 // -------------------------------------------------------------------------------------------
 // backward.  smem regions (stride Wp): R1 = S then A (TH+8 rows), R2 = Bl then GB (TH+6), R3 = Bv (TH+4)
 // -------------------------------------------------------------------------------------------
-template <int NC, bool BLEND, int R, int WT>
+template <int NC, bool BLEND, int R, int WT, int WG>
 __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const FastArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int DIVM = (NC == 1) ? 0 : (NC == 3 ? 1 : 2);
-    const Geo geo = make_geo<WT>(a);
     const int b = blockIdx.x / a.e.tiles_per_img;
-    const int ti = blockIdx.x - b * a.e.tiles_per_img;
+    const int tq = blockIdx.x - b * a.e.tiles_per_img;
+    const int ti = tq / a.tiles_x;                                   // row-strip index; column tile = tq % tiles_x
+    const Geo geo = make_geo<WT, WG>(a, tq - ti * a.tiles_x);
     const int H = geo.H, W = geo.W, Wp = geo.Wp;
     const int C = NC ? NC : a.e.C;
     const int r0 = ti * a.e.TH, r1 = min(r0 + a.e.TH, H);
@@ -566,8 +583,8 @@ __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const 
         const float* gin_b = a.e.g_in + (size_t)b * (BLEND ? C : 1) * hw;
         float* gbase_b = a.e.g_base ? a.e.g_base + (size_t)b * C * hw : nullptr;
         EE_FOR_CHUNKS(ab_lo, ab_hi) {
-            const int col = g * 4, ra = ab_lo + ch * R, rb = min(ra + R, ab_hi);
-            const float* pbl = Bl + kPadL + col;
+            const int lc = g * 4, col = geo.cs + lc, ra = ab_lo + ch * R, rb = min(ra + R, ab_hi);
+            const float* pbl = Bl + kPadL + lc;
             auto body = [&](auto tag) {
                 constexpr bool FULL = decltype(tag)::value;
                 float D[3][4], V[3][4];
@@ -594,7 +611,7 @@ __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const 
                             float we[4];
 #pragma unroll
                             for (int k = 0; k < 4; ++k) we[k] = wgt * edge_from_u(a, u[k]);
-                            const bool interior = (rout >= r0 && rout < r1);
+                            const bool interior = (rout >= r0 && rout < r1 && col >= geo.c0 && col < geo.c1);
                             float4 bs[NC ? NC : 1], go[NC ? NC : 1];
                             if (NC) {
 #pragma unroll
@@ -648,7 +665,7 @@ __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const 
                                     }
                                 }
                             }
-                            const int q = (rout - ab_lo) * Wp + kPadL + col;
+                            const int q = (rout - ab_lo) * Wp + kPadL + lc;
                             st_plane(A + q, av, col == 0, col + 4 == W, 0.0f, 0.0f);
                             st_plane(Bv + q, bv, col == 0, col + 4 == W, 0.0f, 0.0f);
                         }

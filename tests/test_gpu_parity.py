@@ -53,7 +53,7 @@ SHAPES = [
     # B, C, H, W      (W % 4 == 0 -> 128-bit path, otherwise scalar path)
     (2, 3, 64, 64), (3, 1, 28, 28), (2, 3, 32, 32), (1, 3, 224, 224), (2, 3, 17, 23), (2, 2, 9, 12),
     (3, 1, 1, 1), (2, 3, 1, 8), (2, 3, 8, 1), (1, 4, 2, 2), (1, 3, 5, 4), (1, 3, 40, 300),
-    (2, 3, 4, 8), (1, 5, 13, 16), (1, 3, 9, 1028),
+    (2, 3, 4, 8), (1, 5, 13, 16), (1, 3, 9, 1028), (2, 3, 12, 132), (1, 1, 30, 256),
 ]
 VARIANT_MODES = [("step125", "hyst")] + [(v, m) for v in ("canny", "bpda") for m in ("hyst", "mix", "low", "raw")]
 
