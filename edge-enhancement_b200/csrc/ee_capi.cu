@@ -97,7 +97,18 @@ int plan_fast(int H, int W, int R, int rows_per_th, int rows_fixed, int max_halo
     }
     const int G = L.planeW / 4;
     const size_t row_bytes = (size_t)(L.planeW + ee::kPadW) * sizeof(float);
-    auto smem_of = [&](int th) { return (size_t)(rows_per_th * th + rows_fixed) * row_bytes; };
+    // the kernels' regions are min(TH + k, H) rows each (halo rows outside the image do not exist); the k's
+    // are encoded as rows_per_th regions whose halos add up to rows_fixed: step125 fwd {4,2}, bwd {8,6,4},
+    // Canny fwd {8,6,4}, Canny bwd {12,10,8,4}
+    auto smem_of = [&](int th) {
+        int halos[4] = {0, 0, 0, 0};
+        if (rows_per_th == 2) { halos[0] = 4; halos[1] = 2; }
+        else if (rows_per_th == 3) { halos[0] = 8; halos[1] = 6; halos[2] = 4; }
+        else { halos[0] = 12; halos[1] = 10; halos[2] = 8; halos[3] = 4; }
+        size_t rows = 0;
+        for (int i = 0; i < rows_per_th; ++i) rows += (size_t)(th + halos[i] < H ? th + halos[i] : H);
+        return rows * row_bytes;
+    };
     int th;
     if (forced_th > 0) {
         th = forced_th < H ? forced_th : H;

@@ -138,7 +138,7 @@ __device__ __forceinline__ void cfast_emit(const FastArgs& a, const Geo geo, int
 template <int NC, bool BLEND, int R, bool EMIT>
 __device__ __forceinline__ void cfast_stage_nms(const FastArgs& a, const Geo geo, const float* M, float* META, int m_lo,
                                                 int lo, int hi, int b, int mode, int tx, int ty) {
-    const int W = geo.W, H = geo.H, Wp = geo.Wp;
+    const int H = geo.H, Wp = geo.Wp;
     EE_FOR_CHUNKS(lo, hi) {
         const int lc = g * 4, col = geo.cs + lc, ra = lo + ch * R, rb = min(ra + R, hi);
         if (EMIT && (col < geo.c0 || col >= geo.c1)) continue;   // halo groups produce no output
@@ -190,8 +190,8 @@ __global__ void __launch_bounds__(256, 3) edge_fwd_canny_fast(const FastArgs a) 
     const int hc = (mode == MODE_HYST) ? 1 : 0;
 
     float* R1 = smem;
-    float* R2 = R1 + (size_t)(a.e.TH + 8) * Wp;
-    float* R3 = R2 + (size_t)(a.e.TH + 6) * Wp;
+    float* R2 = R1 + (size_t)min(a.e.TH + 8, H) * Wp;
+    float* R3 = R2 + (size_t)min(a.e.TH + 6, H) * Wp;
     const int s_lo = max(r0 - 3 - hc, 0), s_hi = min(r1 + 3 + hc, H);
     const int b_lo = max(r0 - 2 - hc, 0), b_hi = min(r1 + 2 + hc, H);
     const int m_lo = max(r0 - 1 - hc, 0), m_hi = min(r1 + 1 + hc, H);
@@ -267,9 +267,9 @@ __global__ void __launch_bounds__(256, 2) edge_bwd_canny_fast(const FastArgs a) 
     const float fC = a.e.fC, wgt = a.e.w;
 
     float* R1 = smem;
-    float* R2 = R1 + (size_t)(a.e.TH + 12) * Wp;
-    float* R3 = R2 + (size_t)(a.e.TH + 10) * Wp;
-    float* R4 = R3 + (size_t)(a.e.TH + 8) * Wp;
+    float* R2 = R1 + (size_t)min(a.e.TH + 12, H) * Wp;
+    float* R3 = R2 + (size_t)min(a.e.TH + 10, H) * Wp;
+    float* R4 = R3 + (size_t)min(a.e.TH + 8, H) * Wp;
 
     const int ab_lo = max(r0 - ha, 0), ab_hi = min(r1 + ha, H);
     const int c_lo = max(r0 - ha - hc, 0), c_hi = min(r1 + ha + hc, H);

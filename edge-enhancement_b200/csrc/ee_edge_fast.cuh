@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256, EE_MINB_FWD) edge_fwd_step125_fast(const 
     const int s_lo = max(r0 - 2, 0), s_hi = min(r1 + 2, H);
     const int b_lo = max(r0 - 1, 0), b_hi = min(r1 + 1, H);
     float* S = smem;
-    float* Bl = smem + (size_t)(a.e.TH + 4) * Wp;
+    float* Bl = smem + (size_t)min(a.e.TH + 4, H) * Wp;
 
 #if EE_L2_PREFETCH
     if (BLEND && a.tiles_x == 1 && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
@@ -531,7 +531,8 @@ __device__ __forceinline__ void fast_stage_gauss_adjoint_store(const FastArgs& a
 }
 
 // -------------------------------------------------------------------------------------------
-// backward.  smem regions (stride Wp): R1 = S then A (TH+8 rows), R2 = Bl then GB (TH+6), R3 = Bv (TH+4)
+// backward.  smem regions (stride Wp): R1 = S then A (TH+8 rows), R2 = Bl then GB (TH+6), R3 = Bv (TH+4);
+// a region never needs more rows than the image has (halo rows are clipped), so each is min(TH+k, H) rows
 // -------------------------------------------------------------------------------------------
 template <int NC, bool BLEND, int R, int WT, int WG>
 __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const FastArgs a) {
@@ -549,8 +550,8 @@ __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const 
     const bool active = ty < geo.RY;
 
     float* R1 = smem;
-    float* R2 = R1 + (size_t)(a.e.TH + 8) * Wp;
-    float* R3 = R2 + (size_t)(a.e.TH + 6) * Wp;
+    float* R2 = R1 + (size_t)min(a.e.TH + 8, H) * Wp;
+    float* R3 = R2 + (size_t)min(a.e.TH + 6, H) * Wp;
 
     const bool want_gx = (a.e.g_x != nullptr);
     const int s_lo = max(r0 - 4, 0), s_hi = min(r1 + 4, H);
@@ -558,7 +559,6 @@ __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const 
     const int ab_lo = want_gx ? max(r0 - 2, 0) : r0, ab_hi = want_gx ? min(r1 + 2, H) : r1;
     const int gb_lo = max(r0 - 1, 0), gb_hi = min(r1 + 1, H);
     const float fC = a.e.fC, wgt = a.e.w;
-    const float c0 = a.e.c0, c1 = a.e.c1, c2 = a.e.c2;
 
     float* S = R1; float* Bl = R2;
 #if EE_L2_PREFETCH_BWD
