@@ -11,6 +11,9 @@
 //   M          : gated gradient magnitude, ZERO padded (the directional conv is zero padded, core.py:268)
 //   META       : one word per pixel, zero padded: bits 0-3 direction pair + 1, 4-5 low+high, 6 high, 7 removed
 #pragma once
+#ifndef EE_L2_PREFETCH_BWD_CANNY
+#define EE_L2_PREFETCH_BWD_CANNY 0
+#endif
 #include "ee_edge_canny.cuh"
 #include "ee_edge_fast.cuh"
 
@@ -196,11 +199,11 @@ __global__ void __launch_bounds__(256, 3) edge_fwd_canny_fast(const FastArgs a) 
     const int b_lo = max(r0 - 2 - hc, 0), b_hi = min(r1 + 2 + hc, H);
     const int m_lo = max(r0 - 1 - hc, 0), m_hi = min(r1 + 1 + hc, H);
 
+    float* S = R1; float* Bl = R2;
+    if (active) fast_stage_sum<NC, R>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
 #if EE_L2_PREFETCH
     if (BLEND && a.tiles_x == 1 && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
 #endif
-    float* S = R1; float* Bl = R2;
-    if (active) fast_stage_sum<NC, R>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
     __syncthreads();
     if (active) fast_stage_blur<R>(a, geo, S, s_lo, Bl, b_lo, b_hi, tx, ty);
     __syncthreads();
@@ -280,6 +283,16 @@ __global__ void __launch_bounds__(256, 2) edge_bwd_canny_fast(const FastArgs a) 
 
     float* S = R1; float* Bl = R2;
     if (active) fast_stage_sum<NC, R>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
+#if EE_L2_PREFETCH_BWD_CANNY       // measured -8 % on the Canny backward (2 CTAs/SM, operands needed 4 stages later): off
+    if (C <= 32 && a.tiles_x == 1) {            // operands of the A/Bv stage, three stages from now
+        if (BLEND) {
+            if (threadIdx.x < 32) prefetch_rows(a.e.base, b, C, H, W, ab_lo, ab_hi, threadIdx.x);
+            else if (threadIdx.x < 64) prefetch_rows(a.e.g_in, b, C, H, W, ab_lo, ab_hi, threadIdx.x - 32);
+        } else if (threadIdx.x == 0) {
+            prefetch_rows(a.e.g_in, b, 1, H, W, ab_lo, ab_hi, 0);
+        }
+    }
+#endif
     __syncthreads();
     if (active) fast_stage_blur<R>(a, geo, S, s_lo, Bl, b_lo, b_hi, tx, ty);
     __syncthreads();

@@ -100,13 +100,17 @@ __device__ __forceinline__ float clamp01_fast(float v) {
 #define EE_USE_FULL 0
 #endif
 
-// L2 bulk prefetch of the operands a later stage needs: measured +3..12 % on the forward, -4 % on the
-// backward at 64 px (three 144 KB tiles per SM in flight), so it is on for the forward only.
+// L2 bulk prefetch (UBLKPF) of the operands a LATER stage needs (base / g_out).  Placement matters: issued
+// before the x loads of the first stage it competes with them (backward -4 %); issued right after them
+// (mode 2) the backward gains 10 % (5.0 -> 5.5 TB/s at 4096x3x64x64).  0 = off, 1 = at kernel start, 2 = after
+// the first stage's loads.
 #ifndef EE_L2_PREFETCH
-#define EE_L2_PREFETCH 1
+#define EE_L2_PREFETCH 2
 #endif
+// (Also tried: prefetching the x rows of the tile that will replace this CTA on its SM, blockIdx + resident
+// CTAs.  Measured slower -- forward 6.6 -> 6.3, backward 5.5 -> 5.0 TB/s -- and removed.)
 #ifndef EE_L2_PREFETCH_BWD
-#define EE_L2_PREFETCH_BWD 0
+#define EE_L2_PREFETCH_BWD 2
 #endif
 
 // Tile geometry.  When the kernel is specialised on the image width (WT != 0) W, Wp, G and GX are
@@ -287,10 +291,13 @@ __global__ void __launch_bounds__(256, EE_MINB_FWD) edge_fwd_step125_fast(const 
     float* S = smem;
     float* Bl = smem + (size_t)min(a.e.TH + 4, H) * Wp;
 
-#if EE_L2_PREFETCH
+#if EE_L2_PREFETCH == 1
     if (BLEND && a.tiles_x == 1 && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
 #endif
     if (ty < geo.RY) fast_stage_sum<NC, R>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
+#if EE_L2_PREFETCH == 2
+    if (BLEND && a.tiles_x == 1 && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
+#endif
     __syncthreads();
     if (ty < geo.RY) fast_stage_blur<R>(a, geo, S, s_lo, Bl, b_lo, b_hi, tx, ty);
     __syncthreads();
@@ -561,17 +568,23 @@ __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const 
     const float fC = a.e.fC, wgt = a.e.w;
 
     float* S = R1; float* Bl = R2;
-#if EE_L2_PREFETCH_BWD
-    if (C <= 32) {
-        if (BLEND) {
-            if (threadIdx.x < 32) prefetch_rows(a.e.base, b, C, H, W, ab_lo, ab_hi, threadIdx.x);
-            else if (threadIdx.x < 64) prefetch_rows(a.e.g_in, b, C, H, W, ab_lo, ab_hi, threadIdx.x - 32);
-        } else if (threadIdx.x == 0) {
-            prefetch_rows(a.e.g_in, b, 1, H, W, ab_lo, ab_hi, 0);
+    auto prefetch_bwd_operands = [&]() {
+        if (C <= 32 && a.tiles_x == 1) {
+            if (BLEND) {
+                if (threadIdx.x < 32) prefetch_rows(a.e.base, b, C, H, W, ab_lo, ab_hi, threadIdx.x);
+                else if (threadIdx.x < 64) prefetch_rows(a.e.g_in, b, C, H, W, ab_lo, ab_hi, threadIdx.x - 32);
+            } else if (threadIdx.x == 0) {
+                prefetch_rows(a.e.g_in, b, 1, H, W, ab_lo, ab_hi, 0);
+            }
         }
-    }
+    };
+#if EE_L2_PREFETCH_BWD == 1
+    prefetch_bwd_operands();
 #endif
     if (active) fast_stage_sum<NC, R>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
+#if EE_L2_PREFETCH_BWD == 2
+    prefetch_bwd_operands();        // after the x loads are issued, so they do not compete with them
+#endif
     __syncthreads();
     if (active) fast_stage_blur<R>(a, geo, S, s_lo, Bl, b_lo, b_hi, tx, ty);
     __syncthreads();
