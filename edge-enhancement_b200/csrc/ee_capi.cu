@@ -39,7 +39,7 @@ int check_params(const EEParams* p, float& c0, float& c1, float& c2) {
     if (!p) return fail(EE_ERR_INVALID_ARG, "EEParams is null");
     if (p->variant < EE_VARIANT_STEP125 || p->variant > EE_VARIANT_BPDA)
         return fail(EE_ERR_INVALID_ARG, "unknown variant %d", p->variant);
-    if (p->layout != EE_LAYOUT_NCHW) return fail(EE_ERR_UNSUPPORTED, "only dense NCHW is supported");
+    if (p->layout != EE_LAYOUT_NCHW && p->layout != EE_LAYOUT_NHWC) return fail(EE_ERR_INVALID_ARG, "unknown layout %d", p->layout);
     if (p->reserved != 0) return fail(EE_ERR_INVALID_ARG, "EEParams.reserved must be 0");
     const float* g = p->gauss;
     if (!(g[0] == g[2] && g[0] == g[6] && g[0] == g[8] && g[1] == g[3] && g[1] == g[5] && g[1] == g[7]))
@@ -178,6 +178,12 @@ void fill_fast(ee::FastArgs& f, const ee::EdgeArgs& a, const Launch& L) {
 // Specialised instantiations <NC, BLEND, rows/thread, plane width WT, global width WG> for the hot shapes
 // (Tiny-ImageNet 64, CIFAR 32, MNIST 28 as single column tiles; 64-wide planes of column-tiled 224 px
 // images); everything else runs the runtime-width instantiation <.., 0, 0> of the same kernel.
+#define EE_DISPATCH_FAST_NHWC(KERNEL, L, B, f, s, name)                                           \
+    do {                                                                                          \
+        if ((L).tiles_x == 1 && (f).e.W == 64) return launch_fast(KERNEL<3, true, 4, 64, 64, true>, L, B, f, s, name); \
+        return launch_fast(KERNEL<3, true, 4, 0, 0, true>, L, B, f, s, name);                     \
+    } while (0)
+
 #define EE_DISPATCH_FAST(KERNEL, BLEND, L, B, f, s, name)                                         \
     do {                                                                                          \
         const int W_ = (f).e.W, C_ = (f).e.C;                                                     \
@@ -280,6 +286,21 @@ int edge_forward(const float* x, const float* base, float* out, float* edge, int
     const bool vec_ok = (W % 4 == 0) && aligned16(x) && aligned16(base) && aligned16(out) && aligned16(edge);
     cudaStream_t s = (cudaStream_t)stream;
     Launch L;
+    const bool nhwc = (p->layout == EE_LAYOUT_NHWC) && C > 1;       // with one channel the layouts coincide
+    if (nhwc) {
+        // channels_last is implemented by the tuned fused kernels for C = 3; anything else must be
+        // converted by the caller (the Python wrapper does), never silently mis-read
+        if (!(blend && C == 3 && fast_eligible(a, vec_ok)))
+            return fail(EE_ERR_UNSUPPORTED, "NHWC needs the fused blend entry point, C == 3, W %% 4 == 0, 16-byte aligned tensors");
+        const bool st = (p->variant == EE_VARIANT_STEP125);
+        rc = st ? plan_fast(H, W, 4, 2, 6, 4, 40 * 1024, g_th_fwd.load(), L)
+                : plan_fast(H, W, 4, ee::kCannyFastFwdRowsPerTH, ee::kCannyFastFwdRowsFixed, 8, 62 * 1024, g_th_fwd.load(), L);
+        if (rc) return rc;
+        ee::FastArgs f;
+        fill_fast(f, a, L);
+        if (st) EE_DISPATCH_FAST_NHWC(ee::edge_fwd_step125_fast, L, B, f, s, "edge_fwd_step125_fast_nhwc");
+        else EE_DISPATCH_FAST_NHWC(ee::edge_fwd_canny_fast, L, B, f, s, "edge_fwd_canny_fast_nhwc");
+    }
     if (p->variant == EE_VARIANT_STEP125 && fast_eligible(a, vec_ok)) {
         rc = plan_fast(H, W, 4, 2, 6, 4, 40 * 1024, g_th_fwd.load(), L);
         if (rc) return rc;
@@ -323,6 +344,19 @@ int edge_backward(const float* g_in, const float* x, const float* base, float* g
     const bool vec_ok = (W % 4 == 0) && aligned16(x) && aligned16(base) && aligned16(g_in) && aligned16(g_x) && aligned16(g_base);
     cudaStream_t s = (cudaStream_t)stream;
     Launch L;
+    const bool nhwc = (p->layout == EE_LAYOUT_NHWC) && C > 1;
+    if (nhwc) {
+        if (!(blend && C == 3 && fast_eligible(a, vec_ok)))
+            return fail(EE_ERR_UNSUPPORTED, "NHWC needs the fused blend entry point, C == 3, W %% 4 == 0, 16-byte aligned tensors");
+        const bool st = (p->variant == EE_VARIANT_STEP125);
+        rc = st ? plan_fast(H, W, 4, 3, 18, 8, 62 * 1024, g_th_bwd.load(), L)
+                : plan_fast(H, W, 4, ee::kCannyFastBwdRowsPerTH, ee::kCannyFastBwdRowsFixed, 12, 84 * 1024, g_th_bwd.load(), L, 8);
+        if (rc) return rc;
+        ee::FastArgs f;
+        fill_fast(f, a, L);
+        if (st) EE_DISPATCH_FAST_NHWC(ee::edge_bwd_step125_fast, L, B, f, s, "edge_bwd_step125_fast_nhwc");
+        else EE_DISPATCH_FAST_NHWC(ee::edge_bwd_canny_fast, L, B, f, s, "edge_bwd_canny_fast_nhwc");
+    }
     if (p->variant == EE_VARIANT_STEP125 && fast_eligible(a, vec_ok)) {
         rc = plan_fast(H, W, 4, 3, 18, 8, 62 * 1024, g_th_bwd.load(), L);
         if (rc) return rc;

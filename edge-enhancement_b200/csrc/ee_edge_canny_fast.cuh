@@ -106,7 +106,7 @@ __device__ __forceinline__ void meta_partials(const Win& w, int (&hs)[4], int (&
 }
 
 // write edge (+ blended image) of 4 pixels at (row, col)
-template <int NC, bool BLEND>
+template <int NC, bool BLEND, bool NHWC = false>
 __device__ __forceinline__ void cfast_emit(const FastArgs& a, const Geo geo, int b, int row, int col, const float (&e)[4]) {
     const int W = geo.W;
     const int C = NC ? NC : a.e.C;
@@ -115,21 +115,20 @@ __device__ __forceinline__ void cfast_emit(const FastArgs& a, const Geo geo, int
     if (a.e.edge) __stcs(reinterpret_cast<float4*>(a.e.edge + (size_t)b * hw + pix), make_float4(e[0], e[1], e[2], e[3]));
     if (BLEND) {
         const float w0 = a.e.w * e[0], w1 = a.e.w * e[1], w2 = a.e.w * e[2], w3 = a.e.w * e[3];
-        const float* base_b = a.e.base + (size_t)b * C * hw + pix;
-        float* out_b = a.e.out + (size_t)b * C * hw + pix;
+        const float* base_b = a.e.base + (size_t)b * C * hw;
+        float* out_b = a.e.out + (size_t)b * C * hw;
         if (NC) {
             float4 bs[NC ? NC : 1];
-#pragma unroll
-            for (int c = 0; c < (NC ? NC : 1); ++c) bs[c] = __ldg(reinterpret_cast<const float4*>(base_b + c * hw));
+            ld_px4<NC, NHWC>(base_b, hw, pix, bs);
 #pragma unroll
             for (int c = 0; c < (NC ? NC : 1); ++c)
-                __stcs(reinterpret_cast<float4*>(out_b + c * hw),
-                       make_float4(clamp01_fast(bs[c].x + w0), clamp01_fast(bs[c].y + w1), clamp01_fast(bs[c].z + w2),
-                                   clamp01_fast(bs[c].w + w3)));
+                bs[c] = make_float4(clamp01_fast(bs[c].x + w0), clamp01_fast(bs[c].y + w1), clamp01_fast(bs[c].z + w2),
+                                    clamp01_fast(bs[c].w + w3));
+            st_px4<NC, NHWC>(out_b, hw, pix, bs);
         } else {
             for (int c = 0; c < C; ++c) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(base_b + c * hw));
-                __stcs(reinterpret_cast<float4*>(out_b + c * hw),
+                const float4 t = __ldg(reinterpret_cast<const float4*>(base_b + c * hw + pix));
+                __stcs(reinterpret_cast<float4*>(out_b + c * hw + pix),
                        make_float4(clamp01_fast(t.x + w0), clamp01_fast(t.y + w1), clamp01_fast(t.z + w2), clamp01_fast(t.w + w3)));
             }
         }
@@ -138,7 +137,7 @@ __device__ __forceinline__ void cfast_emit(const FastArgs& a, const Geo geo, int
 
 // ---- stage NMS: rows [lo,hi).  EMIT = false: update META in place (hysteresis needs a 3x3 sum of it);
 //      EMIT = true: the non-hysteresis modes write their output directly. ------------------------------
-template <int NC, bool BLEND, int R, bool EMIT>
+template <int NC, bool BLEND, int R, bool EMIT, bool NHWC = false>
 __device__ __forceinline__ void cfast_stage_nms(const FastArgs& a, const Geo geo, const float* M, float* META, int m_lo,
                                                 int lo, int hi, int b, int mode, int tx, int ty) {
     const int H = geo.H, Wp = geo.Wp;
@@ -162,7 +161,7 @@ __device__ __forceinline__ void cfast_stage_nms(const FastArgs& a, const Geo geo
                     float e[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) e[k] = edge_value_simple(mode, thin[k], meta[k]);
-                    cfast_emit<NC, BLEND>(a, geo, b, p, col, e);
+                    cfast_emit<NC, BLEND, NHWC>(a, geo, b, p, col, e);
                 } else {
                     *reinterpret_cast<float4*>(pmeta) = make_float4(__int_as_float(meta[0]), __int_as_float(meta[1]),
                                                                     __int_as_float(meta[2]), __int_as_float(meta[3]));
@@ -175,7 +174,7 @@ __device__ __forceinline__ void cfast_stage_nms(const FastArgs& a, const Geo geo
 // -------------------------------------------------------------------------------------------
 // forward
 // -------------------------------------------------------------------------------------------
-template <int NC, bool BLEND, int R, int WT, int WG>
+template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false>
 __global__ void __launch_bounds__(256, 3) edge_fwd_canny_fast(const FastArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int DIVM = (NC == 1) ? 0 : (NC == 3 ? 1 : 2);
@@ -200,7 +199,7 @@ __global__ void __launch_bounds__(256, 3) edge_fwd_canny_fast(const FastArgs a) 
     const int m_lo = max(r0 - 1 - hc, 0), m_hi = min(r1 + 1 + hc, H);
 
     float* S = R1; float* Bl = R2;
-    if (active) fast_stage_sum<NC, R>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
+    if (active) fast_stage_sum<NC, R, NHWC>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
 #if EE_L2_PREFETCH
     if (BLEND && a.tiles_x == 1 && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
 #endif
@@ -211,11 +210,11 @@ __global__ void __launch_bounds__(256, 3) edge_fwd_canny_fast(const FastArgs a) 
     if (active) cfast_stage_mag_dir<DIVM, R>(a, geo, Bl, b_lo, M, META, m_lo, m_hi, tx, ty);
     __syncthreads();
     if (mode != MODE_HYST) {
-        if (active) cfast_stage_nms<NC, BLEND, R, true>(a, geo, M, META, m_lo, r0, r1, b, mode, tx, ty);
+        if (active) cfast_stage_nms<NC, BLEND, R, true, NHWC>(a, geo, M, META, m_lo, r0, r1, b, mode, tx, ty);
         return;
     }
     const int c_lo = max(r0 - 1, 0), c_hi = min(r1 + 1, H);
-    if (active) cfast_stage_nms<NC, BLEND, R, false>(a, geo, M, META, m_lo, c_lo, c_hi, b, mode, tx, ty);
+    if (active) cfast_stage_nms<NC, BLEND, R, false, NHWC>(a, geo, M, META, m_lo, c_lo, c_hi, b, mode, tx, ty);
     __syncthreads();
     if (!active) return;
     // hysteresis (core.py:317-321 / :494-503): weak = (low+high == 1), kept if the zero-padded 3x3 sum of
@@ -238,7 +237,7 @@ __global__ void __launch_bounds__(256, 3) edge_fwd_canny_fast(const FastArgs a) 
                     const int wih = (meta_lh(c) == 1) && (n >= 2);
                     e[k] = (float)(meta_hi(c) + wih);
                 }
-                cfast_emit<NC, BLEND>(a, geo, b, ra + i - 2, col, e);
+                cfast_emit<NC, BLEND, NHWC>(a, geo, b, ra + i - 2, col, e);
             }
         }
     }
@@ -247,7 +246,7 @@ __global__ void __launch_bounds__(256, 3) edge_fwd_canny_fast(const FastArgs a) 
 // -------------------------------------------------------------------------------------------
 // backward
 // -------------------------------------------------------------------------------------------
-template <int NC, bool BLEND, int R, int WT, int WG>
+template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false>
 __global__ void __launch_bounds__(256, 2) edge_bwd_canny_fast(const FastArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int DIVM = (NC == 1) ? 0 : (NC == 3 ? 1 : 2);
@@ -282,7 +281,7 @@ __global__ void __launch_bounds__(256, 2) edge_bwd_canny_fast(const FastArgs a) 
     const int gb_lo = max(r0 - 1, 0), gb_hi = min(r1 + 1, H);
 
     float* S = R1; float* Bl = R2;
-    if (active) fast_stage_sum<NC, R>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
+    if (active) fast_stage_sum<NC, R, NHWC>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
 #if EE_L2_PREFETCH_BWD_CANNY       // measured -8 % on the Canny backward (2 CTAs/SM, operands needed 4 stages later): off
     if (C <= 32 && a.tiles_x == 1) {            // operands of the A/Bv stage, three stages from now
         if (BLEND) {
@@ -364,9 +363,19 @@ __global__ void __launch_bounds__(256, 2) edge_bwd_canny_fast(const FastArgs a) 
                             we[k] = wgt * e;
                         }
                         const bool interior = (rout >= r0 && rout < r1 && col >= geo.c0 && col < geo.c1);
+                        float4 bs[NC ? NC : 1], go[NC ? NC : 1];
+                        if (NC) {
+                            ld_px4<NC, NHWC>(base_b, hw, pix, bs);
+                            ld_px4<NC, NHWC>(gin_b, hw, pix, go);
+                        }
+#pragma unroll 3
                         for (int c = 0; c < C; ++c) {
-                            const float4 bsc = __ldg(reinterpret_cast<const float4*>(base_b + c * hw + pix));
-                            const float4 goc = __ldg(reinterpret_cast<const float4*>(gin_b + c * hw + pix));
+                            float4 bsc, goc;
+                            if (NC) { bsc = bs[NC ? c : 0]; goc = go[NC ? c : 0]; }
+                            else {
+                                bsc = __ldg(reinterpret_cast<const float4*>(base_b + c * hw + pix));
+                                goc = __ldg(reinterpret_cast<const float4*>(gin_b + c * hw + pix));
+                            }
                             const float bsv[4] = {bsc.x, bsc.y, bsc.z, bsc.w}, gov[4] = {goc.x, goc.y, goc.z, goc.w};
                             float gp[4];
 #pragma unroll
@@ -375,9 +384,11 @@ __global__ void __launch_bounds__(256, 2) edge_bwd_canny_fast(const FastArgs a) 
                                 gp[k] = (pre >= 0.0f && pre <= 1.0f) ? gov[k] : 0.0f;
                                 ge[k] = (c == 0) ? gp[k] * wgt : fmaf(gp[k], wgt, ge[k]);
                             }
-                            if (gbase_b && interior)
+                            if (NC) go[NC ? c : 0] = make_float4(gp[0], gp[1], gp[2], gp[3]);
+                            else if (gbase_b && interior)
                                 __stcs(reinterpret_cast<float4*>(gbase_b + c * hw + pix), make_float4(gp[0], gp[1], gp[2], gp[3]));
                         }
+                        if (NC && gbase_b && interior) st_px4<NC, NHWC>(gbase_b, hw, pix, go);
                     } else {
                         const float4 t = __ldg(reinterpret_cast<const float4*>(gin_b + pix));
                         ge[0] = t.x; ge[1] = t.y; ge[2] = t.z; ge[3] = t.w;
@@ -404,7 +415,7 @@ __global__ void __launch_bounds__(256, 2) edge_bwd_canny_fast(const FastArgs a) 
     float* GB = R2;
     if (active) fast_stage_sobel_adjoint<R>(geo, A, Bv, ab_lo, GB, gb_lo, gb_hi, tx, ty);
     __syncthreads();
-    if (active) fast_stage_gauss_adjoint_store<NC, R>(a, geo, GB, gb_lo, a.e.g_x + (size_t)b * C * hw, r0, r1, tx, ty);
+    if (active) fast_stage_gauss_adjoint_store<NC, R, NHWC>(a, geo, GB, gb_lo, a.e.g_x + (size_t)b * C * hw, r0, r1, tx, ty);
 }
 
 }  // namespace ee

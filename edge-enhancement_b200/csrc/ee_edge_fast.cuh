@@ -157,8 +157,40 @@ __device__ __forceinline__ void st_plane(float* q, const float (&o)[4], bool lef
     if (right) q[4] = rpad;
 }
 
+// ---- channel I/O of 4 consecutive pixels -----------------------------------------------------------------
+// v[c] holds channel c of pixels pix..pix+3 of ONE image (img = that image's first float; an image is C*hw
+// contiguous floats in both layouts).  NCHW: one 128-bit access per channel plane.  NHWC (channels_last,
+// C = 3): the 12 floats of the 4 pixels are 3 consecutive 128-bit words that are (de)interleaved in registers.
+template <int NC, bool NHWC>
+__device__ __forceinline__ void ld_px4(const float* __restrict__ img, size_t hw, int pix, float4 (&v)[NC ? NC : 1]) {
+    if constexpr (NHWC) {
+        static_assert(NC == 3, "channels_last path is specialised for C = 3");
+        const float4* p = reinterpret_cast<const float4*>(img + (size_t)pix * 3);
+        const float4 t0 = __ldg(p), t1 = __ldg(p + 1), t2 = __ldg(p + 2);
+        v[0] = make_float4(t0.x, t0.w, t1.z, t2.y);
+        v[1] = make_float4(t0.y, t1.x, t1.w, t2.z);
+        v[2] = make_float4(t0.z, t1.y, t2.x, t2.w);
+    } else {
+#pragma unroll
+        for (int c = 0; c < (NC ? NC : 1); ++c) v[c] = __ldg(reinterpret_cast<const float4*>(img + c * hw + pix));
+    }
+}
+template <int NC, bool NHWC>
+__device__ __forceinline__ void st_px4(float* img, size_t hw, int pix, const float4 (&v)[NC ? NC : 1]) {
+    if constexpr (NHWC) {
+        static_assert(NC == 3, "channels_last path is specialised for C = 3");
+        float4* p = reinterpret_cast<float4*>(img + (size_t)pix * 3);
+        __stcs(p, make_float4(v[0].x, v[1].x, v[2].x, v[0].y));
+        __stcs(p + 1, make_float4(v[1].y, v[2].y, v[0].z, v[1].z));
+        __stcs(p + 2, make_float4(v[2].z, v[0].w, v[1].w, v[2].w));
+    } else {
+#pragma unroll
+        for (int c = 0; c < (NC ? NC : 1); ++c) __stcs(reinterpret_cast<float4*>(img + c * hw + pix), v[c]);
+    }
+}
+
 // ---- stage S: channel sum of x rows [lo,hi) into a replicate-padded plane -------------------
-template <int NC, int R>
+template <int NC, int R, bool NHWC = false>
 __device__ __forceinline__ void fast_stage_sum(const FastArgs& a, const Geo geo, const float* __restrict__ xb, float* S,
                                                int lo, int hi, int tx, int ty) {
     const int W = geo.W, Wp = geo.Wp;
@@ -171,7 +203,22 @@ __device__ __forceinline__ void fast_stage_sum(const FastArgs& a, const Geo geo,
         auto body = [&](auto tag) {
             constexpr bool FULL = decltype(tag)::value;
             float4 acc[R];
-            if (NC == 3) {
+            if (NHWC) {
+                float4 v1[R], v2[R];
+                const float4* p3 = reinterpret_cast<const float4*>(xb + ((size_t)ra * W + col) * 3);
+#pragma unroll
+                for (int i = 0; i < R; ++i)
+                    if (FULL || ra + i < hi) {
+                        acc[i] = __ldg(p3 + (size_t)i * (3 * W / 4));
+                        v1[i] = __ldg(p3 + (size_t)i * (3 * W / 4) + 1);
+                        v2[i] = __ldg(p3 + (size_t)i * (3 * W / 4) + 2);
+                    }
+#pragma unroll
+                for (int i = 0; i < R; ++i)
+                    if (FULL || ra + i < hi)      // same ((c0 + c1) + c2) order as the planar path
+                        acc[i] = make_float4((acc[i].x + acc[i].y) + acc[i].z, (acc[i].w + v1[i].x) + v1[i].y,
+                                             (v1[i].z + v1[i].w) + v2[i].x, (v2[i].y + v2[i].z) + v2[i].w);
+            } else if (NC == 3) {
                 float4 v1[R], v2[R];
 #pragma unroll
                 for (int i = 0; i < R; ++i)
@@ -266,7 +313,7 @@ __device__ __forceinline__ void sobel_partials(const Win& w, float (&D)[4], floa
 // -------------------------------------------------------------------------------------------
 // forward:  planes S (TH+4 rows) and Bl (TH+2 rows), both with stride Wp
 // -------------------------------------------------------------------------------------------
-template <int NC, bool BLEND, int R, int WT, int WG>
+template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false>
 #ifndef EE_MINB_FWD
 #define EE_MINB_FWD 3
 #endif
@@ -294,7 +341,7 @@ __global__ void __launch_bounds__(256, EE_MINB_FWD) edge_fwd_step125_fast(const 
 #if EE_L2_PREFETCH == 1
     if (BLEND && a.tiles_x == 1 && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
 #endif
-    if (ty < geo.RY) fast_stage_sum<NC, R>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
+    if (ty < geo.RY) fast_stage_sum<NC, R, NHWC>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
 #if EE_L2_PREFETCH == 2
     if (BLEND && a.tiles_x == 1 && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
 #endif
@@ -323,10 +370,7 @@ __global__ void __launch_bounds__(256, EE_MINB_FWD) edge_fwd_step125_fast(const 
                 if (i >= 2 && (FULL || ra + i - 2 < rb)) {
                     const int pix = (ra + i - 2) * W + col;
                     float4 bs[NC ? NC : 1];
-                    if (BLEND && NC) {
-#pragma unroll
-                        for (int c = 0; c < NC; ++c) bs[c] = __ldg(reinterpret_cast<const float4*>(base_b + c * hw + pix));
-                    }
+                    if (BLEND && NC) ld_px4<NC, NHWC>(base_b, hw, pix, bs);
                     float e[4], sgx[4], sgy[4], gx1[4], gy1[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -341,11 +385,10 @@ __global__ void __launch_bounds__(256, EE_MINB_FWD) edge_fwd_step125_fast(const 
                         const float w0 = wgt * e[0], w1 = wgt * e[1], w2 = wgt * e[2], w3 = wgt * e[3];
                         if (NC) {
 #pragma unroll
-                            for (int c = 0; c < NC; ++c) {
-                                const float4 o = make_float4(clamp01_fast(bs[c].x + w0), clamp01_fast(bs[c].y + w1),
-                                                             clamp01_fast(bs[c].z + w2), clamp01_fast(bs[c].w + w3));
-                                __stcs(reinterpret_cast<float4*>(out_b + c * hw + pix), o);
-                            }
+                            for (int c = 0; c < (NC ? NC : 1); ++c)
+                                bs[c] = make_float4(clamp01_fast(bs[c].x + w0), clamp01_fast(bs[c].y + w1),
+                                                    clamp01_fast(bs[c].z + w2), clamp01_fast(bs[c].w + w3));
+                            st_px4<NC, NHWC>(out_b, hw, pix, bs);
                         } else {
                             for (int c = 0; c < C; ++c) {
                                 const float4 t = __ldg(reinterpret_cast<const float4*>(base_b + c * hw + pix));
@@ -491,7 +534,7 @@ __device__ __forceinline__ void fast_stage_sobel_adjoint(const Geo geo, const fl
 }
 
 // g_s rows [r0, r1) = fold(Gauss^T(GB)), written to every channel of g_x (gx_b = image base pointer)
-template <int NC, int R>
+template <int NC, int R, bool NHWC = false>
 __device__ __forceinline__ void fast_stage_gauss_adjoint_store(const FastArgs& a, const Geo geo, const float* GB, int gb_lo,
                                                                float* gx_b, int r0, int r1, int tx, int ty) {
     const int W = geo.W, H = geo.H, Wp = geo.Wp;
@@ -524,11 +567,13 @@ __device__ __forceinline__ void fast_stage_gauss_adjoint_store(const FastArgs& a
         };
         auto store = [&](int row, const float (&o)[4]) {
             const float4 v = make_float4(o[0], o[1], o[2], o[3]);
-            float* pg = gx_b + row * W + col;
             if (NC) {
+                float4 vv[NC ? NC : 1];
 #pragma unroll
-                for (int c = 0; c < (NC ? NC : 1); ++c) __stcs(reinterpret_cast<float4*>(pg + c * hw), v);
+                for (int c = 0; c < (NC ? NC : 1); ++c) vv[c] = v;
+                st_px4<NC, NHWC>(gx_b, hw, row * W + col, vv);
             } else {
+                float* pg = gx_b + row * W + col;
                 for (int c = 0; c < C; ++c) __stcs(reinterpret_cast<float4*>(pg + c * hw), v);
             }
         };
@@ -541,7 +586,7 @@ __device__ __forceinline__ void fast_stage_gauss_adjoint_store(const FastArgs& a
 // backward.  smem regions (stride Wp): R1 = S then A (TH+8 rows), R2 = Bl then GB (TH+6), R3 = Bv (TH+4);
 // a region never needs more rows than the image has (halo rows are clipped), so each is min(TH+k, H) rows
 // -------------------------------------------------------------------------------------------
-template <int NC, bool BLEND, int R, int WT, int WG>
+template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false>
 __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const FastArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int DIVM = (NC == 1) ? 0 : (NC == 3 ? 1 : 2);
@@ -581,7 +626,7 @@ __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const 
 #if EE_L2_PREFETCH_BWD == 1
     prefetch_bwd_operands();
 #endif
-    if (active) fast_stage_sum<NC, R>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
+    if (active) fast_stage_sum<NC, R, NHWC>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
 #if EE_L2_PREFETCH_BWD == 2
     prefetch_bwd_operands();        // after the x loads are issued, so they do not compete with them
 #endif
@@ -627,11 +672,8 @@ __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const 
                             const bool interior = (rout >= r0 && rout < r1 && col >= geo.c0 && col < geo.c1);
                             float4 bs[NC ? NC : 1], go[NC ? NC : 1];
                             if (NC) {
-#pragma unroll
-                                for (int c = 0; c < NC; ++c) {
-                                    bs[c] = __ldg(reinterpret_cast<const float4*>(base_b + c * hw + pix));
-                                    go[c] = __ldg(reinterpret_cast<const float4*>(gin_b + c * hw + pix));
-                                }
+                                ld_px4<NC, NHWC>(base_b, hw, pix, bs);
+                                ld_px4<NC, NHWC>(gin_b, hw, pix, go);
                             }
 #pragma unroll 3
                             for (int c = 0; c < C; ++c) {
@@ -649,9 +691,11 @@ __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const 
                                     gp[k] = (pre >= 0.0f && pre <= 1.0f) ? gov[k] : 0.0f;
                                     ge[k] = (c == 0) ? gp[k] * wgt : fmaf(gp[k], wgt, ge[k]);
                                 }
-                                if (gbase_b && interior)
+                                if (NC) go[NC ? c : 0] = make_float4(gp[0], gp[1], gp[2], gp[3]);     // g_base of this channel
+                                else if (gbase_b && interior)
                                     __stcs(reinterpret_cast<float4*>(gbase_b + c * hw + pix), make_float4(gp[0], gp[1], gp[2], gp[3]));
                             }
+                            if (NC && gbase_b && interior) st_px4<NC, NHWC>(gbase_b, hw, pix, go);
                         } else {
                             const float4 t = __ldg(reinterpret_cast<const float4*>(gin_b + pix));
                             ge[0] = t.x; ge[1] = t.y; ge[2] = t.z; ge[3] = t.w;
@@ -695,7 +739,7 @@ __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const 
     float* GB = R2;
     if (active) fast_stage_sobel_adjoint<R>(geo, A, Bv, ab_lo, GB, gb_lo, gb_hi, tx, ty);
     __syncthreads();
-    if (active) fast_stage_gauss_adjoint_store<NC, R>(a, geo, GB, gb_lo, a.e.g_x + (size_t)b * C * hw, r0, r1, tx, ty);
+    if (active) fast_stage_gauss_adjoint_store<NC, R, NHWC>(a, geo, GB, gb_lo, a.e.g_x + (size_t)b * C * hw, r0, r1, tx, ty);
 }
 
 }  // namespace ee

@@ -12,6 +12,8 @@ import torch
 from . import _lib
 from ._lib import EEParams, EE_VARIANT_BPDA, EE_VARIANT_CANNY, EE_VARIANT_STEP125
 
+EE_LAYOUT_NCHW, EE_LAYOUT_NHWC = 0, 1
+
 VARIANTS = {"step125": EE_VARIANT_STEP125, "canny": EE_VARIANT_CANNY, "bpda": EE_VARIANT_BPDA}
 
 _SOBEL_X = np.array([[-0.5, 0.0, 0.5], [-1.0, 0.0, 1.0], [-0.5, 0.0, 0.5]], dtype=np.float32)
@@ -41,6 +43,10 @@ def make_params(variant, gauss, alpha=0.0, low=None, high=None, hysteresis=False
 
 
 def _chk(t, name, shape=None):
+    return _chk_nocopy(t, name, shape).contiguous()
+
+
+def _chk_nocopy(t, name, shape=None):
     if not isinstance(t, torch.Tensor):
         raise TypeError("%s must be a torch.Tensor" % name)
     if not t.is_cuda:
@@ -50,14 +56,39 @@ def _chk(t, name, shape=None):
         raise TypeError("edge_b200: %s must be float32 (got %s)" % (name, t.dtype))
     if shape is not None and tuple(t.shape) != tuple(shape):
         raise ValueError("edge_b200: %s has shape %s, expected %s" % (name, tuple(t.shape), tuple(shape)))
-    return t.contiguous()
+    return t
+
+
+def _is_channels_last(t):
+    return (t.dim() == 4 and t.shape[1] > 1 and not t.is_contiguous()
+            and t.is_contiguous(memory_format=torch.channels_last))
+
+
+def _nhwc_ok(x):
+    """The fused kernels read torch.channels_last directly for C == 3 and W % 4 == 0 (include/edge_b200.h)."""
+    B, C, H, W = x.shape
+    return _is_channels_last(x) and C == 3 and W % 4 == 0 and W >= 8 and H >= 4
+
+
+def _as_layout(t, name, shape, nhwc):
+    t = _chk_nocopy(t, name, shape)
+    return t.contiguous(memory_format=torch.channels_last) if nhwc else t.contiguous()
+
+
+def _with_layout(params, nhwc):
+    want = EE_LAYOUT_NHWC if nhwc else EE_LAYOUT_NCHW
+    if params.layout == want:
+        return params
+    q = EEParams.from_buffer_copy(params)
+    q.layout = want
+    return q
 
 
 def _out_like(x, out):
     if out is None:
-        return torch.empty_like(x)
-    if not (out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.shape == x.shape):
-        raise ValueError("edge_b200: `out` must be a contiguous float32 CUDA tensor shaped like the input")
+        return torch.empty_like(x)              # preserves x's memory format
+    if not (out.is_cuda and out.dtype == torch.float32 and out.shape == x.shape and out.stride() == x.stride()):
+        raise ValueError("edge_b200: `out` must be a dense float32 CUDA tensor with the shape and strides of the input")
     return out
 
 
@@ -124,18 +155,22 @@ def edge_map_backward(g_edge, x, params):
 
 def edge_blend(x, base, params, w, want_edge=False, out=None):
     """out = clamp(base + w*filter(x), 0, 1) in one pass -- ee_edge_blend_fwd_f32.
-    `out` (optional) is a preallocated result buffer; it must not alias x or base."""
-    x = _chk(x, "img")
+    `out` (optional) is a preallocated result buffer; it must not alias x or base.  channels_last
+    (NHWC) inputs with C == 3 are read in place; other layouts are made NCHW-contiguous first."""
+    x = _chk_nocopy(x, "img")
     if x.dim() != 4:
         raise ValueError("img must be [B,C,H,W]")
+    nhwc = _nhwc_ok(x)
+    x = _as_layout(x, "img", None, nhwc)
     B, C, H, W = x.shape
-    base = _chk(base, "base", x.shape)
+    base = _as_layout(base, "base", x.shape, nhwc)
     out = _out_like(x, out)
     edge = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device) if want_edge else None
     if x.numel():
+        p = _with_layout(params, nhwc)
         with _on_device(x):
             rc = _lib.load().ee_edge_blend_fwd_f32(_ptr(x), _ptr(base), _ptr(out), _ptr(edge), B, C, H, W,
-                                                   ctypes.byref(params), float(w), _stream(x))
+                                                   ctypes.byref(p), float(w), _stream(x))
         _lib.check(rc, "ee_edge_blend_fwd_f32")
     return (out, edge) if want_edge else out
 
@@ -143,16 +178,19 @@ def edge_blend(x, base, params, w, want_edge=False, out=None):
 def edge_blend_backward(g_out, x, base, params, w, need_x=True, need_base=True, g_x=None, g_base=None):
     """(g_x, g_base) of edge_blend in one pass -- ee_edge_blend_bwd_f32.  g_x / g_base may be
     preallocated buffers (not aliasing any input)."""
-    x = _chk(x, "img")
+    x = _chk_nocopy(x, "img")
+    nhwc = _nhwc_ok(x)
+    x = _as_layout(x, "img", None, nhwc)
     B, C, H, W = x.shape
-    base = _chk(base, "base", x.shape)
-    g_out = _chk(g_out, "grad_out", x.shape)
+    base = _as_layout(base, "base", x.shape, nhwc)
+    g_out = _as_layout(g_out, "grad_out", x.shape, nhwc)
     g_x = _out_like(x, g_x) if need_x else None
     g_base = _out_like(x, g_base) if need_base else None
     if x.numel() and (need_x or need_base):
+        p = _with_layout(params, nhwc)
         with _on_device(x):
             rc = _lib.load().ee_edge_blend_bwd_f32(_ptr(g_out), _ptr(x), _ptr(base), _ptr(g_x), _ptr(g_base),
-                                                   B, C, H, W, ctypes.byref(params), float(w), _stream(x))
+                                                   B, C, H, W, ctypes.byref(p), float(w), _stream(x))
         _lib.check(rc, "ee_edge_blend_bwd_f32")
     return g_x, g_base
 

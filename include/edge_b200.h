@@ -8,7 +8,7 @@
  *
  * Contract (all entry points)
  *   - plain pointers and sizes; no torch / C++ types; no exceptions cross the boundary;
- *   - every pointer is a DEVICE pointer to fp32 data, dense NCHW (EE_LAYOUT_NCHW), owned by
+ *   - every pointer is a DEVICE pointer to dense fp32 data in EEParams.layout (NCHW by default), owned by
  *     the caller; the library never allocates, frees or retains device memory and keeps no
  *     global device state, so every call is CUDA-graph capturable;
  *   - work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*) of the
@@ -43,13 +43,16 @@ enum {
     EE_VARIANT_BPDA = 2     /* utils/core.py:386-505  CannyFilter_BPDA      */
 };
 
-enum { EE_LAYOUT_NCHW = 0 };
+/* memory layout of the [B,C,H,W] image tensors (the edge map [B,1,H,W] is the same in both).
+ * EE_LAYOUT_NHWC = torch.channels_last; implemented by the fused blend entry points for C == 3,
+ * W % 4 == 0 (EE_ERR_UNSUPPORTED otherwise -- the caller converts). */
+enum { EE_LAYOUT_NCHW = 0, EE_LAYOUT_NHWC = 1 };
 
 /* Filter description, passed by value into kernel-parameter space (no device constants).
  * Mirrors the module state + forward() arguments of the reference filters. */
 typedef struct EEParams {
     int32_t variant;    /* EE_VARIANT_*                                                        */
-    int32_t layout;     /* EE_LAYOUT_NCHW                                                      */
+    int32_t layout;     /* EE_LAYOUT_NCHW or EE_LAYOUT_NHWC                                    */
     float gauss[9];     /* weight_gaussian, row major (core.py:163-165).  Must have the         */
                         /* corner/edge/centre symmetry every get_gaussian_kernel(3,mu,sigma) has */
     float sobel[9];     /* weight_sobel_x, row major (core.py:175-178); must equal              */

@@ -156,3 +156,43 @@ def test_cuda_graph_capture_of_one_pgd_iteration():
     torch.cuda.synchronize()
     for got, ref in zip((out, g_x, g_base, x_new), want):
         assert torch.equal(got, ref)
+
+
+def test_thread_safety_and_current_stream():
+    """DataParallel worker threads and autograd engine threads call into the library concurrently, each on
+    its own current stream; the library must be re-entrant and enqueue on the caller's stream."""
+    import threading
+    shape = (64, 3, 64, 64)
+    p = F_ee.make_params("canny", O.gaussian3(), 0.0, T.LOW, T.HIGH, True)
+    results, errors = {}, []
+
+    def worker(i):
+        try:
+            gen = torch.Generator(device=DEV).manual_seed(100 + i)
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                x = torch.rand(shape, device=DEV, generator=gen)
+                base = torch.rand(shape, device=DEV, generator=gen)
+                g = torch.randn(shape, device=DEV, generator=gen)
+                outs = []
+                for _ in range(20):
+                    out = F_ee.edge_blend(x, base, p, 1.0)
+                    gx, gb = F_ee.edge_blend_backward(g, x, base, p, 1.0)
+                    outs.append((out, gx, gb))
+                st.synchronize()
+            for out, gx, gb in outs[1:]:
+                assert torch.equal(out, outs[0][0]) and torch.equal(gx, outs[0][1]) and torch.equal(gb, outs[0][2])
+            results[i] = (x.cpu().numpy(), base.cpu().numpy(), g.cpu().numpy(), outs[0][0].cpu().numpy(), outs[0][1].cpu().numpy())
+        except Exception as e:      # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    po = O.make_params("canny", alpha=0.0, low=T.LOW, high=T.HIGH, hysteresis=True)
+    for i, (x, base, g, out, gx) in results.items():
+        assert np.array_equal(out, O.edge_blend_fwd(x, base, po, 1.0))
+        assert np.array_equal(gx, O.edge_blend_bwd(g, x, base, po, 1.0)[0])
