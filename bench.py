@@ -173,12 +173,18 @@ def sample_clocks_until(index, done_event, period=0.002):
         nv.nvmlInit()
         h = nv.nvmlDeviceGetHandleByIndex(index)
         mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-    except Exception:
-        return None
+    except Exception as e:
+        return {"samples": 0, "error": "nvml init: %r" % (e,)}
     names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
              0x80: "hw_power_brake"}
-    samples, reasons = [], set()
-    while not done_event.query():
+    samples, reasons, err = [], set(), None
+    t_stop = time.time() + 120.0
+    while time.time() < t_stop:
+        try:
+            finished = bool(done_event.query())
+        except Exception as e:          # pragma: no cover
+            err = "event.query: %r" % (e,)
+            break
         try:
             samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
             try:
@@ -186,13 +192,17 @@ def sample_clocks_until(index, done_event, period=0.002):
             except Exception:
                 mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
             reasons |= {n for bit, n in names.items() if mask & bit}
-        except Exception:
+        except Exception as e:
+            err = "nvml query: %r" % (e,)
+            break
+        if finished:                    # the last sample may fall just after the end; it is still recorded
             break
         time.sleep(period)
-    if not samples:
-        return None
-    return {"sm_mhz": float(np.median(samples)), "sm_max_mhz": float(mx), "reasons": sorted(reasons),
-            "samples": len(samples), "source": "NVML polled by the launching thread while the timed steps execute"}
+    out = {"sm_mhz": float(np.median(samples)) if samples else None, "sm_max_mhz": float(mx), "reasons": sorted(reasons),
+           "samples": len(samples), "source": "NVML polled by the launching thread while the timed steps execute"}
+    if err:
+        out["error"] = err
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -351,8 +361,10 @@ def run_ours(args):
     barrier()
     sampler.end()
     clocks = sampler.stop()
-    if nvml_samples is not None and nvml_samples["samples"] > clocks.get("samples", 0):
+    if nvml_samples is not None and nvml_samples.get("samples", 0) >= max(2, clocks.get("samples", 0)):
         clocks = nvml_samples
+    elif nvml_samples is not None and nvml_samples.get("error"):
+        clocks["nvml_error"] = nvml_samples["error"]
     ms = t_beg.elapsed_time(t_end)
     ms_t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:

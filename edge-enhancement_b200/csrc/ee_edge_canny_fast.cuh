@@ -247,7 +247,10 @@ __global__ void __launch_bounds__(256, 3) edge_fwd_canny_fast(const FastArgs a) 
 // backward
 // -------------------------------------------------------------------------------------------
 template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false>
-__global__ void __launch_bounds__(256, 2) edge_bwd_canny_fast(const FastArgs a) {
+#ifndef EE_MINB_CANNY_BWD
+#define EE_MINB_CANNY_BWD 2
+#endif
+__global__ void __launch_bounds__(256, EE_MINB_CANNY_BWD) edge_bwd_canny_fast(const FastArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int DIVM = (NC == 1) ? 0 : (NC == 3 ? 1 : 2);
     const int b = blockIdx.x / a.e.tiles_per_img;

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--shapes", default="4096x64,512x224,8192x32,16384x28x1")
     ap.add_argument("--variant", default="step125")
     ap.add_argument("--ths", default="0,4,8,16,32,64,112,224")
+    ap.add_argument("--channels-last", action="store_true")
     args = ap.parse_args()
     L = _lib.load()
     with contextlib.redirect_stdout(io.StringIO()):
@@ -39,6 +40,8 @@ def main():
         B, S = parts[0], parts[1]
         C = parts[2] if len(parts) > 2 else 3
         x = torch.rand(B, C, S, S, device="cuda"); base = torch.rand_like(x) * 1.1 - 0.1; g = torch.randn_like(x)
+        if args.channels_last:
+            x, base, g = (t.contiguous(memory_format=torch.channels_last) for t in (x, base, g))
         o1, o2, o3 = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
         npx = B * S * S
         for th in [int(t) for t in args.ths.split(",")]:
