@@ -217,7 +217,7 @@ def cpu_hot_path(images, side, variant, repeats=1):
     base = (r.random(shape, dtype=np.float32) * 1.1 - 0.1).astype(np.float32)
     g_out = r.standard_normal(shape, dtype=np.float32)
     p = O.make_params(variant, alpha=0.0, low=None if variant == "step125" else LOW, high=HIGH, hysteresis=True)
-    cores = os.cpu_count() or 1
+    cores = O.threads()
     best = None
     for _ in range(repeats):
         x = np.clip(x0 + (r.random(shape, dtype=np.float32) * 2 - 1) * np.float32(EPS), 0, 1).astype(np.float32)
@@ -239,6 +239,8 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is the CPU path on ALL host cores
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     images = args.cpu_images
     for _ in range(max(args.warmup, 0)):
         cpu_hot_path(images, args.side, args.variant)
@@ -246,7 +248,8 @@ def run_reference(args):
     for _ in range(args.steps):
         dt += cpu_hot_path(images, args.side, args.variant)[2]     # hot path only, not the input synthesis
     value = images * args.steps / dt
-    cores = os.cpu_count() or 1
+    from oracle import oracle as O
+    cores = O.threads()
     line = {
         "impl": "reference", "metric": "edge-enhanced PGD-10 hot-path images/sec", "value": value, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,

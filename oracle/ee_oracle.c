@@ -639,3 +639,11 @@ void ee_oracle_safe_sign_bwd(const float *g, const float *in, float *out, int64_
 { for (int64_t i = 0; i < n; ++i) out[i] = (fabsf(in[i]) > 1.001f) ? 0.0f : g[i]; }
 
 int ee_oracle_version(void) { return 1; }
+
+/* number of host threads the parallel loops above will use (reported as `cores` by bench.py) */
+#ifdef _OPENMP
+#include <omp.h>
+int ee_oracle_threads(void) { return omp_get_max_threads(); }
+#else
+int ee_oracle_threads(void) { return 1; }
+#endif

@@ -97,6 +97,13 @@ def lib():
     return L
 
 
+def threads():
+    """Host threads the OpenMP loops of the oracle use."""
+    L = lib()
+    L.ee_oracle_threads.restype = ctypes.c_int
+    return int(L.ee_oracle_threads())
+
+
 def _f32(a):
     a = np.ascontiguousarray(a, dtype=np.float32)
     return a
