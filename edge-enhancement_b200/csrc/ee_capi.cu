@@ -156,6 +156,12 @@ bool fast_eligible(const ee::EdgeArgs& a, bool vec_ok) {
            fabsf(a.alpha) < 1e18f;
 }
 
+// Tiny-ImageNet configuration of the full Canny / BPDA filter: 3x64x64, both thresholds, hysteresis on --
+// compiled with variant and output mode as constants
+bool hot_canny(const ee::FastArgs& f, const Launch& L) {
+    return L.tiles_x == 1 && f.e.W == 64 && f.e.C == 3 && f.e.has_low && f.e.has_high && f.e.hyst;
+}
+
 void fill_fast(ee::FastArgs& f, const ee::EdgeArgs& a, const Launch& L) {
     f.e = a;
     f.e.TH = L.TH; f.e.tiles_per_img = L.tiles; f.e.GX = L.GX; f.e.RY = L.RY;
@@ -321,6 +327,11 @@ int edge_forward(const float* x, const float* base, float* out, float* edge, int
         if (rc) return rc;
         ee::FastArgs f;
         fill_fast(f, a, L);
+        if (blend && hot_canny(f, L)) {
+            if (p->variant == EE_VARIANT_CANNY)
+                return launch_fast(ee::edge_fwd_canny_fast<3, true, 4, 64, 64, false, 1, ee::MODE_HYST>, L, B, f, s, "edge_fwd_canny_fast");
+            return launch_fast(ee::edge_fwd_canny_fast<3, true, 4, 64, 64, false, 2, ee::MODE_HYST>, L, B, f, s, "edge_fwd_canny_fast");
+        }
         if (blend) EE_DISPATCH_FAST(ee::edge_fwd_canny_fast, true, L, B, f, s, "edge_fwd_canny_fast");
         else EE_DISPATCH_FAST(ee::edge_fwd_canny_fast, false, L, B, f, s, "edge_fwd_canny_fast");
     }
@@ -377,6 +388,11 @@ int edge_backward(const float* g_in, const float* x, const float* base, float* g
         if (rc) return rc;
         ee::FastArgs f;
         fill_fast(f, a, L);
+        if (blend && hot_canny(f, L)) {
+            if (p->variant == EE_VARIANT_CANNY)
+                return launch_fast(ee::edge_bwd_canny_fast<3, true, 4, 64, 64, false, 1, ee::MODE_HYST>, L, B, f, s, "edge_bwd_canny_fast");
+            return launch_fast(ee::edge_bwd_canny_fast<3, true, 4, 64, 64, false, 2, ee::MODE_HYST>, L, B, f, s, "edge_bwd_canny_fast");
+        }
         if (blend) EE_DISPATCH_FAST(ee::edge_bwd_canny_fast, true, L, B, f, s, "edge_bwd_canny_fast");
         else EE_DISPATCH_FAST(ee::edge_bwd_canny_fast, false, L, B, f, s, "edge_bwd_canny_fast");
     }

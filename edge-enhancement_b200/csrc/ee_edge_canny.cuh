@@ -214,26 +214,30 @@ __global__ void __launch_bounds__(256) edge_fwd_canny_kernel(const EdgeArgs a) {
     }
 }
 
-// dL/d(thin) from dL/d(edge) for one pixel (see oracle g_thin_of and SURVEY.md A.3)
-__device__ __forceinline__ float g_thin_of(const EdgeArgs& a, int mode, float ge, float thin, int wih) {
+// dL/d(thin) from dL/d(edge) for one pixel (see oracle g_thin_of and SURVEY.md A.3); `variant` is passed
+// separately so that specialised kernels can make it a compile-time constant
+__device__ __forceinline__ float g_thin_of_v(int variant, float low, float high, int mode, float ge, float thin, int wih) {
     if (mode == MODE_RAW) return ge;
-    if (a.variant == 1) {   // CannyFilter: (sign(.)+1)/2 with the BinaryConnect STE window
-        if (mode == MODE_LOW) return bcd_sel(0.5f * ge, thin, a.low);
+    if (variant == 1) {   // CannyFilter: (sign(.)+1)/2 with the BinaryConnect STE window
+        if (mode == MODE_LOW) return bcd_sel(0.5f * ge, thin, low);
         if (mode == MODE_MIX) {
             const float h = 0.5f * ge;
-            return bcd_sel(0.5f * h, thin, a.low) + bcd_sel(0.5f * h, thin, a.high);
+            return bcd_sel(0.5f * h, thin, low) + bcd_sel(0.5f * h, thin, high);
         }
-        return bcd_sel(0.5f * ge, thin, a.high);   // hysteresis: only `high` is differentiable
+        return bcd_sel(0.5f * ge, thin, high);   // hysteresis: only `high` is differentiable
     }
     // CannyFilter_BPDA: To_compare / To_eq windows
     if (mode == MODE_MIX) {
         const float h = 0.5f * ge;
-        return ste_sel(h, thin, a.low) + ste_sel(h, thin, a.high);
+        return ste_sel(h, thin, low) + ste_sel(h, thin, high);
     }
     const float gt = ge * (float)wih;
     const float g_low = 0.5f * gt;
     const float g_high = ge + 0.5f * gt;
-    return ste_sel(g_low, thin, a.low) + ste_sel(g_high, thin, a.high);
+    return ste_sel(g_low, thin, low) + ste_sel(g_high, thin, high);
+}
+__device__ __forceinline__ float g_thin_of(const EdgeArgs& a, int mode, float ge, float thin, int wih) {
+    return g_thin_of_v(a.variant, a.low, a.high, mode, ge, thin, wih);
 }
 
 // -------------------------------------------------------------------------------------------

@@ -32,10 +32,10 @@ __device__ __forceinline__ Win zero_win() { Win w; w.l = w.m0 = w.m1 = w.m2 = w.
 // ---- stage MB: M (gated magnitude) and META (direction) rows [lo,hi) from the blurred plane ----
 template <int DIVM, int R>
 __device__ __forceinline__ void cfast_stage_mag_dir(const FastArgs& a, const Geo geo, const float* Bl, int b_lo, float* M,
-                                                    float* META, int lo, int hi, int tx, int ty) {
+                                                    float* META, int lo, int hi, int tx, int ty, const int variant) {
     const int W = geo.W, H = geo.H, Wp = geo.Wp;
     const float fC = a.e.fC;
-    const bool gate = (a.e.variant == 1);            // only CannyFilter applies alpha (core.py:263-264)
+    const bool gate = (variant == 1);                // only CannyFilter applies alpha (core.py:263-264)
     EE_FOR_CHUNKS(lo, hi) {
         const int lc = g * 4, col = geo.cs + lc, ra = lo + ch * R, rb = min(ra + R, hi);
         const float* pbl = Bl + kPadL + lc;
@@ -72,8 +72,8 @@ __device__ __forceinline__ void cfast_stage_mag_dir(const FastArgs& a, const Geo
 // NMS + double threshold of 4 pixels from the three M windows (rows above / centre / below) and the
 // centre META words.  Returns thin[] and the updated META words.
 __device__ __forceinline__ void nms_threshold4(const FastArgs& a, const Win& wu, const Win& wm, const Win& wd,
-                                               const float4 mt, float (&thin)[4], int (&meta)[4]) {
-    const bool bpda = (a.e.variant == 2);
+                                               const float4 mt, float (&thin)[4], int (&meta)[4], const int variant) {
+    const bool bpda = (variant == 2);
     float u[6], m[6], d[6];
     win_to_array(wu, u); win_to_array(wm, m); win_to_array(wd, d);
     const int words[4] = {__float_as_int(mt.x), __float_as_int(mt.y), __float_as_int(mt.z), __float_as_int(mt.w)};
@@ -139,7 +139,7 @@ __device__ __forceinline__ void cfast_emit(const FastArgs& a, const Geo geo, int
 //      EMIT = true: the non-hysteresis modes write their output directly. ------------------------------
 template <int NC, bool BLEND, int R, bool EMIT, bool NHWC = false>
 __device__ __forceinline__ void cfast_stage_nms(const FastArgs& a, const Geo geo, const float* M, float* META, int m_lo,
-                                                int lo, int hi, int b, int mode, int tx, int ty) {
+                                                int lo, int hi, int b, int mode, int tx, int ty, const int variant) {
     const int H = geo.H, Wp = geo.Wp;
     EE_FOR_CHUNKS(lo, hi) {
         const int lc = g * 4, col = geo.cs + lc, ra = lo + ch * R, rb = min(ra + R, hi);
@@ -156,7 +156,7 @@ __device__ __forceinline__ void cfast_stage_nms(const FastArgs& a, const Geo geo
                 const float4 mt = *reinterpret_cast<const float4*>(pmeta);
                 float thin[4];
                 int meta[4];
-                nms_threshold4(a, wm[(i - 2) % 3], wm[(i - 1) % 3], wm[i % 3], mt, thin, meta);
+                nms_threshold4(a, wm[(i - 2) % 3], wm[(i - 1) % 3], wm[i % 3], mt, thin, meta, variant);
                 if (EMIT) {
                     float e[4];
 #pragma unroll
@@ -174,7 +174,9 @@ __device__ __forceinline__ void cfast_stage_nms(const FastArgs& a, const Geo geo
 // -------------------------------------------------------------------------------------------
 // forward
 // -------------------------------------------------------------------------------------------
-template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false>
+// VAR / MODE: 0 / -1 = read variant and output mode from the arguments; the hot configuration (models always
+// call the filter with both thresholds and hysteresis=True) is compiled with them as constants.
+template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false, int VAR = 0, int MODE = -1>
 __global__ void __launch_bounds__(256, 3) edge_fwd_canny_fast(const FastArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int DIVM = (NC == 1) ? 0 : (NC == 3 ? 1 : 2);
@@ -188,7 +190,8 @@ __global__ void __launch_bounds__(256, 3) edge_fwd_canny_fast(const FastArgs a) 
     const int tx = threadIdx.x % geo.GX, ty = threadIdx.x / geo.GX;
     const size_t hw = (size_t)H * W;
     const bool active = ty < geo.RY;
-    const int mode = canny_mode(a.e);
+    const int variant = VAR ? VAR : a.e.variant;
+    const int mode = (MODE >= 0) ? MODE : canny_mode(a.e);
     const int hc = (mode == MODE_HYST) ? 1 : 0;
 
     float* R1 = smem;
@@ -207,14 +210,14 @@ __global__ void __launch_bounds__(256, 3) edge_fwd_canny_fast(const FastArgs a) 
     if (active) fast_stage_blur<R>(a, geo, S, s_lo, Bl, b_lo, b_hi, tx, ty);
     __syncthreads();
     float* M = R1; float* META = R3;
-    if (active) cfast_stage_mag_dir<DIVM, R>(a, geo, Bl, b_lo, M, META, m_lo, m_hi, tx, ty);
+    if (active) cfast_stage_mag_dir<DIVM, R>(a, geo, Bl, b_lo, M, META, m_lo, m_hi, tx, ty, variant);
     __syncthreads();
     if (mode != MODE_HYST) {
-        if (active) cfast_stage_nms<NC, BLEND, R, true, NHWC>(a, geo, M, META, m_lo, r0, r1, b, mode, tx, ty);
+        if (active) cfast_stage_nms<NC, BLEND, R, true, NHWC>(a, geo, M, META, m_lo, r0, r1, b, mode, tx, ty, variant);
         return;
     }
     const int c_lo = max(r0 - 1, 0), c_hi = min(r1 + 1, H);
-    if (active) cfast_stage_nms<NC, BLEND, R, false, NHWC>(a, geo, M, META, m_lo, c_lo, c_hi, b, mode, tx, ty);
+    if (active) cfast_stage_nms<NC, BLEND, R, false, NHWC>(a, geo, M, META, m_lo, c_lo, c_hi, b, mode, tx, ty, variant);
     __syncthreads();
     if (!active) return;
     // hysteresis (core.py:317-321 / :494-503): weak = (low+high == 1), kept if the zero-padded 3x3 sum of
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(256, 3) edge_fwd_canny_fast(const FastArgs a) 
 // -------------------------------------------------------------------------------------------
 // backward
 // -------------------------------------------------------------------------------------------
-template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false>
+template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false, int VAR = 0, int MODE = -1>
 #ifndef EE_MINB_CANNY_BWD
 #define EE_MINB_CANNY_BWD 2
 #endif
@@ -263,8 +266,9 @@ __global__ void __launch_bounds__(256, EE_MINB_CANNY_BWD) edge_bwd_canny_fast(co
     const int tx = threadIdx.x % geo.GX, ty = threadIdx.x / geo.GX;
     const size_t hw = (size_t)H * W;
     const bool active = ty < geo.RY;
-    const int mode = canny_mode(a.e);
-    const bool bpda = (a.e.variant == 2);
+    const int variant = VAR ? VAR : a.e.variant;
+    const int mode = (MODE >= 0) ? MODE : canny_mode(a.e);
+    const bool bpda = (variant == 2);
     // the forward edge value (blend) or BPDA's To_eq path need weak_is_high on the A/Bv rows
     const int hc = (mode == MODE_HYST && (BLEND || bpda)) ? 1 : 0;
     const bool want_gx = (a.e.g_x != nullptr);
@@ -299,9 +303,9 @@ __global__ void __launch_bounds__(256, EE_MINB_CANNY_BWD) edge_bwd_canny_fast(co
     if (active) fast_stage_blur<R>(a, geo, S, s_lo, Bl, b_lo, b_hi, tx, ty);
     __syncthreads();
     float* M = R1; float* META = R3;
-    if (active) cfast_stage_mag_dir<DIVM, R>(a, geo, Bl, b_lo, M, META, m_lo, m_hi, tx, ty);
+    if (active) cfast_stage_mag_dir<DIVM, R>(a, geo, Bl, b_lo, M, META, m_lo, m_hi, tx, ty, variant);
     __syncthreads();
-    if (active) cfast_stage_nms<NC, false, R, false>(a, geo, M, META, m_lo, c_lo, c_hi, b, mode, tx, ty);
+    if (active) cfast_stage_nms<NC, false, R, false>(a, geo, M, META, m_lo, c_lo, c_hi, b, mode, tx, ty, variant);
     __syncthreads();
 
     // ---- A / Bv on rows [ab_lo, ab_hi).  thin is kept implicitly: M (magnitude) is recomputed from the
@@ -313,7 +317,7 @@ __global__ void __launch_bounds__(256, EE_MINB_CANNY_BWD) edge_bwd_canny_fast(co
         const float* base_b = a.e.base + (size_t)b * C * hw;
         const float* gin_b = a.e.g_in + (size_t)b * (BLEND ? C : 1) * hw;
         float* gbase_b = a.e.g_base ? a.e.g_base + (size_t)b * C * hw : nullptr;
-        const bool gate = (a.e.variant == 1);
+        const bool gate = (variant == 1);
         EE_FOR_CHUNKS(ab_lo, ab_hi) {
             const int lc = g * 4, col = geo.cs + lc, ra = ab_lo + ch * R, rb = min(ra + R, ab_hi);
             const float* pbl = Bl + kPadL + lc;
@@ -400,7 +404,7 @@ __global__ void __launch_bounds__(256, EE_MINB_CANNY_BWD) edge_bwd_canny_fast(co
                         float av[4], bv[4];
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            float gm = g_thin_of(a.e, mode, ge[k], thin[k], wih[k]);
+                            float gm = g_thin_of_v(variant, a.e.low, a.e.high, mode, ge[k], thin[k], wih[k]);
                             if (meta_removed(meta[k])) gm = 0.0f;                     // core.py:290 / :480
                             if (gate && mag[k] < a.e.alpha) gm = 0.0f;                // torch.where backward
                             mag_backward(gm, mag[k], gx1[k], gy1[k], fC, av[k], bv[k]);
