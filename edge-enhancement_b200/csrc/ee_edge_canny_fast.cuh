@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(256, 3) edge_fwd_canny_fast(const FastArgs a) 
     float* S = R1; float* Bl = R2;
     if (active) fast_stage_sum<NC, R, NHWC>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
 #if EE_L2_PREFETCH
-    if (BLEND && a.tiles_x == 1 && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
+    if (BLEND && (!NHWC || (r0 == 0 && r1 == H)) && a.tiles_x == 1 && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
 #endif
     __syncthreads();
     if (active) fast_stage_blur<R>(a, geo, S, s_lo, Bl, b_lo, b_hi, tx, ty);

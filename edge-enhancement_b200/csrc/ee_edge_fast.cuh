@@ -339,11 +339,11 @@ __global__ void __launch_bounds__(256, EE_MINB_FWD) edge_fwd_step125_fast(const 
     float* Bl = smem + (size_t)min(a.e.TH + 4, H) * Wp;
 
 #if EE_L2_PREFETCH == 1
-    if (BLEND && a.tiles_x == 1 && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
+    if (BLEND && (!NHWC || (r0 == 0 && r1 == H)) && a.tiles_x == 1 && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
 #endif
     if (ty < geo.RY) fast_stage_sum<NC, R, NHWC>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
 #if EE_L2_PREFETCH == 2
-    if (BLEND && a.tiles_x == 1 && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
+    if (BLEND && (!NHWC || (r0 == 0 && r1 == H)) && a.tiles_x == 1 && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
 #endif
     __syncthreads();
     if (ty < geo.RY) fast_stage_blur<R>(a, geo, S, s_lo, Bl, b_lo, b_hi, tx, ty);
@@ -614,12 +614,21 @@ __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const 
 
     float* S = R1; float* Bl = R2;
     auto prefetch_bwd_operands = [&]() {
+        if (NHWC && !(ab_lo == 0 && ab_hi == H)) return;     // channels_last: only the whole-image range is contiguous the same way
         if (C <= 32 && a.tiles_x == 1) {
             if (BLEND) {
                 if (threadIdx.x < 32) prefetch_rows(a.e.base, b, C, H, W, ab_lo, ab_hi, threadIdx.x);
                 else if (threadIdx.x < 64) prefetch_rows(a.e.g_in, b, C, H, W, ab_lo, ab_hi, threadIdx.x - 32);
             } else if (threadIdx.x == 0) {
                 prefetch_rows(a.e.g_in, b, 1, H, W, ab_lo, ab_hi, 0);
+            }
+        } else if (BLEND && a.tiles_x > 1) {
+            // column tile: one bulk prefetch per (tensor, channel, row) segment [cs, ce) of the A/Bv rows
+            const int nrows = ab_hi - ab_lo, seg = (geo.ce - geo.cs) * (int)sizeof(float);
+            for (int i = threadIdx.x; i < 2 * C * nrows; i += blockDim.x) {
+                const int t = i / (C * nrows), rem = i - t * (C * nrows), c = rem / nrows, r = ab_lo + rem - c * nrows;
+                const float* src = (t ? a.e.g_in : a.e.base) + ((size_t)b * C + c) * hw + (size_t)r * W + geo.cs;
+                l2_prefetch_bulk(src, (uint32_t)seg);
             }
         }
     };
