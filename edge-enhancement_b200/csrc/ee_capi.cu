@@ -162,6 +162,17 @@ int launch_fast(K kernel, const Launch& L, int B, const ee::FastArgs& a, cudaStr
     return EE_OK;
 }
 
+// whole-image tiles whose height is a compile-time multiple of R = 4: one chunk per thread (HT instantiations)
+template <typename K>
+int launch_fast_even(K kernel, Launch L, int B, const ee::FastArgs& a, cudaStream_t s, const char* name) {
+    L.RY = a.e.H / 4;
+    L.threads = ((L.GX * L.RY + 31) / 32) * 32;
+    return launch_fast(kernel, L, B, a, s, name);
+}
+bool whole_image(const Launch& L, const ee::FastArgs& f, int side) {
+    return L.tiles_x == 1 && L.TH == f.e.H && f.e.H == side && f.e.W == side && L.GX == side / 4;
+}
+
 bool fast_eligible(const ee::EdgeArgs& a, bool vec_ok) {
     if (g_staging.load() == 1 || !vec_ok || a.W < 8 || a.H < 4) return false;
     return std::isfinite(a.high) && std::isfinite(a.alpha) && std::isfinite(a.low) && fabsf(a.high) < 1e18f &&
@@ -198,6 +209,7 @@ void fill_fast(ee::FastArgs& f, const ee::EdgeArgs& a, const Launch& L) {
 // images); everything else runs the runtime-width instantiation <.., 0, 0> of the same kernel.
 #define EE_DISPATCH_FAST_NHWC(KERNEL, L, B, f, s, name)                                           \
     do {                                                                                          \
+        if (whole_image(L, f, 64)) return launch_fast_even(KERNEL<3, true, 4, 64, 64, true, 64>, L, B, f, s, name); \
         if ((L).tiles_x == 1 && (f).e.W == 64) return launch_fast(KERNEL<3, true, 4, 64, 64, true>, L, B, f, s, name); \
         return launch_fast(KERNEL<3, true, 4, 0, 0, true>, L, B, f, s, name);                     \
     } while (0)
@@ -206,6 +218,9 @@ void fill_fast(ee::FastArgs& f, const ee::EdgeArgs& a, const Launch& L) {
     do {                                                                                          \
         const int W_ = (f).e.W, C_ = (f).e.C;                                                     \
         if ((L).tiles_x == 1) {                                                                   \
+            if (C_ == 3 && whole_image(L, f, 64)) return launch_fast_even(KERNEL<3, BLEND, 4, 64, 64, false, 64>, L, B, f, s, name); \
+            if (C_ == 3 && whole_image(L, f, 32)) return launch_fast_even(KERNEL<3, BLEND, 4, 32, 32, false, 32>, L, B, f, s, name); \
+            if (C_ == 1 && whole_image(L, f, 28)) return launch_fast_even(KERNEL<1, BLEND, 4, 28, 28, false, 28>, L, B, f, s, name); \
             if (C_ == 3 && W_ == 64) return launch_fast(KERNEL<3, BLEND, 4, 64, 64>, L, B, f, s, name); \
             if (C_ == 3 && W_ == 32) return launch_fast(KERNEL<3, BLEND, 4, 32, 32>, L, B, f, s, name); \
             if (C_ == 1 && W_ == 28) return launch_fast(KERNEL<1, BLEND, 4, 28, 28>, L, B, f, s, name); \
@@ -340,9 +355,14 @@ int edge_forward(const float* x, const float* base, float* out, float* edge, int
         ee::FastArgs f;
         fill_fast(f, a, L);
         if (blend && hot_canny(f, L)) {
+            if (whole_image(L, f, 64)) {
+                if (p->variant == EE_VARIANT_CANNY)
+                    return launch_fast_even(ee::edge_fwd_canny_fast<3, true, 4, 64, 64, false, 64, 1, ee::MODE_HYST>, L, B, f, s, "edge_fwd_canny_fast");
+                return launch_fast_even(ee::edge_fwd_canny_fast<3, true, 4, 64, 64, false, 64, 2, ee::MODE_HYST>, L, B, f, s, "edge_fwd_canny_fast");
+            }
             if (p->variant == EE_VARIANT_CANNY)
-                return launch_fast(ee::edge_fwd_canny_fast<3, true, 4, 64, 64, false, 1, ee::MODE_HYST>, L, B, f, s, "edge_fwd_canny_fast");
-            return launch_fast(ee::edge_fwd_canny_fast<3, true, 4, 64, 64, false, 2, ee::MODE_HYST>, L, B, f, s, "edge_fwd_canny_fast");
+                return launch_fast(ee::edge_fwd_canny_fast<3, true, 4, 64, 64, false, 0, 1, ee::MODE_HYST>, L, B, f, s, "edge_fwd_canny_fast");
+            return launch_fast(ee::edge_fwd_canny_fast<3, true, 4, 64, 64, false, 0, 2, ee::MODE_HYST>, L, B, f, s, "edge_fwd_canny_fast");
         }
         if (blend) EE_DISPATCH_FAST(ee::edge_fwd_canny_fast, true, L, B, f, s, "edge_fwd_canny_fast");
         else EE_DISPATCH_FAST(ee::edge_fwd_canny_fast, false, L, B, f, s, "edge_fwd_canny_fast");
@@ -401,9 +421,14 @@ int edge_backward(const float* g_in, const float* x, const float* base, float* g
         ee::FastArgs f;
         fill_fast(f, a, L);
         if (blend && hot_canny(f, L)) {
+            if (whole_image(L, f, 64)) {
+                if (p->variant == EE_VARIANT_CANNY)
+                    return launch_fast_even(ee::edge_bwd_canny_fast<3, true, 4, 64, 64, false, 64, 1, ee::MODE_HYST>, L, B, f, s, "edge_bwd_canny_fast");
+                return launch_fast_even(ee::edge_bwd_canny_fast<3, true, 4, 64, 64, false, 64, 2, ee::MODE_HYST>, L, B, f, s, "edge_bwd_canny_fast");
+            }
             if (p->variant == EE_VARIANT_CANNY)
-                return launch_fast(ee::edge_bwd_canny_fast<3, true, 4, 64, 64, false, 1, ee::MODE_HYST>, L, B, f, s, "edge_bwd_canny_fast");
-            return launch_fast(ee::edge_bwd_canny_fast<3, true, 4, 64, 64, false, 2, ee::MODE_HYST>, L, B, f, s, "edge_bwd_canny_fast");
+                return launch_fast(ee::edge_bwd_canny_fast<3, true, 4, 64, 64, false, 0, 1, ee::MODE_HYST>, L, B, f, s, "edge_bwd_canny_fast");
+            return launch_fast(ee::edge_bwd_canny_fast<3, true, 4, 64, 64, false, 0, 2, ee::MODE_HYST>, L, B, f, s, "edge_bwd_canny_fast");
         }
         if (blend) EE_DISPATCH_FAST(ee::edge_bwd_canny_fast, true, L, B, f, s, "edge_bwd_canny_fast");
         else EE_DISPATCH_FAST(ee::edge_bwd_canny_fast, false, L, B, f, s, "edge_bwd_canny_fast");

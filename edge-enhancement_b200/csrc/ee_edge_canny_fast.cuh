@@ -30,24 +30,24 @@ __device__ __forceinline__ void win_to_array(const Win& w, float (&e)[6]) {
 __device__ __forceinline__ Win zero_win() { Win w; w.l = w.m0 = w.m1 = w.m2 = w.m3 = w.r = 0.0f; return w; }
 
 // ---- stage MB: M (gated magnitude) and META (direction) rows [lo,hi) from the blurred plane ----
-template <int DIVM, int R>
+template <int DIVM, int R, bool EVEN = false>
 __device__ __forceinline__ void cfast_stage_mag_dir(const FastArgs& a, const Geo geo, const float* Bl, int b_lo, float* M,
                                                     float* META, int lo, int hi, int tx, int ty, const int variant) {
     const int W = geo.W, H = geo.H, Wp = geo.Wp;
     const float fC = a.e.fC;
     const bool gate = (variant == 1);                // only CannyFilter applies alpha (core.py:263-264)
-    EE_FOR_CHUNKS(lo, hi) {
-        const int lc = g * 4, col = geo.cs + lc, ra = lo + ch * R, rb = min(ra + R, hi);
+    EE_FOR_CHUNKS_E(lo, hi) {
+        const int lc = g * 4, col = geo.cs + lc, ra = lo + ch * R, rb = EVEN ? ra + R : min(ra + R, hi);
         const float* pbl = Bl + kPadL + lc;
         float D[3][4], V[3][4];
 #pragma unroll
         for (int i = 0; i < R + 2; ++i) {
             const int rin = ra - 1 + i;
-            if (rin <= rb) {
+            if (EVEN || rin <= rb) {
                 const int rc = min(max(rin, 0), H - 1);
                 sobel_partials(ld_win(pbl + (rc - b_lo) * Wp), D[i % 3], V[i % 3]);
             }
-            if (i >= 2 && ra + i - 2 < rb) {
+            if (i >= 2 && (EVEN || ra + i - 2 < rb)) {
                 float sgx[4], sgy[4], gx1[4], gy1[4], mm[4], mt[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -137,20 +137,23 @@ __device__ __forceinline__ void cfast_emit(const FastArgs& a, const Geo geo, int
 
 // ---- stage NMS: rows [lo,hi).  EMIT = false: update META in place (hysteresis needs a 3x3 sum of it);
 //      EMIT = true: the non-hysteresis modes write their output directly. ------------------------------
-template <int NC, bool BLEND, int R, bool EMIT, bool NHWC = false>
+template <int NC, bool BLEND, int R, bool EMIT, bool NHWC = false, bool EVEN = false>
 __device__ __forceinline__ void cfast_stage_nms(const FastArgs& a, const Geo geo, const float* M, float* META, int m_lo,
                                                 int lo, int hi, int b, int mode, int tx, int ty, const int variant) {
     const int H = geo.H, Wp = geo.Wp;
-    EE_FOR_CHUNKS(lo, hi) {
-        const int lc = g * 4, col = geo.cs + lc, ra = lo + ch * R, rb = min(ra + R, hi);
-        if (EMIT && (col < geo.c0 || col >= geo.c1)) continue;   // halo groups produce no output
+    EE_FOR_CHUNKS_E(lo, hi) {
+        const int lc = g * 4, col = geo.cs + lc, ra = lo + ch * R, rb = EVEN ? ra + R : min(ra + R, hi);
+        if (!EVEN && EMIT && (col < geo.c0 || col >= geo.c1)) continue;   // halo groups produce no output
         const float* pm = M + kPadL + lc;
         Win wm[3];
 #pragma unroll
         for (int i = 0; i < R + 2; ++i) {
             const int rin = ra - 1 + i;
-            if (rin <= rb) wm[i % 3] = (rin >= 0 && rin < H) ? ld_win(pm + (rin - m_lo) * Wp) : zero_win();
-            if (i >= 2 && ra + i - 2 < rb) {
+            if (EVEN || rin <= rb) {
+                if (EVEN && i > 0 && i < R + 1) wm[i % 3] = ld_win(pm + (rin - m_lo) * Wp);
+                else wm[i % 3] = (rin >= 0 && rin < H) ? ld_win(pm + (rin - m_lo) * Wp) : zero_win();
+            }
+            if (i >= 2 && (EVEN || ra + i - 2 < rb)) {
                 const int p = ra + i - 2;
                 float* pmeta = META + (p - m_lo) * Wp + kPadL + lc;
                 const float4 mt = *reinterpret_cast<const float4*>(pmeta);
@@ -176,62 +179,69 @@ __device__ __forceinline__ void cfast_stage_nms(const FastArgs& a, const Geo geo
 // -------------------------------------------------------------------------------------------
 // VAR / MODE: 0 / -1 = read variant and output mode from the arguments; the hot configuration (models always
 // call the filter with both thresholds and hysteresis=True) is compiled with them as constants.
-template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false, int VAR = 0, int MODE = -1>
+template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false, int HT = 0, int VAR = 0, int MODE = -1>
 __global__ void __launch_bounds__(256, 3) edge_fwd_canny_fast(const FastArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int DIVM = (NC == 1) ? 0 : (NC == 3 ? 1 : 2);
-    const int b = blockIdx.x / a.e.tiles_per_img;
-    const int tq = blockIdx.x - b * a.e.tiles_per_img;
-    const int ti = tq / a.tiles_x;                                   // row-strip index; column tile = tq % tiles_x
-    const Geo geo = make_geo<WT, WG>(a, tq - ti * a.tiles_x);
+    constexpr bool EVEN = (HT != 0);
+    static_assert(!EVEN || (WT != 0 && WT == WG && HT % R == 0), "HT needs a single constant-width column tile");
+    const int b = EVEN ? blockIdx.x : blockIdx.x / a.e.tiles_per_img;
+    const int tq = EVEN ? 0 : blockIdx.x - b * a.e.tiles_per_img;
+    const int ti = EVEN ? 0 : tq / a.tiles_x;                        // row-strip index; column tile = tq % tiles_x
+    Geo geo = make_geo<WT, WG>(a, tq - ti * a.tiles_x);
+    if (EVEN) { geo.H = HT; geo.RY = HT / R; }
     const int H = geo.H, W = geo.W, Wp = geo.Wp;
     const int C = NC ? NC : a.e.C;
-    const int r0 = ti * a.e.TH, r1 = min(r0 + a.e.TH, H);
+    const int r0 = EVEN ? 0 : ti * a.e.TH, r1 = EVEN ? HT : min(r0 + a.e.TH, H);
     const int tx = threadIdx.x % geo.GX, ty = threadIdx.x / geo.GX;
     const size_t hw = (size_t)H * W;
     const bool active = ty < geo.RY;
     const int variant = VAR ? VAR : a.e.variant;
     const int mode = (MODE >= 0) ? MODE : canny_mode(a.e);
     const int hc = (mode == MODE_HYST) ? 1 : 0;
+    const bool one_tile = EVEN || a.tiles_x == 1;
 
     float* R1 = smem;
-    float* R2 = R1 + (size_t)min(a.e.TH + 8, H) * Wp;
-    float* R3 = R2 + (size_t)min(a.e.TH + 6, H) * Wp;
+    float* R2 = R1 + (size_t)(EVEN ? HT : min(a.e.TH + 8, H)) * Wp;
+    float* R3 = R2 + (size_t)(EVEN ? HT : min(a.e.TH + 6, H)) * Wp;
     const int s_lo = max(r0 - 3 - hc, 0), s_hi = min(r1 + 3 + hc, H);
     const int b_lo = max(r0 - 2 - hc, 0), b_hi = min(r1 + 2 + hc, H);
     const int m_lo = max(r0 - 1 - hc, 0), m_hi = min(r1 + 1 + hc, H);
 
     float* S = R1; float* Bl = R2;
-    if (active) fast_stage_sum<NC, R, NHWC>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
+    if (active) fast_stage_sum<NC, R, NHWC, EVEN>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
 #if EE_L2_PREFETCH
-    if (BLEND && (!NHWC || (r0 == 0 && r1 == H)) && a.tiles_x == 1 && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
+    if (BLEND && (!NHWC || (r0 == 0 && r1 == H)) && one_tile && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
 #endif
     __syncthreads();
-    if (active) fast_stage_blur<R>(a, geo, S, s_lo, Bl, b_lo, b_hi, tx, ty);
+    if (active) fast_stage_blur<R, EVEN>(a, geo, S, s_lo, Bl, b_lo, b_hi, tx, ty);
     __syncthreads();
     float* M = R1; float* META = R3;
-    if (active) cfast_stage_mag_dir<DIVM, R>(a, geo, Bl, b_lo, M, META, m_lo, m_hi, tx, ty, variant);
+    if (active) cfast_stage_mag_dir<DIVM, R, EVEN>(a, geo, Bl, b_lo, M, META, m_lo, m_hi, tx, ty, variant);
     __syncthreads();
     if (mode != MODE_HYST) {
-        if (active) cfast_stage_nms<NC, BLEND, R, true, NHWC>(a, geo, M, META, m_lo, r0, r1, b, mode, tx, ty, variant);
+        if (active) cfast_stage_nms<NC, BLEND, R, true, NHWC, EVEN>(a, geo, M, META, m_lo, r0, r1, b, mode, tx, ty, variant);
         return;
     }
     const int c_lo = max(r0 - 1, 0), c_hi = min(r1 + 1, H);
-    if (active) cfast_stage_nms<NC, BLEND, R, false, NHWC>(a, geo, M, META, m_lo, c_lo, c_hi, b, mode, tx, ty, variant);
+    if (active) cfast_stage_nms<NC, BLEND, R, false, NHWC, EVEN>(a, geo, M, META, m_lo, c_lo, c_hi, b, mode, tx, ty, variant);
     __syncthreads();
     if (!active) return;
     // hysteresis (core.py:317-321 / :494-503): weak = (low+high == 1), kept if the zero-padded 3x3 sum of
     // (low+high) is >= 2; edge = high + weak_is_high
-    EE_FOR_CHUNKS(r0, r1) {
-        const int lc = g * 4, col = geo.cs + lc, ra = r0 + ch * R, rb = min(ra + R, r1);
-        if (col < geo.c0 || col >= geo.c1) continue;             // halo groups produce no output
+    EE_FOR_CHUNKS_E(r0, r1) {
+        const int lc = g * 4, col = geo.cs + lc, ra = r0 + ch * R, rb = EVEN ? ra + R : min(ra + R, r1);
+        if (!EVEN && (col < geo.c0 || col >= geo.c1)) continue;  // halo groups produce no output
         const float* pmt = META + kPadL + lc;
         int hs[3][4], cw[3][4];
 #pragma unroll
         for (int i = 0; i < R + 2; ++i) {
             const int rin = ra - 1 + i;
-            if (rin <= rb) meta_partials((rin >= 0 && rin < H) ? ld_win(pmt + (rin - m_lo) * Wp) : zero_win(), hs[i % 3], cw[i % 3]);
-            if (i >= 2 && ra + i - 2 < rb) {
+            if (EVEN || rin <= rb) {
+                if (EVEN && i > 0 && i < R + 1) meta_partials(ld_win(pmt + (rin - m_lo) * Wp), hs[i % 3], cw[i % 3]);
+                else meta_partials((rin >= 0 && rin < H) ? ld_win(pmt + (rin - m_lo) * Wp) : zero_win(), hs[i % 3], cw[i % 3]);
+            }
+            if (i >= 2 && (EVEN || ra + i - 2 < rb)) {
                 float e[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -249,20 +259,23 @@ __global__ void __launch_bounds__(256, 3) edge_fwd_canny_fast(const FastArgs a) 
 // -------------------------------------------------------------------------------------------
 // backward
 // -------------------------------------------------------------------------------------------
-template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false, int VAR = 0, int MODE = -1>
+template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false, int HT = 0, int VAR = 0, int MODE = -1>
 #ifndef EE_MINB_CANNY_BWD
 #define EE_MINB_CANNY_BWD 2
 #endif
 __global__ void __launch_bounds__(256, EE_MINB_CANNY_BWD) edge_bwd_canny_fast(const FastArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int DIVM = (NC == 1) ? 0 : (NC == 3 ? 1 : 2);
-    const int b = blockIdx.x / a.e.tiles_per_img;
-    const int tq = blockIdx.x - b * a.e.tiles_per_img;
-    const int ti = tq / a.tiles_x;                                   // row-strip index; column tile = tq % tiles_x
-    const Geo geo = make_geo<WT, WG>(a, tq - ti * a.tiles_x);
+    constexpr bool EVEN = (HT != 0);
+    static_assert(!EVEN || (WT != 0 && WT == WG && HT % R == 0), "HT needs a single constant-width column tile");
+    const int b = EVEN ? blockIdx.x : blockIdx.x / a.e.tiles_per_img;
+    const int tq = EVEN ? 0 : blockIdx.x - b * a.e.tiles_per_img;
+    const int ti = EVEN ? 0 : tq / a.tiles_x;                        // row-strip index; column tile = tq % tiles_x
+    Geo geo = make_geo<WT, WG>(a, tq - ti * a.tiles_x);
+    if (EVEN) { geo.H = HT; geo.RY = HT / R; }
     const int H = geo.H, W = geo.W, Wp = geo.Wp;
     const int C = NC ? NC : a.e.C;
-    const int r0 = ti * a.e.TH, r1 = min(r0 + a.e.TH, H);
+    const int r0 = EVEN ? 0 : ti * a.e.TH, r1 = EVEN ? HT : min(r0 + a.e.TH, H);
     const int tx = threadIdx.x % geo.GX, ty = threadIdx.x / geo.GX;
     const size_t hw = (size_t)H * W;
     const bool active = ty < geo.RY;
@@ -276,9 +289,9 @@ __global__ void __launch_bounds__(256, EE_MINB_CANNY_BWD) edge_bwd_canny_fast(co
     const float fC = a.e.fC, wgt = a.e.w;
 
     float* R1 = smem;
-    float* R2 = R1 + (size_t)min(a.e.TH + 12, H) * Wp;
-    float* R3 = R2 + (size_t)min(a.e.TH + 10, H) * Wp;
-    float* R4 = R3 + (size_t)min(a.e.TH + 8, H) * Wp;
+    float* R2 = R1 + (size_t)(EVEN ? HT : min(a.e.TH + 12, H)) * Wp;
+    float* R3 = R2 + (size_t)(EVEN ? HT : min(a.e.TH + 10, H)) * Wp;
+    float* R4 = R3 + (size_t)(EVEN ? HT : min(a.e.TH + 8, H)) * Wp;
 
     const int ab_lo = max(r0 - ha, 0), ab_hi = min(r1 + ha, H);
     const int c_lo = max(r0 - ha - hc, 0), c_hi = min(r1 + ha + hc, H);
@@ -288,9 +301,9 @@ __global__ void __launch_bounds__(256, EE_MINB_CANNY_BWD) edge_bwd_canny_fast(co
     const int gb_lo = max(r0 - 1, 0), gb_hi = min(r1 + 1, H);
 
     float* S = R1; float* Bl = R2;
-    if (active) fast_stage_sum<NC, R, NHWC>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
+    if (active) fast_stage_sum<NC, R, NHWC, EVEN>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
 #if EE_L2_PREFETCH_BWD_CANNY       // measured -8 % on the Canny backward (2 CTAs/SM, operands needed 4 stages later): off
-    if (C <= 32 && a.tiles_x == 1) {            // operands of the A/Bv stage, three stages from now
+    if (C <= 32 && (EVEN || a.tiles_x == 1)) {            // operands of the A/Bv stage, three stages from now
         if (BLEND) {
             if (threadIdx.x < 32) prefetch_rows(a.e.base, b, C, H, W, ab_lo, ab_hi, threadIdx.x);
             else if (threadIdx.x < 64) prefetch_rows(a.e.g_in, b, C, H, W, ab_lo, ab_hi, threadIdx.x - 32);
@@ -300,12 +313,12 @@ __global__ void __launch_bounds__(256, EE_MINB_CANNY_BWD) edge_bwd_canny_fast(co
     }
 #endif
     __syncthreads();
-    if (active) fast_stage_blur<R>(a, geo, S, s_lo, Bl, b_lo, b_hi, tx, ty);
+    if (active) fast_stage_blur<R, EVEN>(a, geo, S, s_lo, Bl, b_lo, b_hi, tx, ty);
     __syncthreads();
     float* M = R1; float* META = R3;
-    if (active) cfast_stage_mag_dir<DIVM, R>(a, geo, Bl, b_lo, M, META, m_lo, m_hi, tx, ty, variant);
+    if (active) cfast_stage_mag_dir<DIVM, R, EVEN>(a, geo, Bl, b_lo, M, META, m_lo, m_hi, tx, ty, variant);
     __syncthreads();
-    if (active) cfast_stage_nms<NC, false, R, false>(a, geo, M, META, m_lo, c_lo, c_hi, b, mode, tx, ty, variant);
+    if (active) cfast_stage_nms<NC, false, R, false, false, EVEN>(a, geo, M, META, m_lo, c_lo, c_hi, b, mode, tx, ty, variant);
     __syncthreads();
 
     // ---- A / Bv on rows [ab_lo, ab_hi).  thin is kept implicitly: M (magnitude) is recomputed from the
@@ -318,8 +331,8 @@ __global__ void __launch_bounds__(256, EE_MINB_CANNY_BWD) edge_bwd_canny_fast(co
         const float* gin_b = a.e.g_in + (size_t)b * (BLEND ? C : 1) * hw;
         float* gbase_b = a.e.g_base ? a.e.g_base + (size_t)b * C * hw : nullptr;
         const bool gate = (variant == 1);
-        EE_FOR_CHUNKS(ab_lo, ab_hi) {
-            const int lc = g * 4, col = geo.cs + lc, ra = ab_lo + ch * R, rb = min(ra + R, ab_hi);
+        EE_FOR_CHUNKS_E(ab_lo, ab_hi) {
+            const int lc = g * 4, col = geo.cs + lc, ra = ab_lo + ch * R, rb = EVEN ? ra + R : min(ra + R, ab_hi);
             const float* pbl = Bl + kPadL + lc;
             const float* pmt = META + kPadL + lc;
             float D[3][4], V[3][4];
@@ -327,18 +340,18 @@ __global__ void __launch_bounds__(256, EE_MINB_CANNY_BWD) edge_bwd_canny_fast(co
 #pragma unroll
             for (int i = 0; i < R + 2; ++i) {
                 const int rin = ra - 1 + i;
-                if (rin <= rb) {
+                if (EVEN || rin <= rb) {
                     const int rc = min(max(rin, 0), H - 1);
                     sobel_partials(ld_win(pbl + (rc - b_lo) * Wp), D[i % 3], V[i % 3]);
                     if (hc) {
                         meta_partials((rin >= 0 && rin < H) ? ld_win(pmt + (rin - m_lo) * Wp) : zero_win(), hs[i % 3], cw[i % 3]);
-                    } else if (rin >= ra && rin < rb) {
+                    } else if (EVEN ? (i > 0 && i < R + 1) : (rin >= ra && rin < rb)) {
                         const float4 t = *reinterpret_cast<const float4*>(pmt + (rin - m_lo) * Wp);
                         cw[i % 3][0] = __float_as_int(t.x); cw[i % 3][1] = __float_as_int(t.y);
                         cw[i % 3][2] = __float_as_int(t.z); cw[i % 3][3] = __float_as_int(t.w);
                     }
                 }
-                if (i >= 2 && ra + i - 2 < rb) {
+                if (i >= 2 && (EVEN || ra + i - 2 < rb)) {
                     const int rout = ra + i - 2;
                     const int pix = rout * W + col;
                     float gx1[4], gy1[4], sgx[4], sgy[4], mag[4], thin[4], ge[4];
@@ -369,7 +382,7 @@ __global__ void __launch_bounds__(256, EE_MINB_CANNY_BWD) edge_bwd_canny_fast(co
                                                                 : edge_value_simple(mode, thin[k], meta[k]);
                             we[k] = wgt * e;
                         }
-                        const bool interior = (rout >= r0 && rout < r1 && col >= geo.c0 && col < geo.c1);
+                        const bool interior = EVEN || (rout >= r0 && rout < r1 && col >= geo.c0 && col < geo.c1);
                         float4 bs[NC ? NC : 1], go[NC ? NC : 1];
                         if (NC) {
                             ld_px4<NC, NHWC>(base_b, hw, pix, bs);
@@ -420,9 +433,9 @@ __global__ void __launch_bounds__(256, EE_MINB_CANNY_BWD) edge_bwd_canny_fast(co
     if (!want_gx) return;
     __syncthreads();
     float* GB = R2;
-    if (active) fast_stage_sobel_adjoint<R>(geo, A, Bv, ab_lo, GB, gb_lo, gb_hi, tx, ty);
+    if (active) fast_stage_sobel_adjoint<R, EVEN>(geo, A, Bv, ab_lo, GB, gb_lo, gb_hi, tx, ty);
     __syncthreads();
-    if (active) fast_stage_gauss_adjoint_store<NC, R, NHWC>(a, geo, GB, gb_lo, a.e.g_x + (size_t)b * C * hw, r0, r1, tx, ty);
+    if (active) fast_stage_gauss_adjoint_store<NC, R, NHWC, EVEN>(a, geo, GB, gb_lo, a.e.g_x + (size_t)b * C * hw, r0, r1, tx, ty);
 }
 
 }  // namespace ee

@@ -142,6 +142,12 @@ __device__ __forceinline__ Geo make_geo(const FastArgs& a, int tile_x) {
 #define EE_FOR_CHUNKS(row_lo, row_hi)                                                         \
     for (int ch = ty, n_ch = ((row_hi) - (row_lo) + R - 1) / R; ch < n_ch; ch += geo.RY)      \
         for (int g = tx; g < geo.Gt; g += geo.GX)
+// EVEN (whole-image tile whose height is a multiple of R, one chunk of exactly R rows per active thread):
+// the loops run once and every "is this row inside the chunk" guard is compile-time true
+#define EE_FOR_CHUNKS_E(row_lo, row_hi)                                                                        \
+    for (int ch = ty, n_ch = ((row_hi) - (row_lo) + R - 1) / R, o1_ = 1; EVEN ? o1_ : ch < n_ch;               \
+         ch += geo.RY, o1_ = 0)                                                                                \
+        for (int g = tx, o2_ = 1; EVEN ? o2_ : g < geo.Gt; g += geo.GX, o2_ = 0)
 
 // Every chunk body exists twice: FULL (all R rows present, no image border inside the chunk: no
 // guards, no clamps) and the guarded general version.  `full_t` / `part_t` select them.
@@ -190,18 +196,18 @@ __device__ __forceinline__ void st_px4(float* img, size_t hw, int pix, const flo
 }
 
 // ---- stage S: channel sum of x rows [lo,hi) into a replicate-padded plane -------------------
-template <int NC, int R, bool NHWC = false>
+template <int NC, int R, bool NHWC = false, bool EVEN = false>
 __device__ __forceinline__ void fast_stage_sum(const FastArgs& a, const Geo geo, const float* __restrict__ xb, float* S,
                                                int lo, int hi, int tx, int ty) {
     const int W = geo.W, Wp = geo.Wp;
     const int C = NC ? NC : a.e.C;
     const size_t hw = (size_t)geo.H * W;
-    EE_FOR_CHUNKS(lo, hi) {
+    EE_FOR_CHUNKS_E(lo, hi) {
         const int lc = g * 4, col = geo.cs + lc, ra = lo + ch * R;
         const float* px = xb + (size_t)ra * W + col;
         float* ps = S + (size_t)(ra - lo) * Wp + kPadL + lc;
         auto body = [&](auto tag) {
-            constexpr bool FULL = decltype(tag)::value;
+            constexpr bool FULL = decltype(tag)::value || EVEN;
             float4 acc[R];
             if (NHWC) {
                 float4 v1[R], v2[R];
@@ -272,13 +278,13 @@ __device__ __forceinline__ void gauss_partials(const Win& w, float c0, float c1,
 #define EE_FWD_CHUNK_IS_FULL(ra, rb, H) (EE_USE_FULL && (rb) - (ra) == R && (ra) > 0 && (rb) < (H))
 
 // ---- stage blur: Bl rows [lo,hi) from S ------------------------------------------------------
-template <int R>
+template <int R, bool EVEN = false>
 __device__ __forceinline__ void fast_stage_blur(const FastArgs& a, const Geo geo, const float* S, int s_lo, float* Bl,
                                                 int lo, int hi, int tx, int ty) {
     const int W = geo.W, H = geo.H, Wp = geo.Wp;
     const float c0 = a.e.c0, c1 = a.e.c1, c2 = a.e.c2;
-    EE_FOR_CHUNKS(lo, hi) {
-        const int lc = g * 4, col = geo.cs + lc, ra = lo + ch * R, rb = min(ra + R, hi);
+    EE_FOR_CHUNKS_E(lo, hi) {
+        const int lc = g * 4, col = geo.cs + lc, ra = lo + ch * R, rb = EVEN ? ra + R : min(ra + R, hi);
         const float* ps = S + kPadL + lc;                 // row r at ps + (r - s_lo) * Wp
         float* pb = Bl + (size_t)(ra - lo) * Wp + kPadL + lc;
         auto body = [&](auto tag) {
@@ -287,11 +293,11 @@ __device__ __forceinline__ void fast_stage_blur(const FastArgs& a, const Geo geo
 #pragma unroll
             for (int i = 0; i < R + 2; ++i) {
                 const int rin = ra - 1 + i;
-                if (FULL || rin <= rb) {
+                if (FULL || EVEN || rin <= rb) {
                     const int rc = FULL ? rin : min(max(rin, 0), H - 1);
                     gauss_partials(ld_win(ps + (rc - s_lo) * Wp), c0, c1, c2, P[i % 3], Q[i % 3]);
                 }
-                if (i >= 2 && (FULL || ra + i - 2 < rb)) {
+                if (i >= 2 && (FULL || EVEN || ra + i - 2 < rb)) {
                     float o[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) o[k] = (P[(i - 2) % 3][k] + Q[(i - 1) % 3][k]) + P[i % 3][k];
@@ -313,7 +319,9 @@ __device__ __forceinline__ void sobel_partials(const Win& w, float (&D)[4], floa
 // -------------------------------------------------------------------------------------------
 // forward:  planes S (TH+4 rows) and Bl (TH+2 rows), both with stride Wp
 // -------------------------------------------------------------------------------------------
-template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false>
+// HT != 0: the tile is the whole image, H == HT is a compile-time constant and a multiple of R, so every active
+// thread owns exactly one chunk of R rows in every stage ("EVEN"): chunk loops and row guards disappear.
+template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false, int HT = 0>
 #ifndef EE_MINB_FWD
 #define EE_MINB_FWD 3
 #endif
@@ -323,39 +331,43 @@ template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false>
 __global__ void __launch_bounds__(256, EE_MINB_FWD) edge_fwd_step125_fast(const FastArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int DIVM = (NC == 1) ? 0 : (NC == 3 ? 1 : 2);
-    const int b = blockIdx.x / a.e.tiles_per_img;
-    const int tq = blockIdx.x - b * a.e.tiles_per_img;
-    const int ti = tq / a.tiles_x;                                   // row-strip index; column tile = tq % tiles_x
-    const Geo geo = make_geo<WT, WG>(a, tq - ti * a.tiles_x);
+    constexpr bool EVEN = (HT != 0);
+    static_assert(!EVEN || (WT != 0 && WT == WG && HT % R == 0), "HT needs a single constant-width column tile");
+    const int b = EVEN ? blockIdx.x : blockIdx.x / a.e.tiles_per_img;
+    const int tq = EVEN ? 0 : blockIdx.x - b * a.e.tiles_per_img;
+    const int ti = EVEN ? 0 : tq / a.tiles_x;                        // row-strip index; column tile = tq % tiles_x
+    Geo geo = make_geo<WT, WG>(a, tq - ti * a.tiles_x);
+    if (EVEN) { geo.H = HT; geo.RY = HT / R; }
     const int H = geo.H, W = geo.W, Wp = geo.Wp;
     const int C = NC ? NC : a.e.C;
-    const int r0 = ti * a.e.TH, r1 = min(r0 + a.e.TH, H);
+    const int r0 = EVEN ? 0 : ti * a.e.TH, r1 = EVEN ? HT : min(r0 + a.e.TH, H);
     const int tx = threadIdx.x % geo.GX, ty = threadIdx.x / geo.GX;
     const size_t hw = (size_t)H * W;
 
     const int s_lo = max(r0 - 2, 0), s_hi = min(r1 + 2, H);
     const int b_lo = max(r0 - 1, 0), b_hi = min(r1 + 1, H);
     float* S = smem;
-    float* Bl = smem + (size_t)min(a.e.TH + 4, H) * Wp;
+    float* Bl = smem + (size_t)(EVEN ? HT : min(a.e.TH + 4, H)) * Wp;
+    const bool one_tile = EVEN || a.tiles_x == 1;
 
 #if EE_L2_PREFETCH == 1
-    if (BLEND && (!NHWC || (r0 == 0 && r1 == H)) && a.tiles_x == 1 && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
+    if (BLEND && (!NHWC || (r0 == 0 && r1 == H)) && one_tile && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
 #endif
-    if (ty < geo.RY) fast_stage_sum<NC, R, NHWC>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
+    if (ty < geo.RY) fast_stage_sum<NC, R, NHWC, EVEN>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
 #if EE_L2_PREFETCH == 2
-    if (BLEND && (!NHWC || (r0 == 0 && r1 == H)) && a.tiles_x == 1 && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
+    if (BLEND && (!NHWC || (r0 == 0 && r1 == H)) && one_tile && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
 #endif
     __syncthreads();
-    if (ty < geo.RY) fast_stage_blur<R>(a, geo, S, s_lo, Bl, b_lo, b_hi, tx, ty);
+    if (ty < geo.RY) fast_stage_blur<R, EVEN>(a, geo, S, s_lo, Bl, b_lo, b_hi, tx, ty);
     __syncthreads();
     if (ty >= geo.RY) return;
 
     const float fC = a.e.fC, wgt = a.e.w;
     const float* base_b = a.e.base + (size_t)b * C * hw;
     float* out_b = a.e.out + (size_t)b * C * hw;
-    EE_FOR_CHUNKS(r0, r1) {
-        const int lc = g * 4, col = geo.cs + lc, ra = r0 + ch * R, rb = min(ra + R, r1);
-        if (col < geo.c0 || col >= geo.c1) continue;             // halo groups produce no output
+    EE_FOR_CHUNKS_E(r0, r1) {
+        const int lc = g * 4, col = geo.cs + lc, ra = r0 + ch * R, rb = EVEN ? ra + R : min(ra + R, r1);
+        if (!EVEN && (col < geo.c0 || col >= geo.c1)) continue;  // halo groups produce no output
         const float* pbl = Bl + kPadL + lc;
         auto body = [&](auto tag) {
             constexpr bool FULL = decltype(tag)::value;
@@ -363,11 +375,11 @@ __global__ void __launch_bounds__(256, EE_MINB_FWD) edge_fwd_step125_fast(const 
 #pragma unroll
             for (int i = 0; i < R + 2; ++i) {
                 const int rin = ra - 1 + i;
-                if (FULL || rin <= rb) {
+                if (FULL || EVEN || rin <= rb) {
                     const int rc = FULL ? rin : min(max(rin, 0), H - 1);
                     sobel_partials(ld_win(pbl + (rc - b_lo) * Wp), D[i % 3], V[i % 3]);
                 }
-                if (i >= 2 && (FULL || ra + i - 2 < rb)) {
+                if (i >= 2 && (FULL || EVEN || ra + i - 2 < rb)) {
                     const int pix = (ra + i - 2) * W + col;
                     float4 bs[NC ? NC : 1];
                     if (BLEND && NC) ld_px4<NC, NHWC>(base_b, hw, pix, bs);
@@ -489,13 +501,47 @@ __device__ __forceinline__ void adj_chunk(int ra, int rb, int H, LoadP loadp, Co
     }
 }
 
+// EVEN chunk of a whole-image tile: exactly R output rows [ra, ra+R), ra % R == 0, H % R == 0.  Inputs ra-1 .. ra+R
+// (zero partials outside the image); only the chunks with ra == 0 / ra + R == H produce and fold a ring row.  Ring row
+// -1 combines (zero, zero, row 0), ring row H combines (row H-1, zero, zero): the ring-buffer slot that is not loaded
+// yet (or no longer needed) is zeroed and `combine` is called with the index whose slots line up.
+template <int R, typename LoadP, typename Combine, typename Store>
+__device__ __forceinline__ void adj_chunk_even(int ra, int H, LoadP loadp, Combine combine, Store store) {
+    const bool top = (ra == 0), bot = (ra + R == H);
+    float hold[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    loadp(0, ra - 1, !top);
+    loadp(1, ra, true);
+    if (top) {
+        loadp(2, -2, false);
+        combine(4, hold);                 // slots (2, 0, 1) = (zero, zero, row 0): ring row -1
+    }
+#pragma unroll
+    for (int i = 2; i < R + 2; ++i) {
+        loadp(i, ra - 1 + i, (i < R + 1) || !bot);
+        float o[4];
+        combine(i, o);
+        if (i == 2 && top) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = o[k] + hold[k];
+        }
+        if (i == R + 1 && bot) {
+            float ring[4];
+            loadp(R + 2, H + 1, false);
+            combine(R + 2, ring);         // slots (R, R+1, R+2) = (row H-1, zero, zero): ring row H
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = o[k] + ring[k];
+        }
+        store(ra + i - 2, o);
+    }
+}
+
 // GB rows [gb_lo, gb_hi) = fold(Sobel^T(A, Bv)), zero pad columns.  A / Bv planes start at row ab_lo.
-template <int R>
+template <int R, bool EVEN = false>
 __device__ __forceinline__ void fast_stage_sobel_adjoint(const Geo geo, const float* A, const float* Bv, int ab_lo,
                                                          float* GB, int gb_lo, int gb_hi, int tx, int ty) {
     const int W = geo.W, H = geo.H, Wp = geo.Wp;
-    EE_FOR_CHUNKS(gb_lo, gb_hi) {
-        const int lc = g * 4, col = geo.cs + lc, ra = gb_lo + ch * R, rb = min(ra + R, gb_hi);
+    EE_FOR_CHUNKS_E(gb_lo, gb_hi) {
+        const int lc = g * 4, col = geo.cs + lc, ra = gb_lo + ch * R, rb = EVEN ? ra + R : min(ra + R, gb_hi);
         const AdjBorder bd = {col == 0, col + 4 == W};
         const bool ring = bd.left || bd.right;
         float HA[3][4], HB[3][4], HAr[3], HBr[3];
@@ -528,22 +574,23 @@ __device__ __forceinline__ void fast_stage_sobel_adjoint(const Geo geo, const fl
         auto store = [&](int row, const float (&o)[4]) {
             st_plane(GB + (row - gb_lo) * Wp + kPadL + lc, o, bd.left, bd.right, 0.0f, 0.0f);
         };
-        if (EE_FWD_CHUNK_IS_FULL(ra, rb, H)) adj_chunk<R, true>(ra, rb, H, loadp, combine, store);
+        if constexpr (EVEN) adj_chunk_even<R>(ra, H, loadp, combine, store);
+        else if (EE_FWD_CHUNK_IS_FULL(ra, rb, H)) adj_chunk<R, true>(ra, rb, H, loadp, combine, store);
         else adj_chunk<R, false>(ra, rb, H, loadp, combine, store);
     }
 }
 
 // g_s rows [r0, r1) = fold(Gauss^T(GB)), written to every channel of g_x (gx_b = image base pointer)
-template <int NC, int R, bool NHWC = false>
+template <int NC, int R, bool NHWC = false, bool EVEN = false>
 __device__ __forceinline__ void fast_stage_gauss_adjoint_store(const FastArgs& a, const Geo geo, const float* GB, int gb_lo,
                                                                float* gx_b, int r0, int r1, int tx, int ty) {
     const int W = geo.W, H = geo.H, Wp = geo.Wp;
     const int C = NC ? NC : a.e.C;
     const size_t hw = (size_t)H * W;
     const float c0 = a.e.c0, c1 = a.e.c1, c2 = a.e.c2;
-    EE_FOR_CHUNKS(r0, r1) {
-        const int lc = g * 4, col = geo.cs + lc, ra = r0 + ch * R, rb = min(ra + R, r1);
-        if (col < geo.c0 || col >= geo.c1) continue;             // halo groups produce no output
+    EE_FOR_CHUNKS_E(r0, r1) {
+        const int lc = g * 4, col = geo.cs + lc, ra = r0 + ch * R, rb = EVEN ? ra + R : min(ra + R, r1);
+        if (!EVEN && (col < geo.c0 || col >= geo.c1)) continue;  // halo groups produce no output
         const AdjBorder bd = {col == 0, col + 4 == W};
         const bool ring = bd.left || bd.right;
         float P[3][4], Q[3][4], Pr[3], Qr[3];
@@ -577,7 +624,8 @@ __device__ __forceinline__ void fast_stage_gauss_adjoint_store(const FastArgs& a
                 for (int c = 0; c < C; ++c) __stcs(reinterpret_cast<float4*>(pg + c * hw), v);
             }
         };
-        if (EE_FWD_CHUNK_IS_FULL(ra, rb, H)) adj_chunk<R, true>(ra, rb, H, loadp, combine, store);
+        if constexpr (EVEN) adj_chunk_even<R>(ra, H, loadp, combine, store);
+        else if (EE_FWD_CHUNK_IS_FULL(ra, rb, H)) adj_chunk<R, true>(ra, rb, H, loadp, combine, store);
         else adj_chunk<R, false>(ra, rb, H, loadp, combine, store);
     }
 }
@@ -586,24 +634,28 @@ __device__ __forceinline__ void fast_stage_gauss_adjoint_store(const FastArgs& a
 // backward.  smem regions (stride Wp): R1 = S then A (TH+8 rows), R2 = Bl then GB (TH+6), R3 = Bv (TH+4);
 // a region never needs more rows than the image has (halo rows are clipped), so each is min(TH+k, H) rows
 // -------------------------------------------------------------------------------------------
-template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false>
+template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false, int HT = 0>
 __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const FastArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int DIVM = (NC == 1) ? 0 : (NC == 3 ? 1 : 2);
-    const int b = blockIdx.x / a.e.tiles_per_img;
-    const int tq = blockIdx.x - b * a.e.tiles_per_img;
-    const int ti = tq / a.tiles_x;                                   // row-strip index; column tile = tq % tiles_x
-    const Geo geo = make_geo<WT, WG>(a, tq - ti * a.tiles_x);
+    constexpr bool EVEN = (HT != 0);
+    static_assert(!EVEN || (WT != 0 && WT == WG && HT % R == 0), "HT needs a single constant-width column tile");
+    const int b = EVEN ? blockIdx.x : blockIdx.x / a.e.tiles_per_img;
+    const int tq = EVEN ? 0 : blockIdx.x - b * a.e.tiles_per_img;
+    const int ti = EVEN ? 0 : tq / a.tiles_x;                        // row-strip index; column tile = tq % tiles_x
+    Geo geo = make_geo<WT, WG>(a, tq - ti * a.tiles_x);
+    if (EVEN) { geo.H = HT; geo.RY = HT / R; }
     const int H = geo.H, W = geo.W, Wp = geo.Wp;
     const int C = NC ? NC : a.e.C;
-    const int r0 = ti * a.e.TH, r1 = min(r0 + a.e.TH, H);
+    const int r0 = EVEN ? 0 : ti * a.e.TH, r1 = EVEN ? HT : min(r0 + a.e.TH, H);
     const int tx = threadIdx.x % geo.GX, ty = threadIdx.x / geo.GX;
     const size_t hw = (size_t)H * W;
     const bool active = ty < geo.RY;
+    const bool one_tile = EVEN || a.tiles_x == 1;
 
     float* R1 = smem;
-    float* R2 = R1 + (size_t)min(a.e.TH + 8, H) * Wp;
-    float* R3 = R2 + (size_t)min(a.e.TH + 6, H) * Wp;
+    float* R2 = R1 + (size_t)(EVEN ? HT : min(a.e.TH + 8, H)) * Wp;
+    float* R3 = R2 + (size_t)(EVEN ? HT : min(a.e.TH + 6, H)) * Wp;
 
     const bool want_gx = (a.e.g_x != nullptr);
     const int s_lo = max(r0 - 4, 0), s_hi = min(r1 + 4, H);
@@ -615,14 +667,14 @@ __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const 
     float* S = R1; float* Bl = R2;
     auto prefetch_bwd_operands = [&]() {
         if (NHWC && !(ab_lo == 0 && ab_hi == H)) return;     // channels_last: only the whole-image range is contiguous the same way
-        if (C <= 32 && a.tiles_x == 1) {
+        if (C <= 32 && one_tile) {
             if (BLEND) {
                 if (threadIdx.x < 32) prefetch_rows(a.e.base, b, C, H, W, ab_lo, ab_hi, threadIdx.x);
                 else if (threadIdx.x < 64) prefetch_rows(a.e.g_in, b, C, H, W, ab_lo, ab_hi, threadIdx.x - 32);
             } else if (threadIdx.x == 0) {
                 prefetch_rows(a.e.g_in, b, 1, H, W, ab_lo, ab_hi, 0);
             }
-        } else if (BLEND && a.tiles_x > 1) {
+        } else if (BLEND && !one_tile) {
             // column tile: one bulk prefetch per (tensor, channel, row) segment [cs, ce) of the A/Bv rows
             const int nrows = ab_hi - ab_lo, seg = (geo.ce - geo.cs) * (int)sizeof(float);
             for (int i = threadIdx.x; i < 2 * C * nrows; i += blockDim.x) {
@@ -635,12 +687,12 @@ __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const 
 #if EE_L2_PREFETCH_BWD == 1
     prefetch_bwd_operands();
 #endif
-    if (active) fast_stage_sum<NC, R, NHWC>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
+    if (active) fast_stage_sum<NC, R, NHWC, EVEN>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
 #if EE_L2_PREFETCH_BWD == 2
     prefetch_bwd_operands();        // after the x loads are issued, so they do not compete with them
 #endif
     __syncthreads();
-    if (active) fast_stage_blur<R>(a, geo, S, s_lo, Bl, b_lo, b_hi, tx, ty);
+    if (active) fast_stage_blur<R, EVEN>(a, geo, S, s_lo, Bl, b_lo, b_hi, tx, ty);
     __syncthreads();
 
     // ---- A / Bv = dL/dSgx, dL/dSgy on rows [ab_lo, ab_hi), zero pad columns ---------------------
@@ -649,8 +701,8 @@ __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const 
         const float* base_b = a.e.base + (size_t)b * C * hw;
         const float* gin_b = a.e.g_in + (size_t)b * (BLEND ? C : 1) * hw;
         float* gbase_b = a.e.g_base ? a.e.g_base + (size_t)b * C * hw : nullptr;
-        EE_FOR_CHUNKS(ab_lo, ab_hi) {
-            const int lc = g * 4, col = geo.cs + lc, ra = ab_lo + ch * R, rb = min(ra + R, ab_hi);
+        EE_FOR_CHUNKS_E(ab_lo, ab_hi) {
+            const int lc = g * 4, col = geo.cs + lc, ra = ab_lo + ch * R, rb = EVEN ? ra + R : min(ra + R, ab_hi);
             const float* pbl = Bl + kPadL + lc;
             auto body = [&](auto tag) {
                 constexpr bool FULL = decltype(tag)::value;
@@ -658,11 +710,11 @@ __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const 
 #pragma unroll
                 for (int i = 0; i < R + 2; ++i) {
                     const int rin = ra - 1 + i;
-                    if (FULL || rin <= rb) {
+                    if (FULL || EVEN || rin <= rb) {
                         const int rc = FULL ? rin : min(max(rin, 0), H - 1);
                         sobel_partials(ld_win(pbl + (rc - b_lo) * Wp), D[i % 3], V[i % 3]);
                     }
-                    if (i >= 2 && (FULL || ra + i - 2 < rb)) {
+                    if (i >= 2 && (FULL || EVEN || ra + i - 2 < rb)) {
                         const int rout = ra + i - 2;
                         const int pix = rout * W + col;
                         float gx1[4], gy1[4], u[4], ge[4], sgx[4], sgy[4];
@@ -678,7 +730,7 @@ __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const 
                             float we[4];
 #pragma unroll
                             for (int k = 0; k < 4; ++k) we[k] = wgt * edge_from_u(a, u[k]);
-                            const bool interior = (rout >= r0 && rout < r1 && col >= geo.c0 && col < geo.c1);
+                            const bool interior = EVEN || (rout >= r0 && rout < r1 && col >= geo.c0 && col < geo.c1);
                             float4 bs[NC ? NC : 1], go[NC ? NC : 1];
                             if (NC) {
                                 ld_px4<NC, NHWC>(base_b, hw, pix, bs);
@@ -746,9 +798,9 @@ __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const 
 
     // ---- GB = fold(Sobel^T(A, Bv)) on rows [gb_lo, gb_hi) ; g_s rows [r0, r1) = fold(Gauss^T(GB)) -> g_x -------
     float* GB = R2;
-    if (active) fast_stage_sobel_adjoint<R>(geo, A, Bv, ab_lo, GB, gb_lo, gb_hi, tx, ty);
+    if (active) fast_stage_sobel_adjoint<R, EVEN>(geo, A, Bv, ab_lo, GB, gb_lo, gb_hi, tx, ty);
     __syncthreads();
-    if (active) fast_stage_gauss_adjoint_store<NC, R, NHWC>(a, geo, GB, gb_lo, a.e.g_x + (size_t)b * C * hw, r0, r1, tx, ty);
+    if (active) fast_stage_gauss_adjoint_store<NC, R, NHWC, EVEN>(a, geo, GB, gb_lo, a.e.g_x + (size_t)b * C * hw, r0, r1, tx, ty);
 }
 
 }  // namespace ee
