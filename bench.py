@@ -56,7 +56,8 @@ def parse_args():
     ap.add_argument("--variant", default="step125", choices=["step125", "canny", "bpda"])
     ap.add_argument("--cpu-images", type=int, default=2048, help="images in the bounded CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=4, help="chunks the e2e batch is pipelined in (3 streams)")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="chunks the e2e batch is pipelined in")
+    ap.add_argument("--e2e-streams", type=int, default=3, help="CUDA streams the e2e chunks are issued on round-robin")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--th-fwd", type=int, default=0)
     ap.add_argument("--th-bwd", type=int, default=0)
@@ -462,7 +463,7 @@ def run_e2e(args, torch, dist, dev, world, rank, F_ee, p, resident, barrier):
     buffers: every step copies the clean batch from pinned host memory and reads the adversarial batch back.
     The batch is cut into chunks issued round-robin on three CUDA streams (the library enqueues on the caller's
     current stream), so H2D of one chunk, the kernels of another and D2H of a third overlap."""
-    n_chunks, N_STREAMS = max(1, args.e2e_chunks), 3
+    n_chunks, N_STREAMS = max(1, args.e2e_chunks), max(1, args.e2e_streams)
     B, S = args.batch, args.side
     shape = (B, 3, S, S)
     base, g_out = resident
@@ -512,7 +513,7 @@ def run_e2e_attack_api(args, torch, dist, dev, world, rank, core, attacks, canny
     core.edge_enhance (base = x; the FFT low-pass is out of scope) and whose head is a per-channel mean -> 3-way
     cross-entropy (torch stand-in for the CNN: its kernels and the autograd bookkeeping are inside this number).
     Host buffers and chunking as in run_e2e."""
-    n_chunks, N_STREAMS = max(1, args.e2e_chunks), 3
+    n_chunks, N_STREAMS = max(1, args.e2e_chunks), max(1, args.e2e_streams)
     B, S = args.batch, args.side
     shape = (B, 3, S, S)
     host_in = torch.rand(shape).pin_memory()

@@ -42,6 +42,8 @@ SIGNATURES = {
     "ee_to_eq_bwd_f32": [_vp, _vp, _vp, _i64, _vp],
     "ee_safe_sign_fwd_f32": [_vp, _vp, _i64, _vp],
     "ee_safe_sign_bwd_f32": [_vp, _vp, _vp, _i64, _vp],
+    "ee_add_square_fwd_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
+    "ee_add_square_bwd_f32": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
     "ee_last_error": [],
     "ee_version": [],
     "ee_set_tuning": [_i, _i, _i],

@@ -292,8 +292,9 @@ class HighFreqSuppress(torch.nn.Module):
         return m
 
     def forward(self, x):
-        half = x.shape[-1] // 2 + 1
-        x_hat = torch.fft.fft2(x)[..., :half]
+        # rfft(x, 2, onesided=False) followed by a C2R inverse that reads only the one-sided half equals a
+        # real-to-complex transform of the half spectrum: rfft2 does half the work of fft2(x)[..., :half]
+        x_hat = torch.fft.rfft2(x)
         x_hat = x_hat * self._mask(x.device)
         return torch.fft.irfft2(x_hat, s=x.shape[-2:])
 
@@ -302,8 +303,11 @@ class HighFreqSuppress(torch.nn.Module):
 
 
 class Add_Square(nn.Module):
-    """utils/core.py:589-655 (random square perturbation of the *_square models); torch pass-through
-    that follows the input's device instead of the reference's hard .cuda()."""
+    """utils/core.py:589-655 (random stripe + square perturbation of the *_square models).  The random numbers
+    are drawn with the reference's own calls in the reference's order (torch CPU generator: `torch.rand(shape)`
+    then moved to the device), so a seeded run sees the same stripes and squares; the arithmetic -- stripe add,
+    per-query square add, eps-ball projection, [0,1] clamps, and the autograd through all of it -- is ONE fused
+    kernel per direction (libedge_b200.so: ee_add_square_{fwd,bwd}_f32) instead of ~5 + 7*n_queries eager ones."""
 
     def __init__(self, channels=3, size=224, epsilon=0.05, p_init=0.8, n_queries=5000, rescale_schedule=False):
         super(Add_Square, self).__init__()
@@ -313,17 +317,17 @@ class Add_Square(nn.Module):
         self.p_init = p_init
         self.n_queries = n_queries
         self.rescale_schedule = rescale_schedule
-        self._dev = None
 
     def random_choice(self, shape):
-        t = 2 * torch.rand(shape).to(self._dev) - 1
+        t = 2 * torch.rand(shape) - 1          # CPU generator, like the reference's torch.rand(shape).cuda()
         return torch.sign(t)
 
     def random_int(self, low=0, high=1, shape=[1]):
-        t = low + (high - low) * torch.rand(shape).to(self._dev)
+        t = low + (high - low) * torch.rand(shape)
         return t.long()
 
     def p_selection(self, it):
+        """schedule to decrease the parameter p (core.py:607-637)"""
         if self.rescale_schedule:
             it = int(it / self.n_queries * 10000)
         for bound, div in ((10, 1), (50, 2), (200, 4), (500, 8), (1000, 16), (2000, 32), (4000, 64),
@@ -332,17 +336,29 @@ class Add_Square(nn.Module):
                 return self.p_init / div
         return self.p_init / 512
 
-    def forward(self, x):
-        self._dev = x.device
-        x_best = torch.clamp(x + self.eps * self.random_choice([x.shape[0], self.c, 1, self.h]), 0., 1.)
+    def draw(self, batch):
+        """The reference's random draws, in its order: stripe signs [B,C,1,h] (core.py:641), then per query the
+        square origin (:646) and the per-channel signs (:649).  Returns (stripe[B,C,h], table[n_queries, 2+C]) on
+        the CPU; table rows are (vh, s, 2*eps*sign_0, ...)."""
+        stripe = self.random_choice([batch, self.c, 1, self.h]).reshape(batch, self.c, self.h)
         n_features = self.c * self.h * self.h
+        table = torch.empty((self.n_queries, 2 + self.c), dtype=torch.float32)
         for i_iter in range(self.n_queries):
             p = self.p_selection(i_iter)
             s = max(int(round(math.sqrt(p * n_features / self.c))), 1)
             vh = self.random_int(0, self.h - s)
-            new_deltas = torch.zeros([self.c, self.h, self.h], device=x.device)
-            new_deltas[:, vh:vh + s, vh:vh + s] = 2. * self.eps * self.random_choice([self.c, 1, 1])
-            x_best = x_best + new_deltas
-            x_best = torch.min(torch.max(x_best, x - self.eps), x + self.eps)
-            x_best = torch.clamp(x_best, 0., 1.)
-        return x_best
+            table[i_iter, 0] = float(vh.item())
+            table[i_iter, 1] = float(s)
+            table[i_iter, 2:] = (2. * self.eps * self.random_choice([self.c, 1, 1])).reshape(-1)
+        return stripe, table
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("edge_b200: Add_Square needs a CUDA tensor (no CPU fallback)")
+        if x.dim() != 4 or x.shape[1] != self.c or x.shape[2] != self.h or x.shape[3] != self.h:
+            raise RuntimeError("edge_b200: Add_Square(channels=%d, size=%d) got input of shape %s"
+                               % (self.c, self.h, tuple(x.shape)))
+        stripe, table = self.draw(x.shape[0])
+        stripe = stripe.to(x.device, non_blocking=True)
+        table = table.to(x.device, non_blocking=True)
+        return F_ee.AddSquareFn.apply(x, stripe, table, float(self.eps))

@@ -6,6 +6,7 @@
 #include "ee_edge_canny_fast.cuh"
 #include "ee_edge_fast.cuh"
 #include "ee_edge_step125.cuh"
+#include "ee_square.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -538,6 +539,34 @@ int ee_safe_sign_fwd_f32(const float* in, float* out, int64_t n, void* stream) {
 }
 int ee_safe_sign_bwd_f32(const float* g, const float* in, float* out, int64_t n, void* stream) {
     return launch_ew<2>(g, in, nullptr, nullptr, nullptr, out, n, ee::FSafeSignBwd{}, stream, "ee_safe_sign_bwd_f32");
+}
+
+static int add_square(bool bwd, const float* g, const float* x, const float* stripe, const float* table, float* out, int B,
+                      int C, int H, int W, int n_sq, float eps, void* stream) {
+    const char* name = bwd ? "ee_add_square_bwd_f32" : "ee_add_square_fwd_f32";
+    if (B < 0 || C <= 0 || H <= 0 || W <= 0 || n_sq < 0) return fail(EE_ERR_INVALID_ARG, "%s: bad shape", name);
+    if (B == 0) return EE_OK;
+    if (!x || !stripe || !out || (bwd && !g) || (n_sq > 0 && !table)) return fail(EE_ERR_INVALID_ARG, "%s: null pointer", name);
+    ee::SquareArgs a;
+    a.x = x; a.stripe = stripe; a.table = table; a.g = g; a.out = out;
+    a.C = C; a.H = H; a.W = W; a.n_sq = n_sq; a.n = (int64_t)B * C * H * W; a.eps = eps;
+    const bool vec = (W % 4 == 0) && aligned16(x) && aligned16(stripe) && aligned16(out) && aligned16(g);
+    const int64_t work = ((vec ? a.n / 4 : a.n) + 255) / 256;
+    const unsigned grid = (unsigned)(work < 1 ? 1 : (work > 148 * 32 ? 148 * 32 : work));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (bwd) { if (vec) ee::add_square_kernel<true, 4><<<grid, 256, 0, s>>>(a); else ee::add_square_kernel<true, 1><<<grid, 256, 0, s>>>(a); }
+    else     { if (vec) ee::add_square_kernel<false, 4><<<grid, 256, 0, s>>>(a); else ee::add_square_kernel<false, 1><<<grid, 256, 0, s>>>(a); }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, name);
+    return EE_OK;
+}
+int ee_add_square_fwd_f32(const float* x, const float* stripe, const float* table, float* out, int B, int C, int H, int W,
+                          int n_sq, float eps, void* stream) {
+    return add_square(false, nullptr, x, stripe, table, out, B, C, H, W, n_sq, eps, stream);
+}
+int ee_add_square_bwd_f32(const float* g, const float* x, const float* stripe, const float* table, float* g_x, int B, int C,
+                          int H, int W, int n_sq, float eps, void* stream) {
+    return add_square(true, g, x, stripe, table, g_x, B, C, H, W, n_sq, eps, stream);
 }
 
 const char* ee_last_error(void) { return g_err; }

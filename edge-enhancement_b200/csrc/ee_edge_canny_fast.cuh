@@ -77,21 +77,25 @@ __device__ __forceinline__ void nms_threshold4(const FastArgs& a, const Win& wu,
     float u[6], m[6], d[6];
     win_to_array(wu, u); win_to_array(wm, m); win_to_array(wd, d);
     const int words[4] = {__float_as_int(mt.x), __float_as_int(mt.y), __float_as_int(mt.z), __float_as_int(mt.w)};
+    const bool neg_lo = (0.0f > a.e.low), neg_hi = (0.0f > a.e.high);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int w = words[k] & 15;
         const int dir = w - 1;
         const float mc = m[k + 1];
         // -1 tap offsets (row,col): 0:(0,+1) 1:(-1,+1) 2:(-1,0) 3:(-1,-1) | opposite: (0,-1) (+1,-1) (+1,0) (+1,+1)
-        const float n1 = (dir == 0) ? m[k + 2] : (dir == 1) ? u[k + 2] : (dir == 2) ? u[k + 1] : u[k];
-        const float n2 = (dir == 0) ? m[k] : (dir == 1) ? d[k] : (dir == 2) ? d[k + 1] : d[k + 2];
-        const float d1 = mc - n1, d2 = mc - n2;
-        const int removed = !(fminf(d1, d2) > 0.0f);
+        // min(mc - n1, mc - n2) > 0  <=>  mc > max(n1, n2) (exact for finite values: a - b > 0 <=> a > b with
+        // gradual underflow): the larger neighbour of each of the four pairs, then one select by direction
+        const float mx0 = fmaxf(m[k + 2], m[k]), mx1 = fmaxf(u[k + 2], d[k]);
+        const float mx2 = fmaxf(u[k + 1], d[k + 1]), mx3 = fmaxf(u[k], d[k + 2]);
+        const float mx = (dir & 2) ? ((dir & 1) ? mx3 : mx2) : ((dir & 1) ? mx1 : mx0);
+        const int removed = !(mc > mx);
         const float th = removed ? 0.0f : mc;
         thin[k] = th;
-        const float lo = bpda ? to_compare(th, a.e.low) : sign_step(th, a.e.low);
-        const float hi = bpda ? to_compare(th, a.e.high) : sign_step(th, a.e.high);
-        const int ilo = (lo == 1.0f), ihi = (hi == 1.0f);
+        // sign_step: (th - thr > 0) <=> th > thr ; to_compare additionally turns "not above" into 1 for a negative threshold
+        const bool plo = th > a.e.low, phi = th > a.e.high;
+        const int ilo = bpda ? (plo || (neg_lo && th <= a.e.low)) : plo;
+        const int ihi = bpda ? (phi || (neg_hi && th <= a.e.high)) : phi;
         meta[k] = w | ((ilo + ihi) << 4) | (ihi << 6) | (removed << 7);
     }
 }

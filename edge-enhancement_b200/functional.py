@@ -273,6 +273,51 @@ def pgd_l2_step(x, grad, x0, step, eps):
     return out
 
 
+def _square_operands(x, stripe, table):
+    x = _chk(x, "x")
+    if x.dim() != 4:
+        raise ValueError("edge_b200: add_square needs a [B,C,H,W] tensor")
+    B, C, H, W = x.shape
+    stripe = _chk(stripe, "stripe", (B, C, W))
+    n_sq = 0
+    if table is not None and table.numel():
+        table = _chk(table, "table")
+        if table.dim() != 2 or table.shape[1] != 2 + C:
+            raise ValueError("edge_b200: square table must be [n_queries, 2 + C]")
+        n_sq = table.shape[0]
+    else:
+        table = None
+    return x, stripe, table, n_sq
+
+
+def add_square(x, stripe, table, eps, out=None):
+    """Add_Square.forward (utils/core.py:640-655) from pre-drawn random numbers: stripe[B,C,W] = signs of the
+    column stripes, table[n_queries, 2+C] = (vh, s, 2*eps*sign_c ...) per query.  One pass."""
+    x, stripe, table, n_sq = _square_operands(x, stripe, table)
+    out = _out_like(x, out)
+    B, C, H, W = x.shape
+    if x.numel():
+        with _on_device(x):
+            rc = _lib.load().ee_add_square_fwd_f32(_ptr(x), _ptr(stripe), _ptr(table), _ptr(out), B, C, H, W, n_sq,
+                                                   float(eps), _stream(x))
+        _lib.check(rc, "ee_add_square_fwd_f32")
+    return out
+
+
+def add_square_backward(g, x, stripe, table, eps, out=None):
+    """g_x = g * d(add_square)/d(x): autograd through the clamps and the two-sided projection, recomputed from x."""
+    x, stripe, table, n_sq = _square_operands(x, stripe, table)
+    g = _chk(g, "g", x.shape)
+    out = _out_like(x, out)
+    B, C, H, W = x.shape
+    if x.numel():
+        with _on_device(x):
+            rc = _lib.load().ee_add_square_bwd_f32(_ptr(g), _ptr(x), _ptr(stripe), _ptr(table), _ptr(out), B, C, H, W,
+                                                   n_sq, float(eps), _stream(x))
+        _lib.check(rc, "ee_add_square_bwd_f32")
+    return out
+
+
 def _ew(name, args, n, ref, thr=None):
     out = torch.empty_like(ref)
     if n:
@@ -321,6 +366,21 @@ class EdgeEnhanceFn(torch.autograd.Function):
         need_x, need_base = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         g_x, g_base = edge_blend_backward(g_out, img, base, ctx.params, ctx.w, need_x, need_base)
         return g_x, g_base, None, None
+
+
+class AddSquareFn(torch.autograd.Function):
+    """x_square = Add_Square(x) with the random draws passed in; backward recomputes the multiplier from x."""
+
+    @staticmethod
+    def forward(ctx, x, stripe, table, eps):
+        ctx.eps = eps
+        ctx.save_for_backward(x, stripe, table)
+        return add_square(x, stripe, table, eps)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, stripe, table = ctx.saved_tensors
+        return add_square_backward(g, x, stripe, table, ctx.eps), None, None, None
 
 
 class ToCompareFn(torch.autograd.Function):

@@ -136,6 +136,20 @@ int ee_to_eq_bwd_f32(const float* g, const float* in, float* out, int64_t n, voi
 int ee_safe_sign_fwd_f32(const float* in, float* out, int64_t n, void* stream);                             /* core.py:115-118,:130-135 */
 int ee_safe_sign_bwd_f32(const float* g, const float* in, float* out, int64_t n, void* stream);             /* core.py:138-145 */
 
+/* ---- Add_Square: the random stripe + square perturbation of the *_square models ---- */
+
+/* out[B,C,H,W] = Add_Square.forward(x), replaces utils/core.py:640-655.  The random draws stay with the caller
+ * (torch CPU generator, same calls and order as the reference): stripe[B,C,W] = sign(2*rand-1) (core.py:641),
+ * table[n_sq][2+C] floats = {vh, s, 2*eps*sign_c ...} per query (core.py:646-650; the square is rows AND columns
+ * [vh, vh+s)).  t = clamp(x + eps*stripe, 0, 1); per query t = clamp(min(max(t + d, x-eps), x+eps), 0, 1). */
+int ee_add_square_fwd_f32(const float* x, const float* stripe, const float* table, float* out,
+                          int B, int C, int H, int W, int n_sq, float eps, void* stream);
+
+/* g_x = g * d(out)/d(x) of the above (autograd through clamp / torch.max / torch.min incl. the even split on
+ * ties), recomputed from x: one pass, no saved tensors. */
+int ee_add_square_bwd_f32(const float* g, const float* x, const float* stripe, const float* table, float* g_x,
+                          int B, int C, int H, int W, int n_sq, float eps, void* stream);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 const char* ee_last_error(void); /* thread-local, never NULL */
 int ee_version(void);            /* EE_VERSION */

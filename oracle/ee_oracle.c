@@ -638,6 +638,46 @@ void ee_oracle_safe_sign_fwd(const float *in, float *out, int64_t n)
 void ee_oracle_safe_sign_bwd(const float *g, const float *in, float *out, int64_t n)
 { for (int64_t i = 0; i < n; ++i) out[i] = (fabsf(in[i]) > 1.001f) ? 0.0f : g[i]; }
 
+/* ------------------------------------------------------------------------------------
+ * Add_Square, utils/core.py:640-655.  The random draws are inputs:
+ * stripe[B,C,W] = sign(2*rand-1) of :641, table[n_sq][2+C] = {vh, s, 2*eps*sign_c...} of :646-650.
+ *   x_best = clamp(x + eps*stripe, 0, 1)                                              :641
+ *   per query: x_best += new_deltas (square rows AND columns [vh, vh+s))               :648-652
+ *              x_best = min(max(x_best, x - eps), x + eps); clamp(x_best, 0, 1)        :653-655
+ * bwd (g == NULL: forward): multiplier of autograd through clamp (inclusive mask), torch.max /
+ * torch.min (ties split 1/2 : 1/2 between the two operands, both of which depend on x).
+ * ---------------------------------------------------------------------------------- */
+void ee_oracle_add_square(const float *g, const float *x, const float *stripe, const float *table, float *out,
+                          int B, int C, int H, int W, int n_sq, float eps)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t plane = 0; plane < (int64_t)B * C; ++plane) {
+        const int c = (int)(plane % C);
+        for (int h = 0; h < H; ++h)
+            for (int w = 0; w < W; ++w) {
+                const int64_t i = (plane * H + h) * W + w;
+                const float xv = x[i];
+                const float a0 = xv + eps * stripe[plane * W + w];
+                float t = minn(maxn(a0, 0.0f), 1.0f);
+                float dm = (a0 >= 0.0f && a0 <= 1.0f) ? 1.0f : 0.0f;
+                const float lo = xv - eps, hi = xv + eps;
+                for (int q = 0; q < n_sq; ++q) {
+                    const float *row = table + (size_t)q * (2 + C);
+                    const int pos = (int)row[0], side = (int)row[1];
+                    const int inside = (h >= pos) && (h < pos + side) && (w >= pos) && (w < pos + side);
+                    const float a2 = t + (inside ? row[2 + c] : 0.0f);
+                    dm = (a2 > lo) ? dm : ((a2 < lo) ? 1.0f : fmaf(0.5f, dm, 0.5f));
+                    const float a3 = maxn(a2, lo);
+                    dm = (a3 < hi) ? dm : ((a3 > hi) ? 1.0f : fmaf(0.5f, dm, 0.5f));
+                    const float a4 = minn(a3, hi);
+                    dm = (a4 >= 0.0f && a4 <= 1.0f) ? dm : 0.0f;
+                    t = minn(maxn(a4, 0.0f), 1.0f);
+                }
+                out[i] = g ? g[i] * dm : t;
+            }
+    }
+}
+
 int ee_oracle_version(void) { return 1; }
 
 /* number of host threads the parallel loops above will use (reported as `cores` by bench.py) */

@@ -137,6 +137,46 @@ def run_attack_cases(rc, ra):
         print("pgd10_%s: mean |x_adv - x| = %.4f" % (variant, (xadv - torch.from_numpy(x)).abs().mean()))
 
 
+def run_add_square_cases(rc):
+    """Add_Square (utils/core.py:589-655) hard-codes .cuda(); on this CPU-only container Tensor.cuda is patched to
+    the identity for the duration of the call, nothing else of the reference is touched.  The fixture stores the
+    generator seed, so the drop-in (which draws with the same calls in the same order) must reproduce `out` from
+    the seed alone, plus the draws themselves (stripe, table) for the kernel-level tests."""
+    import math
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        for name, (B, C, S), eps, nq, seed in (("tiny_q1", (4, 3, 64), 16 / 255, 1, 501),
+                                               ("mnist_q1", (8, 1, 28), 0.3, 1, 502),
+                                               ("small_q5", (3, 3, 16), 8 / 255, 5, 503)):
+            m = rc.Add_Square(channels=C, size=S, epsilon=eps, n_queries=nq)
+            r = T.rng(seed)
+            x = r.random((B, C, S, S), dtype=np.float32)
+            x.reshape(-1)[::7] = 0.0                     # exercise both clamp sides
+            x.reshape(-1)[3::11] = 1.0
+            g = r.standard_normal(x.shape, dtype=np.float32)
+            xt = torch.from_numpy(x).requires_grad_()
+            torch.manual_seed(seed)
+            out = m(xt)
+            out.backward(torch.from_numpy(g))
+            # replay the draws (same generator state) to store them
+            torch.manual_seed(seed)
+            stripe = torch.sign(2 * torch.rand([B, C, 1, S]) - 1).reshape(B, C, S).numpy()
+            table = np.zeros((nq, 2 + C), np.float32)
+            for it in range(nq):
+                p = m.p_selection(it)
+                s = max(int(round(math.sqrt(p * (C * S * S) / C))), 1)
+                vh = int((0 + (S - s) * torch.rand([1])).long())
+                sg = torch.sign(2 * torch.rand([C, 1, 1]) - 1).reshape(-1).numpy()
+                table[it, 0], table[it, 1], table[it, 2:] = vh, s, np.float32(2. * eps) * sg
+            np.savez_compressed(os.path.join(OUT, "add_square_%s.npz" % name), x=x, g=g, out=out.detach().numpy(),
+                                g_x=xt.grad.numpy(), stripe=stripe.astype(np.float32), table=table,
+                                meta=np.array([str(C), str(S), repr(eps), str(nq), str(seed)]))
+            print("add_square_%s: mean |out - x| = %.4f" % (name, float((out.detach() - xt.detach()).abs().mean())))
+    finally:
+        torch.Tensor.cuda = orig_cuda
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -145,6 +185,7 @@ def main():
     for case in EDGE_CASES:
         run_edge_case(rc, case)
     run_attack_cases(rc, ra)
+    run_add_square_cases(rc)
     print("fixtures written to", OUT)
 
 

@@ -87,6 +87,8 @@ def lib():
     L.ee_oracle_cw_linf_step.restype = None
     L.ee_oracle_pgd_l2_step.argtypes = [fp, fp, fp, fp, i, i64, f, f]
     L.ee_oracle_pgd_l2_step.restype = None
+    L.ee_oracle_add_square.argtypes = [fp, fp, fp, fp, fp, i, i, i, i, i, f]
+    L.ee_oracle_add_square.restype = None
     for name in ("to_compare",):
         getattr(L, "ee_oracle_%s_fwd" % name).argtypes = [fp, fp, i64, f]
         getattr(L, "ee_oracle_%s_bwd" % name).argtypes = [fp, fp, fp, i64, f]
@@ -188,6 +190,18 @@ def pgd_l2_step(x, g, x0, step, eps):
     out = np.empty_like(x)
     B = x.shape[0]
     lib().ee_oracle_pgd_l2_step(_p(x), _p(g), _p(x0), _p(out), B, x.size // B, step, eps)
+    return out
+
+
+def add_square(x, stripe, table, eps, g=None):
+    """Add_Square forward (g is None) or g * d(out)/d(x); stripe [B,C,W], table [n_sq, 2+C]."""
+    x, stripe = _f32(x), _f32(stripe)
+    B, C, H, W = x.shape
+    table = _f32(table).reshape(-1, 2 + C) if table is not None and np.size(table) else np.zeros((0, 2 + C), np.float32)
+    g = None if g is None else _f32(g)
+    out = np.empty_like(x)
+    lib().ee_oracle_add_square(_p(g), _p(x), _p(stripe), _p(table), _p(out), B, C, H, W, table.shape[0],
+                               float(np.float32(eps)))
     return out
 
 

@@ -168,6 +168,9 @@ def test_high_freq_suppress_restatement():
     y = h(x)
     assert y.shape == x.shape and y.dtype == torch.float32
     assert torch.allclose(y.mean((2, 3)), x.mean((2, 3)), atol=1e-5)       # DC passes
+    half = x.shape[-1] // 2 + 1                                              # the literal restatement: full FFT, one-sided C2R
+    lit = torch.fft.irfft2(torch.fft.fft2(x)[..., :half] * h.temp[..., 0][..., :half], s=x.shape[-2:])
+    assert torch.allclose(y, lit, atol=1e-6)
     full = core.HighFreqSuppress(8, 8, 4)                                   # radius covers everything
     z = torch.rand(1, 1, 8, 8)
     assert torch.allclose(full(z), z, atol=1e-5)

@@ -117,3 +117,24 @@ def test_adjoint_identity():
     close = np.isclose(num, gx, rtol=0.05, atol=0.02)
     assert close.mean() > 0.7, close.mean()
     assert np.isfinite(f0)
+
+
+SQUARE_FILES = sorted(glob.glob(os.path.join(GOLD, "add_square_*.npz")))
+
+
+@pytest.mark.parametrize("path", SQUARE_FILES, ids=lambda p: os.path.basename(p)[11:-4])
+def test_add_square_oracle_matches_reference_fixture(path):
+    """Add_Square (utils/core.py:640-655): forward bit-exact; the gradient is g times a 0/1 multiplier -- exact for
+    n_queries = 1 (every reference config), within 1 ulp of autograd's accumulation order otherwise."""
+    z = np.load(path)
+    eps, nq = float(str(z["meta"][2])), int(str(z["meta"][3]))
+    assert len(SQUARE_FILES) >= 3
+    out = O.add_square(z["x"], z["stripe"], z["table"], eps)
+    assert np.array_equal(out, z["out"])
+    g_x = O.add_square(z["x"], z["stripe"], z["table"], eps, g=z["g"])
+    if nq == 1:
+        assert np.array_equal(g_x, z["g_x"])
+    else:
+        np.testing.assert_allclose(g_x, z["g_x"], rtol=2e-7, atol=0)
+    # properties: inside the eps ball and [0, 1]
+    assert (np.abs(out - z["x"]) <= np.float32(eps) + 1e-7).all() and out.min() >= 0.0 and out.max() <= 1.0
