@@ -55,9 +55,10 @@ def parse_args():
     ap.add_argument("--side", type=int, default=64)
     ap.add_argument("--variant", default="step125", choices=["step125", "canny", "bpda"])
     ap.add_argument("--cpu-images", type=int, default=2048, help="images in the bounded CPU sample")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work in the cpu_baseline leg (bounded sample)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="chunks the e2e batch is pipelined in")
-    ap.add_argument("--e2e-streams", type=int, default=3, help="CUDA streams the e2e chunks are issued on round-robin")
+    ap.add_argument("--e2e-streams", type=int, default=4, help="CUDA streams the e2e chunks are issued on round-robin")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--th-fwd", type=int, default=0)
     ap.add_argument("--th-bwd", type=int, default=0)
@@ -211,8 +212,9 @@ def sample_clocks_until(index, done_event, period=0.002):
 # ---------------------------------------------------------------------------------------------
 # CPU path (oracle port of the reference): the same PGD-10 hot path on a bounded sample
 # ---------------------------------------------------------------------------------------------
-def cpu_hot_path(images, side, variant, repeats=1):
-    """Returns (images/s, cores, seconds) of the oracle port running one PGD-10 hot-path step."""
+def cpu_hot_path(images, side, variant, repeats=1, min_seconds=0.0):
+    """Returns (images/s, cores, seconds per step) of the oracle port running the PGD-10 hot-path step on `images`
+    images: `repeats` steps, or as many as fit in `min_seconds` of CPU work (whichever is more); mean over the steps."""
     from oracle import oracle as O
     r = np.random.default_rng(1234)
     shape = (images, 3, side, side)
@@ -221,18 +223,20 @@ def cpu_hot_path(images, side, variant, repeats=1):
     g_out = r.standard_normal(shape, dtype=np.float32)
     p = O.make_params(variant, alpha=0.0, low=None if variant == "step125" else LOW, high=HIGH, hysteresis=True)
     cores = O.threads()
-    best = None
-    for _ in range(repeats):
-        x = np.clip(x0 + (r.random(shape, dtype=np.float32) * 2 - 1) * np.float32(EPS), 0, 1).astype(np.float32)
+    x_start = np.clip(x0 + (r.random(shape, dtype=np.float32) * 2 - 1) * np.float32(EPS), 0, 1).astype(np.float32)
+    total, n = 0.0, 0
+    while n < repeats or total < min_seconds:
+        x = x_start
         t0 = time.perf_counter()
         for _it in range(N_PGD):
             O.edge_blend_fwd(x, base, p, W_BLEND)
             g_x, _g_base = O.edge_blend_bwd(g_out, x, base, p, W_BLEND)
             x = O.pgd_linf_step(x, g_x, x0, ALPHA, EPS)
         O.edge_blend_fwd(x, base, p, W_BLEND)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return images / best, cores, best
+        total += time.perf_counter() - t0
+        n += 1
+    cpu_hot_path.last_steps = n
+    return images * n / total, cores, total / n
 
 
 def run_reference(args):
@@ -408,9 +412,11 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, secs = cpu_hot_path(args.cpu_images, S, args.variant, repeats=2)
+        v, cores, secs = cpu_hot_path(args.cpu_images, S, args.variant, repeats=2, min_seconds=args.cpu_seconds)
+        n_cpu = cpu_hot_path.last_steps
         cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": "%d images of 3x%dx%d, one full PGD-10 hot-path step (best of 2, %.1f s each)" % (args.cpu_images, S, S, secs)}
+               "sample": "%d images of 3x%dx%d per step, %d full PGD-10 hot-path steps (%.1f s of CPU work, mean)"
+                         % (args.cpu_images, S, S, n_cpu, secs * n_cpu)}
 
     if args.sweep and rank == 0:
         run_sweep(torch, F_ee, canny, dev, peak)

@@ -55,7 +55,7 @@ int check_params(const EEParams* p, float& c0, float& c1, float& c2) {
     return EE_OK;
 }
 
-struct Launch { int vec, threads, GX, RY, TH, tiles; size_t smem; int TW, tiles_x, planeW, halo; };
+struct Launch { int vec, threads, GX, RY, TH, tiles; size_t smem; int TW, tiles_x, planeW, halo; int even_planes = 0; };
 
 // ---- exact threshold cut-offs in u = mag^2 space (sqrt_rn is monotonic) ----------------------
 float f_of(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
@@ -105,12 +105,12 @@ int plan_fast(int H, int W, int R, int rows_per_th, int rows_fixed, int max_halo
     const size_t row_bytes = (size_t)(L.planeW + ee::kPadW) * sizeof(float);
     // the kernels' regions are min(TH + k, H) rows each (halo rows outside the image do not exist); the k's
     // are encoded as rows_per_th regions whose halos add up to rows_fixed: step125 fwd {4,2}, bwd {8,6,4},
-    // Canny fwd {8,6,4}, Canny bwd {12,10,8,4}
+    // Canny fwd {8,6,4}, Canny bwd {12,10,8,4,4}
     auto smem_of = [&](int th) {
-        int halos[4] = {0, 0, 0, 0};
+        int halos[5] = {0, 0, 0, 0, 0};
         if (rows_per_th == 2) { halos[0] = 4; halos[1] = 2; }
         else if (rows_per_th == 3) { halos[0] = 8; halos[1] = 6; halos[2] = 4; }
-        else { halos[0] = 12; halos[1] = 10; halos[2] = 8; halos[3] = 4; }
+        else { halos[0] = 12; halos[1] = 10; halos[2] = 8; halos[3] = 4; halos[4] = 4; }
         size_t rows = 0;
         for (int i = 0; i < rows_per_th; ++i) rows += (size_t)(th + halos[i] < H ? th + halos[i] : H);
         return rows * row_bytes;
@@ -168,6 +168,8 @@ template <typename K>
 int launch_fast_even(K kernel, Launch L, int B, const ee::FastArgs& a, cudaStream_t s, const char* name) {
     L.RY = a.e.H / 4;
     L.threads = ((L.GX * L.RY + 31) / 32) * 32;
+    const int planes = L.even_planes;
+    if (planes) L.smem = (size_t)planes * a.e.H * a.Wp * sizeof(float);     // whole-image planes the kernel really uses
     return launch_fast(kernel, L, B, a, s, name);
 }
 bool whole_image(const Launch& L, const ee::FastArgs& f, int side) {
@@ -394,8 +396,9 @@ int edge_backward(const float* g_in, const float* x, const float* base, float* g
             return fail(EE_ERR_UNSUPPORTED, "NHWC needs the fused blend entry point, C == 3, W %% 4 == 0, 16-byte aligned tensors");
         const bool st = (p->variant == EE_VARIANT_STEP125);
         rc = st ? plan_fast(H, W, 4, 3, 18, 8, 62 * 1024, g_th_bwd.load(), L)
-                : plan_fast(H, W, 4, ee::kCannyFastBwdRowsPerTH, ee::kCannyFastBwdRowsFixed, 12, 84 * 1024, g_th_bwd.load(), L, 8);
+                : plan_fast(H, W, 4, ee::kCannyFastBwdRowsPerTH, ee::kCannyFastBwdRowsFixed, 12, 104 * 1024, g_th_bwd.load(), L, 8);
         if (rc) return rc;
+        if (!st) L.even_planes = 4;      // whole-image Canny backward: gy1 reuses the blurred plane's region
         ee::FastArgs f;
         fill_fast(f, a, L);
         if (st) EE_DISPATCH_FAST_NHWC(ee::edge_bwd_step125_fast, L, B, f, s, "edge_bwd_step125_fast_nhwc");
@@ -417,8 +420,9 @@ int edge_backward(const float* g_in, const float* x, const float* base, float* g
         else EE_DISPATCH(ee::edge_bwd_step125_kernel, false, L, B, a, s, "edge_bwd_step125");
     }
     if (fast_eligible(a, vec_ok)) {
-        rc = plan_fast(H, W, 4, ee::kCannyFastBwdRowsPerTH, ee::kCannyFastBwdRowsFixed, 12, 84 * 1024, g_th_bwd.load(), L, 8);
+        rc = plan_fast(H, W, 4, ee::kCannyFastBwdRowsPerTH, ee::kCannyFastBwdRowsFixed, 12, 104 * 1024, g_th_bwd.load(), L, 8);
         if (rc) return rc;
+        L.even_planes = 4;               // whole-image Canny backward: gy1 reuses the blurred plane's region
         ee::FastArgs f;
         fill_fast(f, a, L);
         if (blend && hot_canny(f, L)) {

@@ -12,7 +12,7 @@
 //   META       : one word per pixel, zero padded: bits 0-3 direction pair + 1, 4-5 low+high, 6 high, 7 removed
 #pragma once
 #ifndef EE_L2_PREFETCH_BWD_CANNY
-#define EE_L2_PREFETCH_BWD_CANNY 0
+#define EE_L2_PREFETCH_BWD_CANNY 2
 #endif
 #include "ee_edge_canny.cuh"
 #include "ee_edge_fast.cuh"
@@ -21,8 +21,8 @@ namespace ee {
 
 // forward : R1 = S -> M (TH+8 rows), R2 = Bl (TH+6), R3 = META (TH+4)
 constexpr int kCannyFastFwdRowsPerTH = 3, kCannyFastFwdRowsFixed = 18;
-// backward: R1 = S -> M -> A (TH+12), R2 = Bl -> GB (TH+10), R3 = META (TH+8), R4 = Bv (TH+4)
-constexpr int kCannyFastBwdRowsPerTH = 4, kCannyFastBwdRowsFixed = 34;
+// backward: R1 = S -> M -> A (TH+12), R2 = Bl -> GB (TH+10), R3 = META (TH+8), R4 = gx1 -> Bv (TH+4), R5 = gy1 (TH+4)
+constexpr int kCannyFastBwdRowsPerTH = 5, kCannyFastBwdRowsFixed = 38;
 
 __device__ __forceinline__ void win_to_array(const Win& w, float (&e)[6]) {
     e[0] = w.l; e[1] = w.m0; e[2] = w.m1; e[3] = w.m2; e[4] = w.m3; e[5] = w.r;
@@ -30,9 +30,15 @@ __device__ __forceinline__ void win_to_array(const Win& w, float (&e)[6]) {
 __device__ __forceinline__ Win zero_win() { Win w; w.l = w.m0 = w.m1 = w.m2 = w.m3 = w.r = 0.0f; return w; }
 
 // ---- stage MB: M (gated magnitude) and META (direction) rows [lo,hi) from the blurred plane ----
-template <int DIVM, int R, bool EVEN = false>
+// STORE_G (backward): also keep gx1 / gy1 of rows [g_lo, g_hi) in two planes (origin g_lo), so that the A/Bv stage
+// does not recompute the Sobel pair, the division by C and the square root.
+// DEFER_GY (EVEN only: one chunk per thread): gy1 is returned in registers instead; the caller stores it into the
+// blurred plane's region after a barrier, so that the backward needs four planes instead of five.
+template <int DIVM, int R, bool EVEN = false, bool STORE_G = false, bool DEFER_GY = false>
 __device__ __forceinline__ void cfast_stage_mag_dir(const FastArgs& a, const Geo geo, const float* Bl, int b_lo, float* M,
-                                                    float* META, int lo, int hi, int tx, int ty, const int variant) {
+                                                    float* META, int lo, int hi, int tx, int ty, const int variant,
+                                                    float* GXp = nullptr, float* GYp = nullptr, int g_lo = 0, int g_hi = 0,
+                                                    float4* gy_keep = nullptr) {
     const int W = geo.W, H = geo.H, Wp = geo.Wp;
     const float fC = a.e.fC;
     const bool gate = (variant == 1);                // only CannyFilter applies alpha (core.py:263-264)
@@ -64,6 +70,15 @@ __device__ __forceinline__ void cfast_stage_mag_dir(const FastArgs& a, const Geo
                 const int q = (ra + i - 2 - lo) * Wp + kPadL + lc;
                 st_plane(M + q, mm, col == 0, col + 4 == W, 0.0f, 0.0f);
                 st_plane(META + q, mt, col == 0, col + 4 == W, 0.0f, 0.0f);
+                if (STORE_G) {
+                    const int rg = ra + i - 2;
+                    if (EVEN || (rg >= g_lo && rg < g_hi)) {
+                        const int qg = (rg - g_lo) * Wp + kPadL + lc;
+                        *reinterpret_cast<float4*>(GXp + qg) = make_float4(gx1[0], gx1[1], gx1[2], gx1[3]);
+                        if (DEFER_GY) gy_keep[i - 2] = make_float4(gy1[0], gy1[1], gy1[2], gy1[3]);
+                        else *reinterpret_cast<float4*>(GYp + qg) = make_float4(gy1[0], gy1[1], gy1[2], gy1[3]);
+                    }
+                }
             }
         }
     }
@@ -267,7 +282,10 @@ template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false, int HT =
 #ifndef EE_MINB_CANNY_BWD
 #define EE_MINB_CANNY_BWD 2
 #endif
-__global__ void __launch_bounds__(256, EE_MINB_CANNY_BWD) edge_bwd_canny_fast(const FastArgs a) {
+#ifndef EE_MINB_CANNY_BWD_EVEN
+#define EE_MINB_CANNY_BWD_EVEN 3
+#endif
+__global__ void __launch_bounds__(256, HT ? EE_MINB_CANNY_BWD_EVEN : EE_MINB_CANNY_BWD) edge_bwd_canny_fast(const FastArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int DIVM = (NC == 1) ? 0 : (NC == 3 ? 1 : 2);
     constexpr bool EVEN = (HT != 0);
@@ -296,6 +314,7 @@ __global__ void __launch_bounds__(256, EE_MINB_CANNY_BWD) edge_bwd_canny_fast(co
     float* R2 = R1 + (size_t)(EVEN ? HT : min(a.e.TH + 12, H)) * Wp;
     float* R3 = R2 + (size_t)(EVEN ? HT : min(a.e.TH + 10, H)) * Wp;
     float* R4 = R3 + (size_t)(EVEN ? HT : min(a.e.TH + 8, H)) * Wp;
+    float* R5 = R4 + (size_t)(EVEN ? HT : min(a.e.TH + 4, H)) * Wp;
 
     const int ab_lo = max(r0 - ha, 0), ab_hi = min(r1 + ha, H);
     const int c_lo = max(r0 - ha - hc, 0), c_hi = min(r1 + ha + hc, H);
@@ -306,49 +325,69 @@ __global__ void __launch_bounds__(256, EE_MINB_CANNY_BWD) edge_bwd_canny_fast(co
 
     float* S = R1; float* Bl = R2;
     if (active) fast_stage_sum<NC, R, NHWC, EVEN>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
-#if EE_L2_PREFETCH_BWD_CANNY       // measured -8 % on the Canny backward (2 CTAs/SM, operands needed 4 stages later): off
-    if (C <= 32 && (EVEN || a.tiles_x == 1)) {            // operands of the A/Bv stage, three stages from now
-        if (BLEND) {
-            if (threadIdx.x < 32) prefetch_rows(a.e.base, b, C, H, W, ab_lo, ab_hi, threadIdx.x);
-            else if (threadIdx.x < 64) prefetch_rows(a.e.g_in, b, C, H, W, ab_lo, ab_hi, threadIdx.x - 32);
-        } else if (threadIdx.x == 0) {
-            prefetch_rows(a.e.g_in, b, 1, H, W, ab_lo, ab_hi, 0);
+    // L2 bulk prefetch of the A/Bv stage's operands (base, g_out).  Placement (EE_L2_PREFETCH_BWD_CANNY): 0 off,
+    // 1 right after the x loads (four stages ahead: measured -8 % at 2 CTAs/SM), 2 after the blur, 3 after mag/dir
+    auto prefetch_ab_operands = [&]() {
+        if (C <= 32 && (EVEN || a.tiles_x == 1) && (!NHWC || (ab_lo == 0 && ab_hi == H))) {
+            if (BLEND) {
+                if (threadIdx.x < 32) prefetch_rows(a.e.base, b, C, H, W, ab_lo, ab_hi, threadIdx.x);
+                else if (threadIdx.x < 64) prefetch_rows(a.e.g_in, b, C, H, W, ab_lo, ab_hi, threadIdx.x - 32);
+            } else if (threadIdx.x == 0) {
+                prefetch_rows(a.e.g_in, b, 1, H, W, ab_lo, ab_hi, 0);
+            }
         }
-    }
+    };
+#if EE_L2_PREFETCH_BWD_CANNY == 1
+    prefetch_ab_operands();
 #endif
     __syncthreads();
     if (active) fast_stage_blur<R, EVEN>(a, geo, S, s_lo, Bl, b_lo, b_hi, tx, ty);
+#if EE_L2_PREFETCH_BWD_CANNY == 2
+    prefetch_ab_operands();
+#endif
     __syncthreads();
     float* M = R1; float* META = R3;
-    if (active) cfast_stage_mag_dir<DIVM, R, EVEN>(a, geo, Bl, b_lo, M, META, m_lo, m_hi, tx, ty, variant);
+    // gy1 plane: whole-image tiles keep it in registers over a barrier and then reuse the (dead) blurred plane's
+    // region, so they need 4 planes (3 CTAs/SM at 64x64); strips use a fifth region
+    float* GXp = R4; float* GYp = EVEN ? R2 : R5;
+    if (EVEN) {
+        float4 gy_keep[R];
+        if (active) cfast_stage_mag_dir<DIVM, R, EVEN, true, true>(a, geo, Bl, b_lo, M, META, m_lo, m_hi, tx, ty, variant, GXp, GYp, ab_lo, ab_hi, gy_keep);
+        __syncthreads();                        // every thread has read its Bl windows
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < R; ++i) *reinterpret_cast<float4*>(GYp + (ty * R + i) * Wp + kPadL + tx * 4) = gy_keep[i];
+        }
+    } else if (active) {
+        cfast_stage_mag_dir<DIVM, R, EVEN, true>(a, geo, Bl, b_lo, M, META, m_lo, m_hi, tx, ty, variant, GXp, GYp, ab_lo, ab_hi);
+    }
+#if EE_L2_PREFETCH_BWD_CANNY == 3
+    prefetch_ab_operands();
+#endif
     __syncthreads();
     if (active) cfast_stage_nms<NC, false, R, false, false, EVEN>(a, geo, M, META, m_lo, c_lo, c_hi, b, mode, tx, ty, variant);
     __syncthreads();
 
-    // ---- A / Bv on rows [ab_lo, ab_hi).  thin is kept implicitly: M (magnitude) is recomputed from the
-    //      blurred plane so that A can take over M's region once every thread has passed the barrier above;
-    //      but M of OTHER rows may still be read by slower threads of this stage?  No: this stage reads only
-    //      Bl and META, never M, so writing A into R1 is safe. -------------------------------------------
-    float* A = R1; float* Bv = R4;
+    // ---- A / Bv on rows [ab_lo, ab_hi).  gx1 / gy1 come from the planes the mag/dir stage kept, the gated magnitude
+    //      from M (M == 0 where the alpha gate closed or mag == 0: both give a zero gradient).  A overwrites M and Bv
+    //      overwrites gx1 IN PLACE (same thread, same element; M and gx1 are only read at the thread's own pixels in
+    //      this stage), so A's origin is M's row of ab_lo. -------------------------------------------------------
+    float* A = R1 + (size_t)(ab_lo - m_lo) * Wp; float* Bv = R4;
     if (active) {
         const float* base_b = a.e.base + (size_t)b * C * hw;
         const float* gin_b = a.e.g_in + (size_t)b * (BLEND ? C : 1) * hw;
         float* gbase_b = a.e.g_base ? a.e.g_base + (size_t)b * C * hw : nullptr;
-        const bool gate = (variant == 1);
         EE_FOR_CHUNKS_E(ab_lo, ab_hi) {
             const int lc = g * 4, col = geo.cs + lc, ra = ab_lo + ch * R, rb = EVEN ? ra + R : min(ra + R, ab_hi);
-            const float* pbl = Bl + kPadL + lc;
             const float* pmt = META + kPadL + lc;
-            float D[3][4], V[3][4];
             int hs[3][4], cw[3][4];
 #pragma unroll
             for (int i = 0; i < R + 2; ++i) {
                 const int rin = ra - 1 + i;
                 if (EVEN || rin <= rb) {
-                    const int rc = min(max(rin, 0), H - 1);
-                    sobel_partials(ld_win(pbl + (rc - b_lo) * Wp), D[i % 3], V[i % 3]);
                     if (hc) {
-                        meta_partials((rin >= 0 && rin < H) ? ld_win(pmt + (rin - m_lo) * Wp) : zero_win(), hs[i % 3], cw[i % 3]);
+                        if (EVEN && i > 0 && i < R + 1) meta_partials(ld_win(pmt + (rin - m_lo) * Wp), hs[i % 3], cw[i % 3]);
+                        else meta_partials((rin >= 0 && rin < H) ? ld_win(pmt + (rin - m_lo) * Wp) : zero_win(), hs[i % 3], cw[i % 3]);
                     } else if (EVEN ? (i > 0 && i < R + 1) : (rin >= ra && rin < rb)) {
                         const float4 t = *reinterpret_cast<const float4*>(pmt + (rin - m_lo) * Wp);
                         cw[i % 3][0] = __float_as_int(t.x); cw[i % 3][1] = __float_as_int(t.y);
@@ -358,20 +397,21 @@ __global__ void __launch_bounds__(256, EE_MINB_CANNY_BWD) edge_bwd_canny_fast(co
                 if (i >= 2 && (EVEN || ra + i - 2 < rb)) {
                     const int rout = ra + i - 2;
                     const int pix = rout * W + col;
-                    float gx1[4], gy1[4], sgx[4], sgy[4], mag[4], thin[4], ge[4];
+                    const int q = (rout - ab_lo) * Wp + kPadL + lc;
+                    float gx1[4], gy1[4], mag[4], thin[4], ge[4];
                     int meta[4], wih[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        sgx[k] = fmaf(0.5f, D[(i - 2) % 3][k] + D[i % 3][k], D[(i - 1) % 3][k]);
-                        sgy[k] = V[i % 3][k] - V[(i - 2) % 3][k];
+                    {
+                        const float4 tx4 = *reinterpret_cast<const float4*>(GXp + q);
+                        const float4 ty4 = *reinterpret_cast<const float4*>(GYp + q);
+                        const float4 tm4 = *reinterpret_cast<const float4*>(A + q);          // = M of this row
+                        gx1[0] = tx4.x; gx1[1] = tx4.y; gx1[2] = tx4.z; gx1[3] = tx4.w;
+                        gy1[0] = ty4.x; gy1[1] = ty4.y; gy1[2] = ty4.z; gy1[3] = ty4.w;
+                        mag[0] = tm4.x; mag[1] = tm4.y; mag[2] = tm4.z; mag[3] = tm4.w;
                     }
-                    div_channels8<DIVM>(sgx, sgy, fC, gx1, gy1);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        mag[k] = magnitude(gx1[k], gy1[k]);
                         meta[k] = cw[(i - 1) % 3][k];
-                        const float magm = (gate && mag[k] < a.e.alpha) ? 0.0f : mag[k];
-                        thin[k] = meta_removed(meta[k]) ? 0.0f : magm;
+                        thin[k] = meta_removed(meta[k]) ? 0.0f : mag[k];
                         wih[k] = 0;
                         if (hc) {
                             const int n = hs[(i - 2) % 3][k] + hs[(i - 1) % 3][k] + hs[i % 3][k];
@@ -423,10 +463,9 @@ __global__ void __launch_bounds__(256, EE_MINB_CANNY_BWD) edge_bwd_canny_fast(co
                         for (int k = 0; k < 4; ++k) {
                             float gm = g_thin_of_v(variant, a.e.low, a.e.high, mode, ge[k], thin[k], wih[k]);
                             if (meta_removed(meta[k])) gm = 0.0f;                     // core.py:290 / :480
-                            if (gate && mag[k] < a.e.alpha) gm = 0.0f;                // torch.where backward
+                            // torch.where backward (alpha gate): M == 0 there, and mag_backward returns 0 for mag == 0
                             mag_backward(gm, mag[k], gx1[k], gy1[k], fC, av[k], bv[k]);
                         }
-                        const int q = (rout - ab_lo) * Wp + kPadL + lc;
                         st_plane(A + q, av, col == 0, col + 4 == W, 0.0f, 0.0f);
                         st_plane(Bv + q, bv, col == 0, col + 4 == W, 0.0f, 0.0f);
                     }

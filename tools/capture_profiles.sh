@@ -20,6 +20,8 @@ for v in $variants; do
     python tools/ncu_raw_summary.py $out/${tag}_${v}.ncu-rep > $out/${tag}_ncu_full_${v}.txt
     ncu -i $out/${tag}_${v}.ncu-rep --page source --csv --print-source sass > $out/${tag}_sass_${v}.csv 2>/dev/null
     python tools/ncu_sass_summary.py $out/${tag}_sass_${v}.csv > $out/${tag}_sass_mix_${v}.txt
+    python tools/ncu_hot_lines.py $out/${tag}_sass_${v}.csv > $out/${tag}_hot_${v}.txt 2>/dev/null
+    rm -f $out/${tag}_${v}.ncu-rep $out/${tag}_sass_${v}.csv          # gpurun_out/ is capped at 64 MiB
   fi
 done
 ls -la $out | tail -20
