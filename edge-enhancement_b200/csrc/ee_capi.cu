@@ -4,6 +4,7 @@
 #include "ee_attack.cuh"
 #include "ee_edge_canny.cuh"
 #include "ee_edge_canny_fast.cuh"
+#include "ee_edge_cluster.cuh"
 #include "ee_edge_fast.cuh"
 #include "ee_edge_step125.cuh"
 #include "ee_square.cuh"
@@ -86,7 +87,7 @@ float cut_lt(float alpha) {
 // wide with 8 floats of padding per row; R rows per thread chunk.  Images up to 128 columns use one
 // column tile (full-width strips); wider ones are cut into ~64-column tiles.
 int plan_fast(int H, int W, int R, int rows_per_th, int rows_fixed, int max_halo_rows, int budget_bytes, int forced_th,
-              Launch& L, int halo_cols = 4, int max_full_width = 128) {
+              Launch& L, int halo_cols = 4, int max_full_width = 128, int pref_th_tiled = 0) {
     L.vec = 4;
     L.halo = halo_cols;
     // Full-width strips up to max_full_width columns (measured at 224 px: the forward is faster with
@@ -123,6 +124,9 @@ int plan_fast(int H, int W, int R, int rows_per_th, int rows_fixed, int max_halo
         th = (int)(fit < 4 ? 4 : (fit > H ? H : fit));
         const int tiles = (H + th - 1) / th;
         th = (H + tiles - 1) / tiles;
+        // measured preference for column-tiled images (Canny backward at 224 px: 48-row strips 2.06 TB/s, the
+        // equalised 56-row strips 1.49 TB/s)
+        if (L.tiles_x > 1 && pref_th_tiled > 0 && pref_th_tiled <= fit && pref_th_tiled < H) th = pref_th_tiled;
         // strips that are a multiple of the R = 4 rows a thread slides over keep every chunk full
         // (measured at 224 px: 19-row strips 5.8 TB/s, 16- or 28-row strips 6.3 TB/s)
         if (L.tiles_x == 1 && th < H && (th & 3)) {
@@ -174,6 +178,36 @@ int launch_fast_even(K kernel, Launch L, int B, const ee::FastArgs& a, cudaStrea
 }
 bool whole_image(const Launch& L, const ee::FastArgs& f, int side) {
     return L.tiles_x == 1 && L.TH == f.e.H && f.e.H == side && f.e.W == side && L.GX == side / 4;
+}
+
+void fill_fast(ee::FastArgs& f, const ee::EdgeArgs& a, const Launch& L);
+
+// One thread-block cluster per image (ee_edge_cluster.cuh): CS CTAs x TH rows, halo rows through DSMEM.
+template <typename K>
+int launch_cluster(K kernel, int W, int TH, int CS, int B, const ee::EdgeArgs& e, cudaStream_t s, const char* name) {
+    Launch L;
+    L.vec = 4; L.TH = TH; L.tiles = CS; L.GX = W / 4; L.RY = TH / 4; L.TW = W; L.tiles_x = 1; L.planeW = W; L.halo = 4;
+    L.threads = ((L.GX * L.RY + 31) / 32) * 32;
+    if (L.threads < 256) L.threads = 256;
+    L.smem = (size_t)3 * TH * (W + ee::kPadW) * sizeof(float);
+    ee::FastArgs f;
+    fill_fast(f, e, L);
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+    if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute");
+    if ((long long)B * CS > 0x7fffffffLL) return fail(EE_ERR_TOO_LARGE, "too many tiles");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * CS));
+    cfg.blockDim = dim3((unsigned)L.threads);
+    cfg.dynamicSmemBytes = L.smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    err = cudaLaunchKernelEx(&cfg, kernel, f);
+    if (err != cudaSuccess) return cuda_fail(err, name);
+    return EE_OK;
 }
 
 bool fast_eligible(const ee::EdgeArgs& a, bool vec_ok) {
@@ -396,13 +430,19 @@ int edge_backward(const float* g_in, const float* x, const float* base, float* g
             return fail(EE_ERR_UNSUPPORTED, "NHWC needs the fused blend entry point, C == 3, W %% 4 == 0, 16-byte aligned tensors");
         const bool st = (p->variant == EE_VARIANT_STEP125);
         rc = st ? plan_fast(H, W, 4, 3, 18, 8, 62 * 1024, g_th_bwd.load(), L)
-                : plan_fast(H, W, 4, ee::kCannyFastBwdRowsPerTH, ee::kCannyFastBwdRowsFixed, 12, 104 * 1024, g_th_bwd.load(), L, 8);
+                : plan_fast(H, W, 4, ee::kCannyFastBwdRowsPerTH, ee::kCannyFastBwdRowsFixed, 12, 104 * 1024, g_th_bwd.load(), L, 8, 128, 48);
         if (rc) return rc;
         if (!st) L.even_planes = 4;      // whole-image Canny backward: gy1 reuses the blurred plane's region
         ee::FastArgs f;
         fill_fast(f, a, L);
         if (st) EE_DISPATCH_FAST_NHWC(ee::edge_bwd_step125_fast, L, B, f, s, "edge_bwd_step125_fast_nhwc");
         else EE_DISPATCH_FAST_NHWC(ee::edge_bwd_canny_fast, L, B, f, s, "edge_bwd_canny_fast_nhwc");
+    }
+    if (p->variant == EE_VARIANT_STEP125 && fast_eligible(a, vec_ok) && g_staging.load() == 5 && C == 3 && H == 224 && W == 224) {
+        // opt-in (staging 5; measured equal to the strip kernels, ee_edge_cluster.cuh): ImageNet size as one cluster of
+        // 8 CTAs x 28 rows per image, halo rows exchanged through distributed shared memory
+        if (blend) return launch_cluster(ee::edge_bwd_step125_cluster<3, true, 4, 224, 28, 8>, 224, 28, 8, B, a, s, "edge_bwd_step125_cluster");
+        return launch_cluster(ee::edge_bwd_step125_cluster<3, false, 4, 224, 28, 8>, 224, 28, 8, B, a, s, "edge_bwd_step125_cluster");
     }
     if (p->variant == EE_VARIANT_STEP125 && fast_eligible(a, vec_ok)) {
         rc = plan_fast(H, W, 4, 3, 18, 8, 62 * 1024, g_th_bwd.load(), L);
@@ -420,7 +460,7 @@ int edge_backward(const float* g_in, const float* x, const float* base, float* g
         else EE_DISPATCH(ee::edge_bwd_step125_kernel, false, L, B, a, s, "edge_bwd_step125");
     }
     if (fast_eligible(a, vec_ok)) {
-        rc = plan_fast(H, W, 4, ee::kCannyFastBwdRowsPerTH, ee::kCannyFastBwdRowsFixed, 12, 104 * 1024, g_th_bwd.load(), L, 8);
+        rc = plan_fast(H, W, 4, ee::kCannyFastBwdRowsPerTH, ee::kCannyFastBwdRowsFixed, 12, 104 * 1024, g_th_bwd.load(), L, 8, 128, 48);
         if (rc) return rc;
         L.even_planes = 4;               // whole-image Canny backward: gy1 reuses the blurred plane's region
         ee::FastArgs f;

@@ -630,6 +630,87 @@ __device__ __forceinline__ void fast_stage_gauss_adjoint_store(const FastArgs& a
     }
 }
 
+// One output row (4 pixels) of the backward's A/Bv stage: from the Sobel partials of the three blurred rows around it
+// recompute gx1, gy1, u = mag^2 and the edge value, apply the blend's clamp mask to g_out (-> g_base, written when
+// `interior`), reduce over channels, apply the STE window and the magnitude adjoint, and store A = dL/dSgx,
+// Bv = dL/dSgy into the planes (pad columns zeroed by the border groups).
+template <int NC, bool BLEND, bool NHWC, int DIVM>
+__device__ __forceinline__ void bwd_abv_row(const FastArgs& a, const float (&Du)[4], const float (&Dm)[4], const float (&Dd)[4],
+                                            const float (&Vu)[4], const float (&Vd)[4], int pix, bool interior, bool left,
+                                            bool right, const float* __restrict__ base_b, const float* __restrict__ gin_b,
+                                            float* gbase_b, size_t hw, bool want_gx, float* Adst, float* Bvdst) {
+    const int C = NC ? NC : a.e.C;
+    const float fC = a.e.fC, wgt = a.e.w;
+    float gx1[4], gy1[4], u[4], ge[4], sgx[4], sgy[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        sgx[k] = fmaf(0.5f, Du[k] + Dd[k], Dm[k]);
+        sgy[k] = Vd[k] - Vu[k];
+    }
+    div_channels8<DIVM>(sgx, sgy, fC, gx1, gy1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = gx1[k] * gx1[k] + gy1[k] * gy1[k];
+    if (BLEND) {
+        float we[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) we[k] = wgt * edge_from_u(a, u[k]);
+        float4 bs[NC ? NC : 1], go[NC ? NC : 1];
+        if (NC) {
+            ld_px4<NC, NHWC>(base_b, hw, pix, bs);
+            ld_px4<NC, NHWC>(gin_b, hw, pix, go);
+        }
+#pragma unroll 3
+        for (int c = 0; c < C; ++c) {
+            float4 bsc, goc;
+            if (NC) { bsc = bs[NC ? c : 0]; goc = go[NC ? c : 0]; }
+            else {
+                bsc = __ldg(reinterpret_cast<const float4*>(base_b + c * hw + pix));
+                goc = __ldg(reinterpret_cast<const float4*>(gin_b + c * hw + pix));
+            }
+            const float bsv[4] = {bsc.x, bsc.y, bsc.z, bsc.w}, gov[4] = {goc.x, goc.y, goc.z, goc.w};
+            float gp[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float pre = bsv[k] + we[k];
+                gp[k] = (pre >= 0.0f && pre <= 1.0f) ? gov[k] : 0.0f;
+                ge[k] = (c == 0) ? gp[k] * wgt : fmaf(gp[k], wgt, ge[k]);
+            }
+            if (NC) go[NC ? c : 0] = make_float4(gp[0], gp[1], gp[2], gp[3]);     // g_base of this channel
+            else if (gbase_b && interior)
+                __stcs(reinterpret_cast<float4*>(gbase_b + c * hw + pix), make_float4(gp[0], gp[1], gp[2], gp[3]));
+        }
+        if (NC && gbase_b && interior) st_px4<NC, NHWC>(gbase_b, hw, pix, go);
+    } else {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(gin_b + pix));
+        ge[0] = t.x; ge[1] = t.y; ge[2] = t.z; ge[3] = t.w;
+    }
+    if (want_gx) {
+        float av[4], bv[4];
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // To_compare.backward window and the torch.where gate in u-space:
+            // (mag > high, mag <= 1.001, not mag < alpha) <=> e_cut < u <= w_cut
+            const bool in_win = (u[k] > a.e_cut) && (u[k] <= a.w_cut);
+            ge[k] = in_win ? ge[k] : 0.0f;
+            av[k] = 0.0f; bv[k] = 0.0f;
+            any = any || (ge[k] != 0.0f);
+        }
+        if (any) {          // ~5 % of pixels carry gradient: one branch per 4 pixels
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (ge[k] != 0.0f && u[k] != 0.0f) {
+                    const float t = ge[k] / (sqrtf(u[k]) * fC);
+                    av[k] = t * gx1[k];
+                    bv[k] = t * gy1[k];
+                }
+            }
+        }
+        st_plane(Adst, av, left, right, 0.0f, 0.0f);
+        st_plane(Bvdst, bv, left, right, 0.0f, 0.0f);
+    }
+}
+
 // -------------------------------------------------------------------------------------------
 // backward.  smem regions (stride Wp): R1 = S then A (TH+8 rows), R2 = Bl then GB (TH+6), R3 = Bv (TH+4);
 // a region never needs more rows than the image has (halo rows are clipped), so each is min(TH+k, H) rows
@@ -662,7 +743,6 @@ __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const 
     const int b_lo = max(r0 - 3, 0), b_hi = min(r1 + 3, H);
     const int ab_lo = want_gx ? max(r0 - 2, 0) : r0, ab_hi = want_gx ? min(r1 + 2, H) : r1;
     const int gb_lo = max(r0 - 1, 0), gb_hi = min(r1 + 1, H);
-    const float fC = a.e.fC, wgt = a.e.w;
 
     float* S = R1; float* Bl = R2;
     auto prefetch_bwd_operands = [&]() {
@@ -716,77 +796,11 @@ __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const 
                     }
                     if (i >= 2 && (FULL || EVEN || ra + i - 2 < rb)) {
                         const int rout = ra + i - 2;
-                        const int pix = rout * W + col;
-                        float gx1[4], gy1[4], u[4], ge[4], sgx[4], sgy[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            sgx[k] = fmaf(0.5f, D[(i - 2) % 3][k] + D[i % 3][k], D[(i - 1) % 3][k]);
-                            sgy[k] = V[i % 3][k] - V[(i - 2) % 3][k];
-                        }
-                        div_channels8<DIVM>(sgx, sgy, fC, gx1, gy1);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) u[k] = gx1[k] * gx1[k] + gy1[k] * gy1[k];
-                        if (BLEND) {
-                            float we[4];
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) we[k] = wgt * edge_from_u(a, u[k]);
-                            const bool interior = EVEN || (rout >= r0 && rout < r1 && col >= geo.c0 && col < geo.c1);
-                            float4 bs[NC ? NC : 1], go[NC ? NC : 1];
-                            if (NC) {
-                                ld_px4<NC, NHWC>(base_b, hw, pix, bs);
-                                ld_px4<NC, NHWC>(gin_b, hw, pix, go);
-                            }
-#pragma unroll 3
-                            for (int c = 0; c < C; ++c) {
-                                float4 bsc, goc;
-                                if (NC) { bsc = bs[NC ? c : 0]; goc = go[NC ? c : 0]; }
-                                else {
-                                    bsc = __ldg(reinterpret_cast<const float4*>(base_b + c * hw + pix));
-                                    goc = __ldg(reinterpret_cast<const float4*>(gin_b + c * hw + pix));
-                                }
-                                const float bsv[4] = {bsc.x, bsc.y, bsc.z, bsc.w}, gov[4] = {goc.x, goc.y, goc.z, goc.w};
-                                float gp[4];
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    const float pre = bsv[k] + we[k];
-                                    gp[k] = (pre >= 0.0f && pre <= 1.0f) ? gov[k] : 0.0f;
-                                    ge[k] = (c == 0) ? gp[k] * wgt : fmaf(gp[k], wgt, ge[k]);
-                                }
-                                if (NC) go[NC ? c : 0] = make_float4(gp[0], gp[1], gp[2], gp[3]);     // g_base of this channel
-                                else if (gbase_b && interior)
-                                    __stcs(reinterpret_cast<float4*>(gbase_b + c * hw + pix), make_float4(gp[0], gp[1], gp[2], gp[3]));
-                            }
-                            if (NC && gbase_b && interior) st_px4<NC, NHWC>(gbase_b, hw, pix, go);
-                        } else {
-                            const float4 t = __ldg(reinterpret_cast<const float4*>(gin_b + pix));
-                            ge[0] = t.x; ge[1] = t.y; ge[2] = t.z; ge[3] = t.w;
-                        }
-                        if (want_gx) {
-                            float av[4], bv[4];
-                            bool any = false;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                // To_compare.backward window and the torch.where gate in u-space:
-                                // (mag > high, mag <= 1.001, not mag < alpha) <=> e_cut < u <= w_cut
-                                const bool in_win = (u[k] > a.e_cut) && (u[k] <= a.w_cut);
-                                ge[k] = in_win ? ge[k] : 0.0f;
-                                av[k] = 0.0f; bv[k] = 0.0f;
-                                any = any || (ge[k] != 0.0f);
-                            }
-                            if (any) {          // ~5 % of pixels carry gradient: one branch per 4 pixels
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    if (ge[k] != 0.0f && u[k] != 0.0f) {
-                                        const float t = ge[k] / (sqrtf(u[k]) * fC);
-                                        av[k] = t * gx1[k];
-                                        bv[k] = t * gy1[k];
-                                    }
-                                }
-                            }
-                            const int q = (rout - ab_lo) * Wp + kPadL + lc;
-                            st_plane(A + q, av, col == 0, col + 4 == W, 0.0f, 0.0f);
-                            st_plane(Bv + q, bv, col == 0, col + 4 == W, 0.0f, 0.0f);
-                        }
+                        const bool interior = EVEN || (rout >= r0 && rout < r1 && col >= geo.c0 && col < geo.c1);
+                        const int q = (rout - ab_lo) * Wp + kPadL + lc;
+                        bwd_abv_row<NC, BLEND, NHWC, DIVM>(a, D[(i - 2) % 3], D[(i - 1) % 3], D[i % 3], V[(i - 2) % 3], V[i % 3],
+                                                           rout * W + col, interior, col == 0, col + 4 == W, base_b, gin_b, gbase_b,
+                                                           hw, want_gx, A + q, Bv + q);
                     }
                 }
             };

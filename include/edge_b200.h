@@ -155,7 +155,8 @@ const char* ee_last_error(void); /* thread-local, never NULL */
 int ee_version(void);            /* EE_VERSION */
 
 /* Tuning knob for benchmarks/tests: force the row-strip height of the tiled edge kernels
- * (0 = heuristic) and the staging path (0 = auto, 1 = generic kernels only, 4 = tuned kernels even for wide images).
+ * (0 = heuristic) and the staging path (0 = auto, 1 = generic kernels only, 4 = tuned kernels even for wide images,
+ * 5 = experimental thread-block-cluster backward for 3x224x224).
  * Process-wide; returns EE_OK.  Not needed for normal use. */
 int ee_set_tuning(int strip_rows_fwd, int strip_rows_bwd, int staging);
 

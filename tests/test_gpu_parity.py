@@ -136,6 +136,29 @@ def test_only_g_base_requested():
         assert_same("g_x", g_x, O.edge_blend_bwd(g_out, x, base, po, 1.0)[0])
 
 
+def test_cluster_backward_224():
+    """ImageNet size: the opt-in backward that runs as one thread-block cluster per image (8 CTAs x 28 rows, halo
+    rows through distributed shared memory, ee_edge_cluster.cuh; staging 5).  Same bits as the oracle and as the
+    default strip kernels, also when only one of the two gradients is requested."""
+    x, base, g_out, g_edge = T.make_inputs(224, 3, 3, 224, 224)
+    pc, po = both_params("step125", 0.02, None, T.HIGH, False)
+    L = _lib.load()
+    o_gx, o_gb = O.edge_blend_bwd(g_out, x, base, po, 1.0)
+    for staging in (0, 5):
+        L.ee_set_tuning(0, 0, staging)
+        g_x, g_base = F_ee.edge_blend_backward(cu(g_out), cu(x), cu(base), pc, 1.0)
+        assert_same("g_base", g_base, o_gb)
+        assert_same("g_x", g_x, o_gx)
+        only_b = F_ee.edge_blend_backward(cu(g_out), cu(x), cu(base), pc, 1.0, need_x=False, need_base=True)
+        assert only_b[0] is None
+        assert_same("g_base only", only_b[1], o_gb)
+        only_x = F_ee.edge_blend_backward(cu(g_out), cu(x), cu(base), pc, 1.0, need_x=True, need_base=False)
+        assert only_x[1] is None
+        assert_same("g_x only", only_x[0], o_gx)
+        assert_same("g_x(edge)", F_ee.edge_map_backward(cu(g_edge), cu(x), pc), O.edge_bwd(g_edge, x, po))
+    L.ee_set_tuning(0, 0, 0)
+
+
 # ---------------------------------------------------------------------------------------------
 # attack updates: bit-exact vs the oracle AND vs the torch expression of the reference on the GPU
 # ---------------------------------------------------------------------------------------------
