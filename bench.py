@@ -73,6 +73,26 @@ def dist_env():
     return rank, world, local
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host threads (and therefore the first-touch placement of its pinned staging buffers) to the CPUs
+    NVML reports as local to GPU `index`, so that with several ranks per box the H2D / D2H traffic of the e2e leg does
+    not cross the socket interconnect.  Returns the number of CPUs bound to (0 = left unchanged)."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        words = nv.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        cpus = [i * 64 + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def shard_sizes(total, world):
     """Contiguous batch shards, sizes differ by at most one (what DistributedSampler does)."""
     base, rem = divmod(total, world)
@@ -297,6 +317,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU port)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = bind_to_gpu_numa_node(local) if world > 1 else 0
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=dev)
 
@@ -426,7 +447,7 @@ def run_ours(args):
             "metric": "edge-enhanced PGD-10 hot-path images/sec", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, B, world),
+            "config": dict(workload_config(args, B, world), host_cpus_bound_per_rank=numa_cpus),
             "clocks": clocks, "e2e": e2e, "e2e_attack_api": e2e_api, "gpu_launches": launches,
             "roofline": roofline, "kernels": kern, "cpu_baseline": cpu,
         }

@@ -1,0 +1,230 @@
+"""Edge-enhanced PGD-10 adversarial TRAINING throughput (images/s) with a real CNN, 1..N GPUs (DDP over NCCL).
+
+    python tools/train_throughput.py [--front ours|eager|both] [--iters 6] [--batch 256]
+    torchrun --nproc-per-node N tools/train_throughput.py ...
+
+BASELINE.json configs[1]: Tiny-ImageNet PreAct-ResNet18, 3x64x64, batch 256 per GPU (weak scaling), PGD-10
+(eps 16/255, step 2/255), CannyFilter_step125_1 front end (high 76/255, w = 1, r = 8), SGD.  The CNN, the loss, DDP's
+gradient all-reduce and the FFT low-pass stay on stock PyTorch (outside the product); what changes between the two
+front ends is ONLY the hot path:
+  ours  : core.EdgeEnhance (fused edge + blend kernels) and attacks.PGD (fused sign/project/clamp step)
+  eager : the same mathematics composed from stock torch ops the way the reference composes it (per-channel
+          replicate-pad + 3x3 conv, channel-summing Sobel convs, pow / where / masked writes, autograd through all
+          of it; 8 elementwise kernels per PGD update; the five host-side zeros + H2D scratch allocations per call) --
+          written here from SURVEY.md section 2.3, it stands for "the reference's op chain on the same B200" (the
+          reference itself cannot travel to the GPU box).
+  eager_clean : the same without the reference's dead host-side allocations (what a tidy eager version would cost).
+One iteration = PGD-10 attack (10 x model forward + input gradient + update) + training forward/backward + SGD step,
+i.e. what Tiny_ImageNet/experiments_tinyimagenet.py:train does per batch.  Synthetic data, random-init weights.
+Prints one JSON line per front end (rank 0).  This is supporting evidence for the north-star metric; the judged
+bench line is bench.py (hot path only).
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import sys
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+EPS, ALPHA, HIGH = 16 / 255, 2 / 255, 76 / 255
+
+
+# ---- stock CNN: PreAct-ResNet18 for 64x64 inputs (AWP/Tiny_imagenet/models_tiny_awp/preactresnet.py is the reference's) ----
+class PreActBlock(nn.Module):
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.bn1, self.bn2 = nn.BatchNorm2d(cin), nn.BatchNorm2d(cout)
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
+        self.short = nn.Conv2d(cin, cout, 1, stride, bias=False) if (stride != 1 or cin != cout) else None
+
+    def forward(self, x):
+        o = F.relu(self.bn1(x))
+        sc = self.short(o) if self.short is not None else x
+        o = self.conv1(o)
+        o = self.conv2(F.relu(self.bn2(o)))
+        return o + sc
+
+
+class PreActResNet18(nn.Module):
+    def __init__(self, front, n_class=200):
+        super().__init__()
+        self.front = front
+        self.conv1 = nn.Conv2d(3, 64, 3, 1, 1, bias=False)
+        cfg, layers, cin = [(64, 1), (128, 2), (256, 2), (512, 2)], [], 64
+        for cout, stride in cfg:
+            layers += [PreActBlock(cin, cout, stride), PreActBlock(cout, cout, 1)]
+            cin = cout
+        self.layers = nn.Sequential(*layers)
+        self.bn = nn.BatchNorm2d(512)
+        self.fc = nn.Linear(512, n_class)
+
+    def forward(self, x):
+        x = self.front(x)
+        o = self.layers(self.conv1(x))
+        o = F.relu(self.bn(o))
+        return self.fc(F.adaptive_avg_pool2d(o, 1).flatten(1))
+
+
+# ---- eager front end: the reference's composition out of stock torch ops ----
+class _ThresholdSTE(torch.autograd.Function):
+    """binary mask `v > thr` with the straight-through window (thr, 1.001] in the backward"""
+
+    @staticmethod
+    def forward(ctx, v, thr):
+        ctx.save_for_backward(v, thr)
+        out = v.clone()
+        out[v > thr] = 1.0
+        out[v <= thr] = 0.0
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        v, thr = ctx.saved_tensors
+        gi = g.clone()
+        gi[v > 1.001] = 0
+        gi[v <= thr] = 0
+        return gi, None
+
+
+class EagerFront(nn.Module):
+    def __init__(self, size, r, w, high, dev, faithful=True):
+        super().__init__()
+        self.faithful = faithful        # True: also the reference's per-call host-side zeros + H2D scratch allocations
+        import numpy as np
+        from edge_enhancement_b200 import core
+        self.w, self.high = w, high
+        self.hfs = core.HighFreqSuppress(size, size, r)                 # same torch.fft low-pass in both arms
+        g = torch.from_numpy(core.get_gaussian_kernel(3, 0, 1)).float()[None, None].to(dev)
+        sx = torch.from_numpy(core.get_sobel_kernel(3)).float()[None, None].to(dev)
+        self.wg, self.wsx, self.wsy = g, sx, sx.transpose(2, 3).contiguous()
+        self.pad = nn.ReplicationPad2d(1)
+
+    def edge(self, img):
+        B, C, H, W = img.shape
+        dev = img.device
+        if self.faithful:               # utils/core.py:553-557: five torch.zeros(...).to(device) per call, four of them unused
+            blurred = torch.zeros((B, C, H, W)).to(dev)
+            for _name in ("gx", "gy", "mag", "ori"):
+                torch.zeros((B, 1, H, W)).to(dev)
+        else:
+            blurred = torch.empty((B, C, H, W), device=dev)
+        for c in range(C):
+            blurred[:, c:c + 1] = F.conv2d(self.pad(img[:, c:c + 1]), self.wg)
+        pb = self.pad(blurred)
+        gx = F.conv2d(pb, self.wsx.repeat(1, C, 1, 1)) / C
+        gy = F.conv2d(pb, self.wsy.repeat(1, C, 1, 1)) / C
+        mag = (gx ** 2 + gy ** 2) ** 0.5
+        mag = torch.where(mag < 0.0, torch.zeros_like(mag), mag)          # alpha gate (alpha = 0)
+        thin = mag.clone()
+        return _ThresholdSTE.apply(thin, torch.tensor(self.high)) * 1
+
+    def forward(self, x):
+        x_hfs = self.hfs(x)
+        x = x_hfs + self.w * self.edge(x)
+        return torch.clamp(x, 0.0, 1.0)
+
+
+def eager_pgd(model, x0, y, steps, alpha, eps):
+    x = x0.detach()
+    for _ in range(steps):
+        x.requires_grad_()
+        with torch.enable_grad():
+            loss = F.cross_entropy(model(x), y, reduction='sum')
+        grad = torch.autograd.grad(loss, [x])[0]
+        x = x.detach() + alpha * torch.sign(grad.detach())
+        x = torch.min(torch.max(x, x0 - eps), x0 + eps)
+        x = torch.clamp(x, 0, 1)
+    return x
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--front", default="all", choices=["ours", "eager", "eager_clean", "all"])
+    ap.add_argument("--iters", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU")
+    ap.add_argument("--side", type=int, default=64)
+    ap.add_argument("--pgd-steps", type=int, default=10)
+    args = ap.parse_args()
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from edge_enhancement_b200 import attacks, core
+
+    class A:
+        random = True
+        epsilon = EPS
+
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.rand((args.batch, 3, args.side, args.side), device=dev, generator=gen)
+    y = torch.randint(0, 200, (args.batch,), device=dev, generator=gen)
+    results = []
+    for front_name in (["ours", "eager", "eager_clean"] if args.front == "all" else [args.front]):
+        torch.manual_seed(0)
+        if front_name == "ours":
+            with contextlib.redirect_stdout(io.StringIO()):
+                front = core.EdgeEnhance(cize=args.side, r=8, w=1.0, low=38.0, high=76.0, alpha=0.0, sigma=1,
+                                         type_canny='CannyFilter_step125_1')
+        else:
+            front = EagerFront(args.side, 8, 1.0, HIGH, dev, faithful=(front_name == "eager"))
+        model = PreActResNet18(front).to(dev)
+        net = nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+        opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9, weight_decay=2e-4)
+
+        def iteration():
+            net.eval()                                       # attack in eval mode keeps BN statistics out of the inner loop
+            if front_name == "ours":
+                x_adv = attacks.PGD(net, A, x, y, args.pgd_steps, ALPHA)
+            else:
+                xs = torch.clamp(x + torch.zeros_like(x).uniform_(-EPS, EPS), 0, 1)
+                x_adv = eager_pgd(net, xs, y, args.pgd_steps, ALPHA, EPS)
+            net.train()
+            loss = F.cross_entropy(net(x_adv), y)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            return loss
+
+        for _ in range(args.warmup):
+            iteration()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.iters):
+            loss = iteration()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ips = world * args.batch * args.iters / (float(ms.item()) / 1e3)
+        results.append((front_name, ips))
+        if rank == 0:
+            print(json.dumps({"metric": "edge-enhanced PGD-%d adversarial training images/sec" % args.pgd_steps, "front_end": front_name,
+                              "value": ips, "unit": "images/s", "n_gpus": world, "ms_per_iteration": float(ms.item()) / args.iters,
+                              "config": "PreAct-ResNet18 (stock torch ops, fp32, cudnn TF32 default), 3x%dx%d, batch %d per GPU, "
+                                        "CannyFilter_step125_1 + torch.fft low-pass, eps 16/255, step 2/255, SGD; DDP/NCCL for N > 1"
+                                        % (args.side, args.side, args.batch),
+                              "final_loss": float(loss.item()), "data": "synthetic"}), flush=True)
+        del net, model, opt
+        torch.cuda.empty_cache()
+    if rank == 0 and len(results) > 1:
+        print(json.dumps({"speedup_ours_over_" + n: results[0][1] / v for n, v in results[1:]}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
