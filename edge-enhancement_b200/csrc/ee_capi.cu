@@ -5,6 +5,7 @@
 #include "ee_edge_canny.cuh"
 #include "ee_edge_canny_fast.cuh"
 #include "ee_edge_cluster.cuh"
+#include "ee_edge_tiles.cuh"
 #include "ee_edge_fast.cuh"
 #include "ee_edge_step125.cuh"
 #include "ee_square.cuh"
@@ -208,6 +209,18 @@ int launch_cluster(K kernel, int W, int TH, int CS, int B, const ee::EdgeArgs& e
     err = cudaLaunchKernelEx(&cfg, kernel, f);
     if (err != cudaSuccess) return cuda_fail(err, name);
     return EE_OK;
+}
+
+// Chunk-aligned tiles for wide images (ee_edge_tiles.cuh): <= 56 x 56 outputs per CTA, 64 x 64 planes, 16 x 16 chunks.
+void plan_tiles(int H, int W, Launch& L) {
+    int ty = (H + 55) / 56, tx = (W + 55) / 56;
+    L.TH = (((H + ty - 1) / ty) + 3) & ~3;
+    L.TW = (((W + tx - 1) / tx) + 3) & ~3;
+    ty = (H + L.TH - 1) / L.TH;
+    L.tiles_x = (W + L.TW - 1) / L.TW;
+    L.tiles = ty * L.tiles_x;
+    L.vec = 4; L.planeW = 64; L.halo = 4; L.GX = 16; L.RY = 16; L.threads = 256;
+    L.smem = (size_t)3 * (L.TH + 8) * (64 + ee::kPadW) * sizeof(float);
 }
 
 bool fast_eligible(const ee::EdgeArgs& a, bool vec_ok) {
@@ -443,6 +456,19 @@ int edge_backward(const float* g_in, const float* x, const float* base, float* g
         // 8 CTAs x 28 rows per image, halo rows exchanged through distributed shared memory
         if (blend) return launch_cluster(ee::edge_bwd_step125_cluster<3, true, 4, 224, 28, 8>, 224, 28, 8, B, a, s, "edge_bwd_step125_cluster");
         return launch_cluster(ee::edge_bwd_step125_cluster<3, false, 4, 224, 28, 8>, 224, 28, 8, B, a, s, "edge_bwd_step125_cluster");
+    }
+    if (p->variant == EE_VARIANT_STEP125 && fast_eligible(a, vec_ok) && W > 128 && H % 4 == 0 && H >= 16 && g_th_bwd.load() == 0 &&
+        g_staging.load() != 3) {
+        // wide images: chunk-aligned 56 x 56 tiles, one chunk per thread, no row guards (staging 3 = the older strip path)
+        plan_tiles(H, W, L);
+        ee::FastArgs f;
+        fill_fast(f, a, L);
+        if (C == 3) {
+            if (blend) return launch_fast(ee::edge_bwd_step125_tiles<3, true, 4, 64>, L, B, f, s, "edge_bwd_step125_tiles");
+            return launch_fast(ee::edge_bwd_step125_tiles<3, false, 4, 64>, L, B, f, s, "edge_bwd_step125_tiles");
+        }
+        if (blend) return launch_fast(ee::edge_bwd_step125_tiles<0, true, 4, 64>, L, B, f, s, "edge_bwd_step125_tiles");
+        return launch_fast(ee::edge_bwd_step125_tiles<0, false, 4, 64>, L, B, f, s, "edge_bwd_step125_tiles");
     }
     if (p->variant == EE_VARIANT_STEP125 && fast_eligible(a, vec_ok)) {
         rc = plan_fast(H, W, 4, 3, 18, 8, 62 * 1024, g_th_bwd.load(), L);

@@ -54,13 +54,14 @@ SHAPES = [
     (2, 3, 64, 64), (3, 1, 28, 28), (2, 3, 32, 32), (1, 3, 224, 224), (2, 3, 17, 23), (2, 2, 9, 12),
     (3, 1, 1, 1), (2, 3, 1, 8), (2, 3, 8, 1), (1, 4, 2, 2), (1, 3, 5, 4), (1, 3, 40, 300),
     (2, 3, 4, 8), (1, 5, 13, 16), (1, 3, 9, 1028), (2, 3, 12, 132), (1, 1, 30, 256),
+    (1, 1, 64, 256), (1, 2, 32, 200), (1, 3, 288, 288),        # wide + H % 4 == 0: chunk-aligned tile backward
 ]
 VARIANT_MODES = [("step125", "hyst")] + [(v, m) for v in ("canny", "bpda") for m in ("hyst", "mix", "low", "raw")]
 
 
-# staging knob of ee_set_tuning: 0 = auto (tuned kernels for W <= 128), 1 = generic kernels only,
-# 4 = tuned kernels also for wide images
-@pytest.mark.parametrize("staging", [0, 1, 4])
+# staging knob of ee_set_tuning: 0 = auto, 1 = generic kernels only, 3 = strip kernels instead of the chunk-aligned
+# tiles for wide images, 4 = tuned kernels also for wide images
+@pytest.mark.parametrize("staging", [0, 1, 3, 4])
 @pytest.mark.parametrize("strip", [0, 1, 3, 7])
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("variant,mode", VARIANT_MODES)
@@ -137,14 +138,14 @@ def test_only_g_base_requested():
 
 
 def test_cluster_backward_224():
-    """ImageNet size: the opt-in backward that runs as one thread-block cluster per image (8 CTAs x 28 rows, halo
-    rows through distributed shared memory, ee_edge_cluster.cuh; staging 5).  Same bits as the oracle and as the
-    default strip kernels, also when only one of the two gradients is requested."""
+    """ImageNet size: the default chunk-aligned tile backward (ee_edge_tiles.cuh), the older strip kernels (staging 3)
+    and the opt-in thread-block-cluster backward (8 CTAs x 28 rows, halo rows through distributed shared memory,
+    ee_edge_cluster.cuh; staging 5) all give the oracle's bits, also when only one of the two gradients is requested."""
     x, base, g_out, g_edge = T.make_inputs(224, 3, 3, 224, 224)
     pc, po = both_params("step125", 0.02, None, T.HIGH, False)
     L = _lib.load()
     o_gx, o_gb = O.edge_blend_bwd(g_out, x, base, po, 1.0)
-    for staging in (0, 5):
+    for staging in (0, 3, 5):
         L.ee_set_tuning(0, 0, staging)
         g_x, g_base = F_ee.edge_blend_backward(cu(g_out), cu(x), cu(base), pc, 1.0)
         assert_same("g_base", g_base, o_gb)
