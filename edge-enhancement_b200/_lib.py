@@ -36,6 +36,8 @@ SIGNATURES = {
     "ee_free_at_step_f32": [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _vp],
     "ee_cw_linf_step_f32": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _vp],
     "ee_pgd_l2_step_f32": [_vp, _vp, _vp, _vp, _i, _i64, _f, _f, _vp],
+    "ee_add_clamp_f32": [_vp, _vp, _vp, _i64, _f, _f, _vp],
+    "ee_avmixup_mix_f32": [_vp, _vp, _vp, _vp, _i, _i64, _f, _vp],
     "ee_to_compare_fwd_f32": [_vp, _vp, _i64, _f, _vp],
     "ee_to_compare_bwd_f32": [_vp, _vp, _vp, _i64, _f, _vp],
     "ee_to_eq_fwd_f32": [_vp, _vp, _i64, _vp],

@@ -14,6 +14,12 @@ import torch.nn.functional as F
 from . import functional as F_ee
 
 
+def _random_start(x, epsilon):
+    """utils/attacks.py:15-17: x + U(-eps, eps), clamped to [0, 1].  The noise is the reference's own draw
+    (zeros_like(x).uniform_ advances the generator identically); add + clamp are one kernel."""
+    return F_ee.add_clamp(x, torch.empty_like(x).uniform_(-epsilon, epsilon), 0.0, 1.0)
+
+
 def _linf_step(x, grad, inputs, step_signed, epsilon):
     """utils/attacks.py:25-27 fused: clamp(min(max(x + a*sign(g), x0-eps), x0+eps), 0, 1)."""
     return F_ee.pgd_linf_step(x.detach(), grad.detach(), inputs.detach(), step_signed, epsilon, 0.0, 1.0)
@@ -24,8 +30,7 @@ def PGD(model, args, inputs, targets, num_steps, step_size):
     x = inputs.detach()
 
     if args.random:
-        x = x + torch.zeros_like(x).uniform_(-args.epsilon, args.epsilon)
-        x = torch.clamp(x, 0, 1)
+        x = _random_start(x, args.epsilon)
 
     for i in range(num_steps):
         x.requires_grad_()
@@ -45,8 +50,7 @@ def targeted_PGD(model, args, inputs, labels, num_steps, step_size, nclass, devi
     target_labels = torch.fmod(labels + label_offset, nclass)
 
     if args.random:
-        x = x + torch.zeros_like(x).uniform_(-args.epsilon, args.epsilon)
-        x = torch.clamp(x, 0.0, 1.0)
+        x = _random_start(x, args.epsilon)
 
     for i in range(num_steps):
         x.requires_grad_()
@@ -381,8 +385,7 @@ class AVmixup:
     def _attack(self, model, inputs, soft_targets, step_signed):
         x = inputs.detach()
         if self.args.random:
-            x = x + torch.zeros_like(x).uniform_(-self.args.epsilon, self.args.epsilon)
-            x = torch.clamp(x, 0, 1)
+            x = _random_start(x, self.args.epsilon)
         for i in range(self.num_steps):
             x.requires_grad_()
             with torch.enable_grad():
@@ -394,17 +397,15 @@ class AVmixup:
         return x
 
     def _mix(self, x, inputs, targets):
-        perturb = (x - inputs) * self.gamma
-        adversarial_vertex = inputs + perturb
-        adversarial_vertex = torch.clamp(adversarial_vertex, 0, 1)
         y_nat = self._label_smoothing(targets, self.lambda1)
         y_vertex = self._label_smoothing(targets, self.lambda2)
         x_weight = np.random.beta(1.0, 1.0, [x.shape[0], 1, 1, 1])
-        x_weight_torch = torch.from_numpy(x_weight).to(self.device)
-        y_weight = torch.from_numpy(np.reshape(x_weight, [-1, 1])).to(self.device)
-        x = inputs * x_weight_torch + adversarial_vertex * (1 - x_weight_torch)
+        x_weight_torch = torch.from_numpy(x_weight).to(x.device)
+        y_weight = torch.from_numpy(np.reshape(x_weight, [-1, 1])).to(x.device)
+        # attacks.py:469-471 + :476 (vertex, clamp, float64 mix, cast back) fused into one pass
+        x = F_ee.avmixup_mix(x.detach(), inputs.detach(), x_weight_torch, self.gamma)
         y = y_nat * y_weight + y_vertex * (1 - y_weight)
-        return x.to(torch.float), y
+        return x, y
 
     def perturb(self, model, inputs, targets):
         """attacks.py:447-479 (targets are soft / one-hot labels)."""

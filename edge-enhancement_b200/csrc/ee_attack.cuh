@@ -80,6 +80,10 @@ struct FFgsm {        // inputs: x, g
         return minn(maxn(a[0][k] + alpha_signed * sgnf(a[1][k]), lo), hi);
     }
 };
+struct FAddClamp {    // inputs: x, noise -- the random start x = clamp(x + U(-eps,eps), 0, 1) of utils/attacks.py:15-17
+    float lo, hi;
+    __device__ __forceinline__ float operator()(const float (&a)[5][4], int k) const { return minn(maxn(a[0][k] + a[1][k], lo), hi); }
+};
 struct FCwLinf {      // inputs: adv, g, x, min_x, max_x
     float step, magnitude;
     __device__ __forceinline__ float operator()(const float (&a)[5][4], int k) const {
@@ -140,6 +144,29 @@ __global__ void __launch_bounds__(256) free_at_kernel(float* __restrict__ delta,
         const float d = upd(delta[i], g[i]);
         delta[i] = d;
         if (x_adv) x_adv[i] = adv(x0[i], d);
+    }
+}
+
+// AVmixup vertex + mix (utils/attacks.py:469-478): vertex = clamp(inputs + (x_adv - inputs)*gamma, 0, 1) in fp32, then
+// out = float(inputs*w_b + vertex*(1 - w_b)) evaluated in DOUBLE like the reference (its per-sample weight is a float64
+// tensor, so torch promotes the whole mix to float64 before the final .to(torch.float)).  One pass: 12 B/element
+// instead of ~9 eager kernels, three of them over float64 temporaries.
+__global__ void __launch_bounds__(256) avmixup_mix_kernel(const float* __restrict__ x_adv, const float* __restrict__ inputs,
+                                                          const double* __restrict__ weight, float* __restrict__ out,
+                                                          int64_t n, int64_t n_per, int vec_ok, float gamma) {
+    auto mix = [&](float xa, float in, double w) {
+        const float vertex = minn(maxn(in + (xa - in) * gamma, 0.0f), 1.0f);
+        return (float)((double)in * w + (double)vertex * (1.0 - w));
+    };
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
+    if (vec_ok) {                                         // n_per % 4 == 0: a float4 never straddles two samples
+        for (int64_t i = tid; i < (n >> 2); i += nthreads) {
+            const double w = __ldg(weight + (i << 2) / n_per);
+            const float4 a = __ldcs(reinterpret_cast<const float4*>(x_adv) + i), c = __ldcs(reinterpret_cast<const float4*>(inputs) + i);
+            __stcs(reinterpret_cast<float4*>(out) + i, make_float4(mix(a.x, c.x, w), mix(a.y, c.y, w), mix(a.z, c.z, w), mix(a.w, c.w, w)));
+        }
+    } else {
+        for (int64_t i = tid; i < n; i += nthreads) out[i] = mix(x_adv[i], inputs[i], weight[i / n_per]);
     }
 }
 

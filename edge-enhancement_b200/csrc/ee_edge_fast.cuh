@@ -20,6 +20,9 @@
 //     (ee_capi.cu: largest fp32 u with sqrtf(u) <= thr).  sqrt is only evaluated in the backward,
 //     on the ~5 % of pixels that carry gradient.
 #pragma once
+#include <cuda.h>
+#include <cuda/barrier>
+
 #include <type_traits>
 
 #include "ee_edge_step125.cuh"
@@ -40,6 +43,7 @@ struct FastArgs {
     int TW;           // columns per tile (multiple of 4; == W for a single column tile)
     int tiles_x;      // column tiles per image
     int halo;         // plane halo columns on each side of a column tile (4, or 8 for the Canny backward)
+    alignas(64) CUtensorMap x_map;   // TMA-staged kernels only: x as a [B*C, H, W] tensor, box = (plane width + 8) x rows x 1
 };
 
 // (sgx, sgy)[4] / C, value-identical to the IEEE division.  DIVM: 0 -> C == 1, 1 -> C == 3, 2 -> any C.
@@ -715,9 +719,16 @@ __device__ __forceinline__ void bwd_abv_row(const FastArgs& a, const float (&Du)
 // backward.  smem regions (stride Wp): R1 = S then A (TH+8 rows), R2 = Bl then GB (TH+6), R3 = Bv (TH+4);
 // a region never needs more rows than the image has (halo rows are clipped), so each is min(TH+k, H) rows
 // -------------------------------------------------------------------------------------------
-template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false, int HT = 0>
-__global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const FastArgs a) {
-    extern __shared__ __align__(16) float smem[];
+// TMA (whole-image tiles, C = 3, NCHW): the three channel planes of x -- INCLUDING the pad columns, i.e. a box of W + 8
+// columns x H rows starting at column -4 (out-of-bounds columns zero-filled) -- are staged by the TMA engine
+// (cp.async.bulk.tensor.3d, one elected thread, mbarrier completion) straight into the three plane regions, which are
+// all dead at kernel start; the channel sum then runs shared -> shared in place.  Otherwise 128-bit LDGs are summed in
+// registers.
+template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false, int HT = 0, bool TMA = false>
+__global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const __grid_constant__ FastArgs a) {
+    extern __shared__ __align__(128) float smem_bwd125[];        // TMA destinations must be 128-byte aligned
+    float* smem = smem_bwd125;
+    static_assert(!TMA || (HT != 0 && NC == 3 && !NHWC), "TMA staging: whole-image tiles, C = 3, NCHW");
     constexpr int DIVM = (NC == 1) ? 0 : (NC == 3 ? 1 : 2);
     constexpr bool EVEN = (HT != 0);
     static_assert(!EVEN || (WT != 0 && WT == WG && HT % R == 0), "HT needs a single constant-width column tile");
@@ -767,10 +778,44 @@ __global__ void __launch_bounds__(256, EE_MINB_BWD) edge_bwd_step125_fast(const 
 #if EE_L2_PREFETCH_BWD == 1
     prefetch_bwd_operands();
 #endif
-    if (active) fast_stage_sum<NC, R, NHWC, EVEN>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
+    if constexpr (TMA) {
+        namespace cde = cuda::device::experimental;
+#pragma nv_diag_suppress static_var_with_dynamic_init
+        __shared__ cuda::barrier<cuda::thread_scope_block> bar;
+        if (threadIdx.x == 0) {
+            init(&bar, blockDim.x);
+            cde::fence_proxy_async_shared_cta();
+        }
+        __syncthreads();
+        cuda::barrier<cuda::thread_scope_block>::arrival_token tok;
+        if (threadIdx.x == 0) {
+            cde::cp_async_bulk_tensor_3d_global_to_shared(R1, &a.x_map, -kPadL, 0, b * 3 + 0, bar);
+            cde::cp_async_bulk_tensor_3d_global_to_shared(R2, &a.x_map, -kPadL, 0, b * 3 + 1, bar);
+            cde::cp_async_bulk_tensor_3d_global_to_shared(R3, &a.x_map, -kPadL, 0, b * 3 + 2, bar);
+            tok = cuda::device::barrier_arrive_tx(bar, 1, 3u * (uint32_t)(HT * (WT + kPadW) * sizeof(float)));
+        } else {
+            tok = bar.arrive();
+        }
+        prefetch_bwd_operands();    // the x tiles are in flight: ask for base / g_out right behind them
+        bar.wait(std::move(tok));
+        if (active) {
+            const int q0 = ty * R * Wp + kPadL + tx * 4;
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const int q = q0 + i * Wp;
+                const float4 v0 = *reinterpret_cast<const float4*>(R1 + q), v1 = *reinterpret_cast<const float4*>(R2 + q),
+                             v2 = *reinterpret_cast<const float4*>(R3 + q);
+                const float4 sum = f4add(f4add(v0, v1), v2);
+                const float o[4] = {sum.x, sum.y, sum.z, sum.w};
+                st_plane(S + q, o, tx == 0, tx == geo.GX - 1, o[0], o[3]);
+            }
+        }
+    } else {
+        if (active) fast_stage_sum<NC, R, NHWC, EVEN>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
 #if EE_L2_PREFETCH_BWD == 2
-    prefetch_bwd_operands();        // after the x loads are issued, so they do not compete with them
+        prefetch_bwd_operands();        // after the x loads are issued, so they do not compete with them
 #endif
+    }
     __syncthreads();
     if (active) fast_stage_blur<R, EVEN>(a, geo, S, s_lo, Bl, b_lo, b_hi, tx, ty);
     __syncthreads();

@@ -10,14 +10,24 @@
 //   * there are no chunk loops and no "is this row inside my chunk" guards (as in the HT-specialised kernels),
 //   * an image border (replicate rows, ring-row fold of the adjoint) can only coincide with a chunk border.
 // Replaces the guarded strip path of ee_edge_fast.cuh for these shapes (same bits: tests/test_gpu_parity.py).
+//
+// TMA = true (C == 3): the three channel tiles of x -- the plane INCLUDING its pad columns, i.e. a box of PW + 8
+// columns x TH + 8 rows starting at column cs - 4 -- are staged by the TMA engine (cp.async.bulk.tensor.3d over a
+// [B*C, H, W] tensor map, out-of-bounds columns zero-filled) straight into the three plane regions, one elected
+// thread issuing the copies and everybody waiting on an mbarrier; the channel sum then runs shared -> shared in
+// place.  TMA = false: 128-bit LDGs summed in registers (the TMA engine cannot add channels in flight).
 #pragma once
+#include <cuda.h>
+#include <cuda/barrier>
+
 #include "ee_edge_fast.cuh"
 
 namespace ee {
 
-template <int NC, bool BLEND, int R, int PW>
-__global__ void __launch_bounds__(256, 3) edge_bwd_step125_tiles(const FastArgs a) {
-    extern __shared__ __align__(16) float smem[];
+template <int NC, bool BLEND, int R, int PW, bool TMA = false>
+__global__ void __launch_bounds__(256, 3) edge_bwd_step125_tiles(const FastArgs a, const __grid_constant__ CUtensorMap x_map) {
+    extern __shared__ __align__(128) float smem_tiles[];       // TMA destinations must be 128-byte aligned
+    float* smem = smem_tiles;
     constexpr int DIVM = (NC == 1) ? 0 : (NC == 3 ? 1 : 2);
     constexpr int Wp = PW + kPadW, GXT = PW / 4;               // plane row stride; thread columns (16 for PW = 64)
     static_assert(R == 4 && PW % 4 == 0 && (256 % GXT) == 0, "16 x 16 chunks of 4 x 4 pixels");
@@ -46,7 +56,40 @@ __global__ void __launch_bounds__(256, 3) edge_bwd_step125_tiles(const FastArgs 
     auto prow = [&](int r) { return (min(max(r, a_lo), a_hi - 1) - a_lo) * Wp + kPadL + lc; };   // clamped plane row
 
     // ---- stage 0: S = channel sum of the plane rows (pad columns: replicate; only meaningful at image edges) -----
-    if (active) {
+    if constexpr (TMA) {
+        static_assert(!TMA || NC == 3, "the TMA staging path is built for C = 3");
+        namespace cde = cuda::device::experimental;
+#pragma nv_diag_suppress static_var_with_dynamic_init
+        __shared__ cuda::barrier<cuda::thread_scope_block> bar;
+        if (threadIdx.x == 0) {
+            init(&bar, 256);
+            cde::fence_proxy_async_shared_cta();
+        }
+        __syncthreads();
+        cuda::barrier<cuda::thread_scope_block>::arrival_token tok;
+        if (threadIdx.x == 0) {
+            // box = (PW + 8) columns x (TH + 8) rows x 1 plane; column cs - 4 lands on plane offset 0, so image column cs
+            // sits at kPadL and the pad columns hold the real neighbours (zeros outside the image)
+            cde::cp_async_bulk_tensor_3d_global_to_shared(R1, &x_map, cs - kPadL, a_lo, b * 3 + 0, bar);
+            cde::cp_async_bulk_tensor_3d_global_to_shared(R2, &x_map, cs - kPadL, a_lo, b * 3 + 1, bar);
+            cde::cp_async_bulk_tensor_3d_global_to_shared(R3, &x_map, cs - kPadL, a_lo, b * 3 + 2, bar);
+            tok = cuda::device::barrier_arrive_tx(bar, 1, 3u * (uint32_t)((a.e.TH + 8) * Wp * sizeof(float)));
+        } else {
+            tok = bar.arrive();
+        }
+        bar.wait(std::move(tok));
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const int q = prow(ra + i);
+                const float4 v0 = *reinterpret_cast<const float4*>(R1 + q), v1 = *reinterpret_cast<const float4*>(R2 + q),
+                             v2 = *reinterpret_cast<const float4*>(R3 + q);
+                const float4 sum = f4add(f4add(v0, v1), v2);
+                const float o[4] = {sum.x, sum.y, sum.z, sum.w};
+                st_plane(R1 + q, o, p_left, p_right, o[0], o[3]);
+            }
+        }
+    } else if (active) {
         const float* px = a.e.x + (size_t)b * C * hw + (size_t)ra * W + col;
         float4 acc[R];
         if (NC == 3) {

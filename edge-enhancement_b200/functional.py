@@ -249,6 +249,33 @@ def free_at_step_(delta, grad, x0=None, alpha=0.0, eps=0.0, lo=0.0, hi=1.0, want
     return x_adv
 
 
+def add_clamp(x, noise, lo=0.0, hi=1.0, out=None):
+    """clamp(x + noise, lo, hi): the random start of the attacks (utils/attacks.py:15-17) in one pass."""
+    x, noise = _same(x, noise)
+    out = _out_like(x, out)
+    if x.numel():
+        with _on_device(x):
+            rc = _lib.load().ee_add_clamp_f32(_ptr(x), _ptr(noise), _ptr(out), x.numel(), float(lo), float(hi), _stream(x))
+        _lib.check(rc, "ee_add_clamp_f32")
+    return out
+
+
+def avmixup_mix(x_adv, inputs, weight, gamma):
+    """AVmixup vertex + mix (utils/attacks.py:469-471, :476): weight is the float64 per-sample tensor ([B] or [B,1,1,1])."""
+    x_adv, inputs = _same(x_adv, inputs)
+    B = x_adv.shape[0]
+    if not (isinstance(weight, torch.Tensor) and weight.is_cuda and weight.dtype == torch.float64 and weight.numel() == B):
+        raise ValueError("edge_b200: avmixup weight must be a float64 CUDA tensor with one entry per sample")
+    weight = weight.reshape(B).contiguous()
+    out = torch.empty_like(x_adv)
+    if x_adv.numel():
+        with _on_device(x_adv):
+            rc = _lib.load().ee_avmixup_mix_f32(_ptr(x_adv), _ptr(inputs), weight.data_ptr(), _ptr(out), B,
+                                                x_adv.numel() // B, float(gamma), _stream(x_adv))
+        _lib.check(rc, "ee_avmixup_mix_f32")
+    return out
+
+
 def cw_linf_step(adv, grad, x, min_x, max_x, step, magnitude, out=None):
     adv, grad, x, min_x, max_x = _same(adv, grad, x, min_x, max_x)
     out = _out_like(adv, out)

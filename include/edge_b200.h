@@ -123,6 +123,16 @@ int ee_cw_linf_step_f32(const float* adv, const float* g, const float* x, const 
                         const float* max_x, float* out, int64_t n, float step, float magnitude,
                         void* stream);
 
+/* out = clamp(x + noise, lo, hi): the random start of every attack, replaces utils/attacks.py:15-17 (:45-47, :74-77,
+ * :454-456, :495-497); the noise itself stays a torch uniform_ draw so that a seeded run follows the reference. */
+int ee_add_clamp_f32(const float* x, const float* noise, float* out, int64_t n, float lo, float hi, void* stream);
+
+/* AVmixup vertex + mix, replaces utils/attacks.py:469-471 + :476 (and :508-510 + :515):
+ * vertex = clamp(inputs + (x_adv - inputs)*gamma, 0, 1) (fp32); out = float(inputs*w_b + vertex*(1 - w_b)) evaluated in
+ * double, w = the reference's float64 np.random.beta weights, one per sample (device pointer, [B]). */
+int ee_avmixup_mix_f32(const float* x_adv, const float* inputs, const double* weight, float* out, int B,
+                       int64_t n_per_sample, float gamma, void* stream);
+
 /* TRADES PGD-L2 step with per-sample RMS norms, replaces utils/attacks.py:391-399 and
  * l2_norm (:360-366).  One CTA per sample; out must NOT alias x. */
 int ee_pgd_l2_step_f32(const float* x, const float* g, const float* x0, float* out, int B,
@@ -156,7 +166,8 @@ int ee_version(void);            /* EE_VERSION */
 
 /* Tuning knob for benchmarks/tests: force the row-strip height of the tiled edge kernels
  * (0 = heuristic) and the staging path (0 = auto, 1 = generic kernels only, 4 = tuned kernels even for wide images,
- * 5 = experimental thread-block-cluster backward for 3x224x224).
+ * 3 = strip kernels instead of chunk-aligned tiles for wide images, 5 = experimental thread-block-cluster backward
+ * for 3x224x224, 6 = always stage the x tiles of wide images by TMA tensor copies, 7 = never use TMA staging).
  * Process-wide; returns EE_OK.  Not needed for normal use. */
 int ee_set_tuning(int strip_rows_fwd, int strip_rows_bwd, int staging);
 

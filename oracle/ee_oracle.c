@@ -638,6 +638,30 @@ void ee_oracle_safe_sign_fwd(const float *in, float *out, int64_t n)
 void ee_oracle_safe_sign_bwd(const float *g, const float *in, float *out, int64_t n)
 { for (int64_t i = 0; i < n; ++i) out[i] = (fabsf(in[i]) > 1.001f) ? 0.0f : g[i]; }
 
+/* random start, attacks.py:15-17: x = clamp(x + noise, lo, hi) (the uniform noise is an input) */
+void ee_oracle_add_clamp(const float *x, const float *noise, float *out, int64_t n, float lo, float hi)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) out[i] = minn(maxn(x[i] + noise[i], lo), hi);
+}
+
+/* AVmixup vertex + mix, attacks.py:469-471 and :476: perturb = (x - inputs)*gamma; vertex = clamp(inputs + perturb, 0, 1)
+ * in fp32; the mix inputs*w + vertex*(1 - w) runs in float64 (w is a float64 tensor, torch promotes) and is cast back
+ * to float at :478. */
+void ee_oracle_avmixup_mix(const float *x_adv, const float *inputs, const double *weight, float *out, int B,
+                           int64_t n_per, float gamma)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)B * n_per; ++i) {
+        const double w = weight[i / n_per];
+        const float in = inputs[i];
+        const float perturb = (x_adv[i] - in) * gamma;
+        const float vertex = minn(maxn(in + perturb, 0.0f), 1.0f);
+        const double a = (double)in * w, b = (double)vertex * (1.0 - w);
+        out[i] = (float)(a + b);
+    }
+}
+
 /* ------------------------------------------------------------------------------------
  * Add_Square, utils/core.py:640-655.  The random draws are inputs:
  * stripe[B,C,W] = sign(2*rand-1) of :641, table[n_sq][2+C] = {vh, s, 2*eps*sign_c...} of :646-650.

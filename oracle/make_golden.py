@@ -137,6 +137,24 @@ def run_attack_cases(rc, ra):
         print("pgd10_%s: mean |x_adv - x| = %.4f" % (variant, (xadv - torch.from_numpy(x)).abs().mean()))
 
 
+def run_attack_extras():
+    """The torch expressions of the attack-loop host side, evaluated on CPU exactly as the
+    reference writes them: random start (attacks.py:15-17) and the AVmixup vertex / mix (attacks.py:469-478)."""
+    eps, gamma = 16 / 255, 2.0
+    x, _, x0 = T.make_attack_inputs(601, (6, 3, 8, 8), eps)
+    tx, tx0 = torch.from_numpy(x), torch.from_numpy(x0)
+    torch.manual_seed(601)
+    noise = torch.zeros_like(tx0).uniform_(-eps, eps)
+    start = torch.clamp(tx0 + noise, 0, 1)
+    x_weight = np.random.default_rng(602).beta(1.0, 1.0, [x.shape[0], 1, 1, 1])
+    perturb = (tx - tx0) * gamma
+    vertex = torch.clamp(tx0 + perturb, 0, 1)
+    w = torch.from_numpy(x_weight)
+    mixed = (tx0 * w + vertex * (1 - w)).to(torch.float)
+    np.savez_compressed(os.path.join(OUT, "attack_extras.npz"), x=x, x0=x0, noise=noise.numpy(), start=start.numpy(),
+                        weight=x_weight, mixed=mixed.numpy(), gamma=np.array(gamma), eps=np.array(eps))
+
+
 def run_add_square_cases(rc):
     """Add_Square (utils/core.py:589-655) hard-codes .cuda(); on this CPU-only container Tensor.cuda is patched to
     the identity for the duration of the call, nothing else of the reference is touched.  The fixture stores the
@@ -186,6 +204,7 @@ def main():
         run_edge_case(rc, case)
     run_attack_cases(rc, ra)
     run_add_square_cases(rc)
+    run_attack_extras()
     print("fixtures written to", OUT)
 
 

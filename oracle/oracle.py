@@ -87,6 +87,10 @@ def lib():
     L.ee_oracle_cw_linf_step.restype = None
     L.ee_oracle_pgd_l2_step.argtypes = [fp, fp, fp, fp, i, i64, f, f]
     L.ee_oracle_pgd_l2_step.restype = None
+    L.ee_oracle_add_clamp.argtypes = [fp, fp, fp, i64, f, f]
+    L.ee_oracle_add_clamp.restype = None
+    L.ee_oracle_avmixup_mix.argtypes = [fp, fp, ctypes.POINTER(ctypes.c_double), fp, i, i64, f]
+    L.ee_oracle_avmixup_mix.restype = None
     L.ee_oracle_add_square.argtypes = [fp, fp, fp, fp, fp, i, i, i, i, i, f]
     L.ee_oracle_add_square.restype = None
     for name in ("to_compare",):
@@ -190,6 +194,23 @@ def pgd_l2_step(x, g, x0, step, eps):
     out = np.empty_like(x)
     B = x.shape[0]
     lib().ee_oracle_pgd_l2_step(_p(x), _p(g), _p(x0), _p(out), B, x.size // B, step, eps)
+    return out
+
+
+def add_clamp(x, noise, lo=0.0, hi=1.0):
+    x, noise = _f32(x), _f32(noise)
+    out = np.empty_like(x)
+    lib().ee_oracle_add_clamp(_p(x), _p(noise), _p(out), x.size, lo, hi)
+    return out
+
+
+def avmixup_mix(x_adv, inputs, weight, gamma):
+    x_adv, inputs = _f32(x_adv), _f32(inputs)
+    w = np.ascontiguousarray(weight, dtype=np.float64).reshape(-1)
+    B = x_adv.shape[0]
+    out = np.empty_like(x_adv)
+    lib().ee_oracle_avmixup_mix(_p(x_adv), _p(inputs), w.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), _p(out), B,
+                                x_adv.size // B, float(np.float32(gamma)))
     return out
 
 

@@ -125,3 +125,20 @@ def test_full_pgd10_against_reference_run(variant):
     assert bad.mean() < 0.01, "%.3f %% of the adversarial example differs" % (100 * bad.mean())
     unexplained = bad & ~ambiguous
     assert unexplained.sum() <= 0.002 * bad.size, "%d differing elements are not sign-ambiguous" % unexplained.sum()
+
+
+def test_attack_extras_fixture():
+    """random start and AVmixup vertex / mix: CUDA kernels vs the reference's torch expressions (bit-exact)"""
+    z = np.load(os.path.join(GOLD, "attack_extras.npz"))
+    start = F_ee.add_clamp(cu(z["x0"]), cu(z["noise"]))
+    assert np.array_equal(start.cpu().numpy(), z["start"])
+    w = torch.from_numpy(z["weight"]).to(DEV)
+    mixed = F_ee.avmixup_mix(cu(z["x"]), cu(z["x0"]), w, float(z["gamma"]))
+    assert np.array_equal(mixed.cpu().numpy(), z["mixed"])
+    # the same numbers through the drop-in attack helper: seeded torch generator -> same noise as the reference draw
+    torch.manual_seed(601)
+    x0 = cu(z["x0"])
+    ref_noise = torch.zeros_like(x0).uniform_(-float(z["eps"]), float(z["eps"]))
+    torch.manual_seed(601)
+    got = attacks._random_start(x0, float(z["eps"]))
+    assert torch.equal(got, torch.clamp(x0 + ref_noise, 0, 1))

@@ -60,8 +60,8 @@ VARIANT_MODES = [("step125", "hyst")] + [(v, m) for v in ("canny", "bpda") for m
 
 
 # staging knob of ee_set_tuning: 0 = auto, 1 = generic kernels only, 3 = strip kernels instead of the chunk-aligned
-# tiles for wide images, 4 = tuned kernels also for wide images
-@pytest.mark.parametrize("staging", [0, 1, 3, 4])
+# tiles for wide images, 4 = tuned kernels also for wide images, 6 / 7 = always / never stage x tiles by TMA tensor copies
+@pytest.mark.parametrize("staging", [0, 1, 3, 4, 6, 7])
 @pytest.mark.parametrize("strip", [0, 1, 3, 7])
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("variant,mode", VARIANT_MODES)
@@ -140,12 +140,12 @@ def test_only_g_base_requested():
 def test_cluster_backward_224():
     """ImageNet size: the default chunk-aligned tile backward (ee_edge_tiles.cuh), the older strip kernels (staging 3)
     and the opt-in thread-block-cluster backward (8 CTAs x 28 rows, halo rows through distributed shared memory,
-    ee_edge_cluster.cuh; staging 5) all give the oracle's bits, also when only one of the two gradients is requested."""
+    ee_edge_cluster.cuh; staging 5) and the TMA-staged tiles (staging 6) all give the oracle's bits, also when only one of the two gradients is requested."""
     x, base, g_out, g_edge = T.make_inputs(224, 3, 3, 224, 224)
     pc, po = both_params("step125", 0.02, None, T.HIGH, False)
     L = _lib.load()
     o_gx, o_gb = O.edge_blend_bwd(g_out, x, base, po, 1.0)
-    for staging in (0, 3, 5):
+    for staging in (0, 3, 5, 6, 7):
         L.ee_set_tuning(0, 0, staging)
         g_x, g_base = F_ee.edge_blend_backward(cu(g_out), cu(x), cu(base), pc, 1.0)
         assert_same("g_base", g_base, o_gb)

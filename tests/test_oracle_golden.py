@@ -138,3 +138,10 @@ def test_add_square_oracle_matches_reference_fixture(path):
         np.testing.assert_allclose(g_x, z["g_x"], rtol=2e-7, atol=0)
     # properties: inside the eps ball and [0, 1]
     assert (np.abs(out - z["x"]) <= np.float32(eps) + 1e-7).all() and out.min() >= 0.0 and out.max() <= 1.0
+
+
+def test_attack_extras_bit_exact():
+    """random start (attacks.py:15-17) and AVmixup vertex / float64 mix (attacks.py:469-478)"""
+    z = np.load(os.path.join(GOLD, "attack_extras.npz"))
+    assert np.array_equal(O.add_clamp(z["x0"], z["noise"]), z["start"])
+    assert np.array_equal(O.avmixup_mix(z["x"], z["x0"], z["weight"], float(z["gamma"])), z["mixed"])
