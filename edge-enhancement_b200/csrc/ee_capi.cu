@@ -6,6 +6,7 @@
 #include "ee_edge_canny_fast.cuh"
 #include "ee_edge_cluster.cuh"
 #include "ee_edge_tiles.cuh"
+#include "ee_edge_canny_tiles.cuh"
 #include "ee_edge_fast.cuh"
 #include "ee_edge_step125.cuh"
 #include "ee_square.cuh"
@@ -211,16 +212,22 @@ int launch_cluster(K kernel, int W, int TH, int CS, int B, const ee::EdgeArgs& e
     return EE_OK;
 }
 
+bool fast_eligible(const ee::EdgeArgs& a, bool vec_ok);
+
 // Chunk-aligned tiles for wide images (ee_edge_tiles.cuh): <= 56 x 56 outputs per CTA, 64 x 64 planes, 16 x 16 chunks.
-void plan_tiles(int H, int W, Launch& L) {
-    int ty = (H + 55) / 56, tx = (W + 55) / 56;
+void plan_tiles(int H, int W, Launch& L, int max_tile = 56, int planes = 3) {
+    int ty = (H + max_tile - 1) / max_tile, tx = (W + max_tile - 1) / max_tile;
     L.TH = (((H + ty - 1) / ty) + 3) & ~3;
     L.TW = (((W + tx - 1) / tx) + 3) & ~3;
     ty = (H + L.TH - 1) / L.TH;
     L.tiles_x = (W + L.TW - 1) / L.TW;
     L.tiles = ty * L.tiles_x;
     L.vec = 4; L.planeW = 64; L.halo = 4; L.GX = 16; L.RY = 16; L.threads = 256;
-    L.smem = (size_t)3 * (L.TH + 8) * (64 + ee::kPadW) * sizeof(float);
+    L.smem = (size_t)planes * (L.TH + (64 - max_tile)) * (64 + ee::kPadW) * sizeof(float);
+}
+bool canny_tiles_ok(const ee::EdgeArgs& a, bool vec_ok, int th_forced) {
+    return fast_eligible(a, vec_ok) && a.W > 128 && a.H % 4 == 0 && a.H >= 16 && th_forced == 0 && g_staging.load() != 3 &&
+           a.has_low && a.has_high && a.hyst;
 }
 
 // Tensor map of x as [B*C, H, W] fp32 with a (64 + 8) x (TH + 8) x 1 box for the TMA-staged tile kernel.  The driver
@@ -441,6 +448,17 @@ int edge_forward(const float* x, const float* base, float* out, float* edge, int
         if (blend) EE_DISPATCH(ee::edge_fwd_step125_kernel, true, L, B, a, s, "edge_fwd_step125");
         else EE_DISPATCH(ee::edge_fwd_step125_kernel, false, L, B, a, s, "edge_fwd_step125");
     }
+    if (canny_tiles_ok(a, vec_ok, g_th_fwd.load())) {
+        // wide images, hysteresis mode: chunk-aligned 56 x 56 tiles (ee_edge_canny_tiles.cuh)
+        plan_tiles(H, W, L, 56, 3);
+        ee::FastArgs f;
+        fill_fast(f, a, L);
+        const bool cn = (p->variant == EE_VARIANT_CANNY);
+        if (C == 3 && blend) return cn ? launch_fast(ee::edge_fwd_canny_tiles<3, true, 4, 64, 1>, L, B, f, s, "edge_fwd_canny_tiles")
+                                       : launch_fast(ee::edge_fwd_canny_tiles<3, true, 4, 64, 2>, L, B, f, s, "edge_fwd_canny_tiles");
+        if (blend) return launch_fast(ee::edge_fwd_canny_tiles<0, true, 4, 64, 0>, L, B, f, s, "edge_fwd_canny_tiles");
+        return launch_fast(ee::edge_fwd_canny_tiles<0, false, 4, 64, 0>, L, B, f, s, "edge_fwd_canny_tiles");
+    }
     if (fast_eligible(a, vec_ok)) {
         rc = plan_fast(H, W, 4, ee::kCannyFastFwdRowsPerTH, ee::kCannyFastFwdRowsFixed, 8, 62 * 1024, g_th_fwd.load(), L);
         if (rc) return rc;
@@ -542,6 +560,17 @@ int edge_backward(const float* g_in, const float* x, const float* base, float* g
         a.TH = L.TH; a.tiles_per_img = L.tiles; a.GX = L.GX; a.RY = L.RY;
         if (blend) EE_DISPATCH(ee::edge_bwd_step125_kernel, true, L, B, a, s, "edge_bwd_step125");
         else EE_DISPATCH(ee::edge_bwd_step125_kernel, false, L, B, a, s, "edge_bwd_step125");
+    }
+    if (canny_tiles_ok(a, vec_ok, g_th_bwd.load())) {
+        // wide images, hysteresis mode: chunk-aligned 48 x 48 tiles with an 8-pixel halo (ee_edge_canny_tiles.cuh)
+        plan_tiles(H, W, L, 48, 4);
+        ee::FastArgs f;
+        fill_fast(f, a, L);
+        const bool cn = (p->variant == EE_VARIANT_CANNY);
+        if (C == 3 && blend) return cn ? launch_fast(ee::edge_bwd_canny_tiles<3, true, 4, 64, 1>, L, B, f, s, "edge_bwd_canny_tiles")
+                                       : launch_fast(ee::edge_bwd_canny_tiles<3, true, 4, 64, 2>, L, B, f, s, "edge_bwd_canny_tiles");
+        if (blend) return launch_fast(ee::edge_bwd_canny_tiles<0, true, 4, 64, 0>, L, B, f, s, "edge_bwd_canny_tiles");
+        return launch_fast(ee::edge_bwd_canny_tiles<0, false, 4, 64, 0>, L, B, f, s, "edge_bwd_canny_tiles");
     }
     if (fast_eligible(a, vec_ok)) {
         rc = plan_fast(H, W, 4, ee::kCannyFastBwdRowsPerTH, ee::kCannyFastBwdRowsFixed, 12, 104 * 1024, g_th_bwd.load(), L, 8, 128, 48);
