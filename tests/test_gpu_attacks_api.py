@@ -202,3 +202,33 @@ def test_model_level_gradients_match_unfused_torch_path(setup):
     h = F.relu(model.conv(z)).mean((2, 3))
     g2 = torch.autograd.grad(F.cross_entropy(model.fc(h), y), [x2])[0]
     assert torch.allclose(g1, g2, rtol=1e-5, atol=1e-7 * float(g2.abs().max()))
+
+
+def test_graphed_pgd_matches_eager_pgd():
+    """attacks.GraphedPGD (one captured iteration replayed num_steps times) returns exactly what attacks.PGD returns:
+    same kernels, same order, only the launches come from a CUDA graph."""
+    import contextlib, io
+    B, C, S, n_class = 64, 3, 32, 10
+    gen = torch.Generator(device=DEV).manual_seed(21)
+    x = torch.rand((B, C, S, S), device=DEV, generator=gen)
+    y = torch.randint(0, n_class, (B,), device=DEV, generator=gen)
+    with contextlib.redirect_stdout(io.StringIO()):
+        canny = core.CannyFilter_step125_1(use_cuda=False, alpha=0.0)
+    weight = torch.randn((n_class, C * S * S), device=DEV, generator=gen) * 0.05
+
+    def model(inp):
+        z = core.edge_enhance(inp, inp, canny, 1.0, None, 76 / 255, True)
+        return z.reshape(z.shape[0], -1) @ weight.t()
+
+    class A:
+        random = False
+        epsilon = 16 / 255
+
+    want = attacks.PGD(model, A, x, y, 7, 2 / 255)
+    pgd = attacks.GraphedPGD(model, A, x, y, 2 / 255)
+    got = pgd(x, y, 7)
+    assert torch.equal(got, want)
+    # a second batch through the same captured graph
+    x2 = torch.rand((B, C, S, S), device=DEV, generator=gen)
+    y2 = torch.randint(0, n_class, (B,), device=DEV, generator=gen)
+    assert torch.equal(pgd(x2, y2, 5), attacks.PGD(model, A, x2, y2, 5, 2 / 255))
