@@ -26,11 +26,16 @@ def build(force=False, verbose=False):
     return _build.build(force=force, verbose=verbose)
 
 
-def install(package="utils"):
+def install(package="utils", shims=False):
     """Make ``from utils.core import CannyFilter`` / ``from utils.attacks import PGD`` (the imports
     at the top of every reference experiment script) resolve to this package's drop-ins.  Other
-    ``utils.*`` modules (helper, data_loader, ...) keep resolving to the reference's own files."""
+    ``utils.*`` modules (helper, data_loader, ...) keep resolving to the reference's own files.
+    shims=True additionally registers stand-ins for the scripts' small third-party imports
+    (easydict, managpu, autoattack) when those are not installed (compat.py)."""
     import importlib
+    if shims:
+        from . import compat
+        compat.install_shims()
     try:
         pkg = importlib.import_module(package)
     except ImportError:

@@ -177,3 +177,55 @@ def test_high_freq_suppress_restatement():
     if ref_loader.available():
         rc, _ = ref_loader.load()
         assert torch.equal(rc.HighFreqSuppress(64, 64, 8).temp, core.HighFreqSuppress(64, 64, 8).temp)
+
+
+def test_compat_shims():
+    from edge_enhancement_b200 import compat
+    d = compat.EasyDict({"a": 1, "b": {"c": [1, {"d": 2}]}})
+    assert d.a == 1 and d.b.c[1].d == 2 and d["b"]["c"][0] == 1
+    d.e = {"f": 3}
+    assert d.e.f == 3 and d["e"]["f"] == 3
+    with pytest.raises(AttributeError):
+        d.missing
+    assert compat.GpuManager().set_by_memory(1) in ([], [0])
+    with pytest.raises(RuntimeError):
+        compat.AutoAttack(None, norm="Linf").run_standard_evaluation(None, None)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference checkout not present")
+def test_reference_scripts_import_on_top_of_the_dropins():
+    """with install(shims=True) the reference's own experiment scripts import unmodified
+    (their module-level code runs: argparse helpers, GpuManager().set_by_memory(1), `from models_* import *`) and the
+    names they pulled from utils.core / utils.attacks are this package's drop-ins."""
+    import importlib
+    root = ref_loader.REFERENCE_ROOT
+    saved_mods = dict(sys.modules)
+    saved_path = list(sys.path)
+    try:
+        for k in list(sys.modules):
+            if k == "utils" or k.startswith("utils."):
+                del sys.modules[k]
+        shim = __import__("types").ModuleType("torch._six")
+        shim.builtins = __import__("builtins")
+        sys.modules.setdefault("torch._six", shim)             # utils/u2net -> nothing; utils/_jit_internal is no longer imported
+        sys.path.insert(0, root)
+        ee.install("utils", shims=True)
+        for sub, script, names in (("MNIST", "experiments_mnist", ["PGD", "FGSM", "Trades", "AVmixup"]),
+                                   ("Tiny_ImageNet", "experiments_tinyimagenet", ["PGD", "targeted_PGD", "Add_Square"]),
+                                   ("ImageNet", "experiments_imagenet", ["PGD", "targeted_PGD_trick", "tar_alp_imagenet"])):
+            sys.path.insert(0, os.path.join(root, sub))
+            try:
+                with contextlib.redirect_stdout(io.StringIO()):
+                    mod = importlib.import_module(script)
+            finally:
+                sys.path.remove(os.path.join(root, sub))
+            for n in names:
+                ours = getattr(attacks, n, None) or getattr(core, n)
+                assert getattr(mod, n) is ours, (script, n)
+            assert mod.parse_config_file.__module__ == "utils.helper"          # the reference's own helper stays in use
+    finally:
+        sys.path[:] = saved_path
+        for k in list(sys.modules):
+            if k not in saved_mods:
+                del sys.modules[k]
+        sys.modules.update(saved_mods)
