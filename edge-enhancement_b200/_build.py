@@ -38,14 +38,34 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+PARTS = (1, 2, 3, 4, 5)      # ee_capi.cu is compiled once per kernel family (-DEE_PART=k), in parallel, then linked
+
+
 def build(force=False, verbose=False, extra_flags=()):
     """Compile if missing or older than its sources.  Returns the path of the .so."""
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = _nvcc()
+    objdir = os.path.join(PKG, "build")
+    os.makedirs(objdir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags)
+    src = os.path.join(CSRC, SOURCES[0])
+
+    def compile_part(k):
+        obj = os.path.join(objdir, "ee_part%d.o" % k)
+        cmd = [nvcc] + compile_flags + ["-DEE_PART=%d" % k, "-c", src, "-o", obj]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(PARTS), os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_part, PARTS))
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"] + objs + ["-o", LIB]
     if verbose:
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
+        print(" ".join(link), flush=True)
+    subprocess.check_call(link)
     return LIB
 
 

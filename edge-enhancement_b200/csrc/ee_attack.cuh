@@ -101,7 +101,7 @@ struct FSafeSignFwd { __device__ __forceinline__ float operator()(const float (&
 struct FSafeSignBwd { __device__ __forceinline__ float operator()(const float (&a)[5][4], int k) const { return (fabsf(a[1][k]) > 1.001f) ? 0.0f : a[0][k]; } };
 
 // free / fast-AT: two outputs (delta in place, x_adv), so it has its own kernel.
-__global__ void __launch_bounds__(256) free_at_kernel(float* __restrict__ delta, const float* __restrict__ g,
+static __global__ void __launch_bounds__(256) free_at_kernel(float* __restrict__ delta, const float* __restrict__ g,
                                                       const float* __restrict__ x0, float* __restrict__ x_adv,
                                                       int64_t n, int vec_ok, float alpha, float eps, float lo, float hi) {
     constexpr int UNROLL = 4;
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) free_at_kernel(float* __restrict__ delta,
 // out = float(inputs*w_b + vertex*(1 - w_b)) evaluated in DOUBLE like the reference (its per-sample weight is a float64
 // tensor, so torch promotes the whole mix to float64 before the final .to(torch.float)).  One pass: 12 B/element
 // instead of ~9 eager kernels, three of them over float64 temporaries.
-__global__ void __launch_bounds__(256) avmixup_mix_kernel(const float* __restrict__ x_adv, const float* __restrict__ inputs,
+static __global__ void __launch_bounds__(256) avmixup_mix_kernel(const float* __restrict__ x_adv, const float* __restrict__ inputs,
                                                           const double* __restrict__ weight, float* __restrict__ out,
                                                           int64_t n, int64_t n_per, int vec_ok, float gamma) {
     auto mix = [&](float xa, float in, double w) {
@@ -189,7 +189,7 @@ __device__ __forceinline__ float block_sum_1024(float v, float* sh) {
     return __shfl_sync(0xffffffffu, t, 0);
 }
 
-__global__ void __launch_bounds__(1024) pgd_l2_kernel(const float* __restrict__ x, const float* __restrict__ g,
+static __global__ void __launch_bounds__(1024) pgd_l2_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                       const float* __restrict__ x0, float* __restrict__ out,
                                                       int64_t n_per, float step, float eps) {
     __shared__ float sh[32];

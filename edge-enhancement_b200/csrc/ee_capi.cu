@@ -18,10 +18,34 @@
 #include <cstdlib>
 #include <cstring>
 
-namespace {
+// The library is compiled as five translation units from this one source (edge-enhancement_b200/_build.py, in
+// parallel): -DEE_PART=1 the C ABI + elementwise kernels, 2 / 3 the step125 forward / backward kernel families,
+// 4 / 5 the Canny + BPDA forward / backward families.  EE_PART undefined (0) builds everything in one unit.
+#ifndef EE_PART
+#define EE_PART 0
+#endif
+#define EE_HAS(k) (EE_PART == 0 || EE_PART == (k))
 
+namespace ee_shared {       // process-wide state, defined in part 1
+extern thread_local char g_err[512];
+extern std::atomic<int> g_th_fwd, g_th_bwd, g_staging;
+#if EE_HAS(1)
 thread_local char g_err[512] = "";
 std::atomic<int> g_th_fwd{0}, g_th_bwd{0}, g_staging{0};
+#endif
+// kernel-family dispatchers (one translation unit each)
+int fwd_step125(ee::EdgeArgs& a, const EEParams* p, int B, bool blend, bool vec_ok, bool nhwc, cudaStream_t s);
+int bwd_step125(ee::EdgeArgs& a, const EEParams* p, int B, bool blend, bool vec_ok, bool nhwc, cudaStream_t s);
+int fwd_canny(ee::EdgeArgs& a, const EEParams* p, int B, bool blend, bool vec_ok, bool nhwc, cudaStream_t s);
+int bwd_canny(ee::EdgeArgs& a, const EEParams* p, int B, bool blend, bool vec_ok, bool nhwc, cudaStream_t s);
+}  // namespace ee_shared
+
+namespace {
+
+using ee_shared::g_err;
+using ee_shared::g_th_fwd;
+using ee_shared::g_th_bwd;
+using ee_shared::g_staging;
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -406,34 +430,29 @@ int fill_args(ee::EdgeArgs& a, int B, int C, int H, int W, const EEParams* p, fl
         return launch(KERNEL<1, 0, BLEND>, L, B, a, s, name);                                     \
     } while (0)
 
-int edge_forward(const float* x, const float* base, float* out, float* edge, int B, int C, int H, int W,
-                 const EEParams* p, float w, bool blend, void* stream) {
-    ee::EdgeArgs a;
-    int rc = fill_args(a, B, C, H, W, p, w);
-    if (rc) return rc;
-    if (!x) return fail(EE_ERR_INVALID_ARG, "x is null");
-    if (blend && (!base || !out)) return fail(EE_ERR_INVALID_ARG, "base/out is null");
-    if (!blend && !edge) return fail(EE_ERR_INVALID_ARG, "edge is null");
-    a.x = x; a.base = base; a.out = out; a.edge = edge;
-    const bool vec_ok = (W % 4 == 0) && aligned16(x) && aligned16(base) && aligned16(out) && aligned16(edge);
-    cudaStream_t s = (cudaStream_t)stream;
+#define EE_NHWC_MSG "NHWC needs the fused blend entry point, C == 3, W %% 4 == 0, 16-byte aligned tensors"
+
+}  // namespace
+
+// =================================================================================================
+// kernel-family dispatchers
+// =================================================================================================
+#if EE_HAS(2)
+int ee_shared::fwd_step125(ee::EdgeArgs& a, const EEParams* p, int B, bool blend, bool vec_ok, bool nhwc, cudaStream_t s) {
+    const int C = a.C, H = a.H, W = a.W;
     Launch L;
-    const bool nhwc = (p->layout == EE_LAYOUT_NHWC) && C > 1;       // with one channel the layouts coincide
+    int rc;
     if (nhwc) {
         // channels_last is implemented by the tuned fused kernels for C = 3; anything else must be
         // converted by the caller (the Python wrapper does), never silently mis-read
-        if (!(blend && C == 3 && fast_eligible(a, vec_ok)))
-            return fail(EE_ERR_UNSUPPORTED, "NHWC needs the fused blend entry point, C == 3, W %% 4 == 0, 16-byte aligned tensors");
-        const bool st = (p->variant == EE_VARIANT_STEP125);
-        rc = st ? plan_fast(H, W, 4, 2, 6, 4, 40 * 1024, g_th_fwd.load(), L, 4, 512)
-                : plan_fast(H, W, 4, ee::kCannyFastFwdRowsPerTH, ee::kCannyFastFwdRowsFixed, 8, 62 * 1024, g_th_fwd.load(), L);
+        if (!(blend && C == 3 && fast_eligible(a, vec_ok))) return fail(EE_ERR_UNSUPPORTED, EE_NHWC_MSG);
+        rc = plan_fast(H, W, 4, 2, 6, 4, 40 * 1024, g_th_fwd.load(), L, 4, 512);
         if (rc) return rc;
         ee::FastArgs f;
         fill_fast(f, a, L);
-        if (st) EE_DISPATCH_FAST_NHWC(ee::edge_fwd_step125_fast, L, B, f, s, "edge_fwd_step125_fast_nhwc");
-        else EE_DISPATCH_FAST_NHWC(ee::edge_fwd_canny_fast, L, B, f, s, "edge_fwd_canny_fast_nhwc");
+        EE_DISPATCH_FAST_NHWC(ee::edge_fwd_step125_fast, L, B, f, s, "edge_fwd_step125_fast_nhwc");
     }
-    if (p->variant == EE_VARIANT_STEP125 && fast_eligible(a, vec_ok)) {
+    if (fast_eligible(a, vec_ok)) {
         rc = plan_fast(H, W, 4, 2, 6, 4, 40 * 1024, g_th_fwd.load(), L, 4, 512);
         if (rc) return rc;
         ee::FastArgs f;
@@ -441,12 +460,26 @@ int edge_forward(const float* x, const float* base, float* out, float* edge, int
         if (blend) EE_DISPATCH_FAST(ee::edge_fwd_step125_fast, true, L, B, f, s, "edge_fwd_step125_fast");
         else EE_DISPATCH_FAST(ee::edge_fwd_step125_fast, false, L, B, f, s, "edge_fwd_step125_fast");
     }
-    if (p->variant == EE_VARIANT_STEP125) {
-        rc = plan(H, W, vec_ok, 2, 6, 4, 44 * 1024, g_th_fwd.load(), L);
+    rc = plan(H, W, vec_ok, 2, 6, 4, 44 * 1024, g_th_fwd.load(), L);
+    if (rc) return rc;
+    a.TH = L.TH; a.tiles_per_img = L.tiles; a.GX = L.GX; a.RY = L.RY;
+    if (blend) EE_DISPATCH(ee::edge_fwd_step125_kernel, true, L, B, a, s, "edge_fwd_step125");
+    else EE_DISPATCH(ee::edge_fwd_step125_kernel, false, L, B, a, s, "edge_fwd_step125");
+}
+#endif
+
+#if EE_HAS(4)
+int ee_shared::fwd_canny(ee::EdgeArgs& a, const EEParams* p, int B, bool blend, bool vec_ok, bool nhwc, cudaStream_t s) {
+    const int C = a.C, H = a.H, W = a.W;
+    Launch L;
+    int rc;
+    if (nhwc) {
+        if (!(blend && C == 3 && fast_eligible(a, vec_ok))) return fail(EE_ERR_UNSUPPORTED, EE_NHWC_MSG);
+        rc = plan_fast(H, W, 4, ee::kCannyFastFwdRowsPerTH, ee::kCannyFastFwdRowsFixed, 8, 62 * 1024, g_th_fwd.load(), L);
         if (rc) return rc;
-        a.TH = L.TH; a.tiles_per_img = L.tiles; a.GX = L.GX; a.RY = L.RY;
-        if (blend) EE_DISPATCH(ee::edge_fwd_step125_kernel, true, L, B, a, s, "edge_fwd_step125");
-        else EE_DISPATCH(ee::edge_fwd_step125_kernel, false, L, B, a, s, "edge_fwd_step125");
+        ee::FastArgs f;
+        fill_fast(f, a, L);
+        EE_DISPATCH_FAST_NHWC(ee::edge_fwd_canny_fast, L, B, f, s, "edge_fwd_canny_fast_nhwc");
     }
     if (canny_tiles_ok(a, vec_ok, g_th_fwd.load())) {
         // wide images, hysteresis mode: chunk-aligned 56 x 56 tiles (ee_edge_canny_tiles.cuh)
@@ -483,42 +516,29 @@ int edge_forward(const float* x, const float* base, float* out, float* edge, int
     if (blend) EE_DISPATCH(ee::edge_fwd_canny_kernel, true, L, B, a, s, "edge_fwd_canny");
     else EE_DISPATCH(ee::edge_fwd_canny_kernel, false, L, B, a, s, "edge_fwd_canny");
 }
+#endif
 
-int edge_backward(const float* g_in, const float* x, const float* base, float* g_x, float* g_base, int B, int C,
-                  int H, int W, const EEParams* p, float w, bool blend, void* stream) {
-    ee::EdgeArgs a;
-    int rc = fill_args(a, B, C, H, W, p, w);
-    if (rc) return rc;
-    if (!x || !g_in) return fail(EE_ERR_INVALID_ARG, "x/g is null");
-    if (blend && !base) return fail(EE_ERR_INVALID_ARG, "base is null");
-    if (!blend && !g_x) return fail(EE_ERR_INVALID_ARG, "g_x is null");
-    if (blend && !g_x && !g_base) return EE_OK;   // nothing requested
-    a.x = x; a.base = base; a.g_in = g_in; a.g_x = g_x; a.g_base = g_base;
-    const bool vec_ok = (W % 4 == 0) && aligned16(x) && aligned16(base) && aligned16(g_in) && aligned16(g_x) && aligned16(g_base);
-    cudaStream_t s = (cudaStream_t)stream;
+#if EE_HAS(3)
+int ee_shared::bwd_step125(ee::EdgeArgs& a, const EEParams* p, int B, bool blend, bool vec_ok, bool nhwc, cudaStream_t s) {
+    const int C = a.C, H = a.H, W = a.W;
+    const float* x = a.x;
     Launch L;
-    const bool nhwc = (p->layout == EE_LAYOUT_NHWC) && C > 1;
+    int rc;
     if (nhwc) {
-        if (!(blend && C == 3 && fast_eligible(a, vec_ok)))
-            return fail(EE_ERR_UNSUPPORTED, "NHWC needs the fused blend entry point, C == 3, W %% 4 == 0, 16-byte aligned tensors");
-        const bool st = (p->variant == EE_VARIANT_STEP125);
-        rc = st ? plan_fast(H, W, 4, 3, 18, 8, 62 * 1024, g_th_bwd.load(), L)
-                : plan_fast(H, W, 4, ee::kCannyFastBwdRowsPerTH, ee::kCannyFastBwdRowsFixed, 12, 104 * 1024, g_th_bwd.load(), L, 8, 128, 48);
+        if (!(blend && C == 3 && fast_eligible(a, vec_ok))) return fail(EE_ERR_UNSUPPORTED, EE_NHWC_MSG);
+        rc = plan_fast(H, W, 4, 3, 18, 8, 62 * 1024, g_th_bwd.load(), L);
         if (rc) return rc;
-        if (!st) L.even_planes = 4;      // whole-image Canny backward: gy1 reuses the blurred plane's region
         ee::FastArgs f;
         fill_fast(f, a, L);
-        if (st) EE_DISPATCH_FAST_NHWC(ee::edge_bwd_step125_fast, L, B, f, s, "edge_bwd_step125_fast_nhwc");
-        else EE_DISPATCH_FAST_NHWC(ee::edge_bwd_canny_fast, L, B, f, s, "edge_bwd_canny_fast_nhwc");
+        EE_DISPATCH_FAST_NHWC(ee::edge_bwd_step125_fast, L, B, f, s, "edge_bwd_step125_fast_nhwc");
     }
-    if (p->variant == EE_VARIANT_STEP125 && fast_eligible(a, vec_ok) && g_staging.load() == 5 && C == 3 && H == 224 && W == 224) {
+    if (fast_eligible(a, vec_ok) && g_staging.load() == 5 && C == 3 && H == 224 && W == 224) {
         // opt-in (staging 5; measured equal to the strip kernels, ee_edge_cluster.cuh): ImageNet size as one cluster of
         // 8 CTAs x 28 rows per image, halo rows exchanged through distributed shared memory
         if (blend) return launch_cluster(ee::edge_bwd_step125_cluster<3, true, 4, 224, 28, 8>, 224, 28, 8, B, a, s, "edge_bwd_step125_cluster");
         return launch_cluster(ee::edge_bwd_step125_cluster<3, false, 4, 224, 28, 8>, 224, 28, 8, B, a, s, "edge_bwd_step125_cluster");
     }
-    if (p->variant == EE_VARIANT_STEP125 && fast_eligible(a, vec_ok) && W > 128 && H % 4 == 0 && H >= 16 && g_th_bwd.load() == 0 &&
-        g_staging.load() != 3) {
+    if (fast_eligible(a, vec_ok) && W > 128 && H % 4 == 0 && H >= 16 && g_th_bwd.load() == 0 && g_staging.load() != 3) {
         // wide images: chunk-aligned 56 x 56 tiles, one chunk per thread, no row guards (staging 3 = the older strip path;
         // staging 6 = x tiles staged by TMA tensor copies instead of LDGs, C == 3)
         plan_tiles(H, W, L);
@@ -539,7 +559,7 @@ int edge_backward(const float* g_in, const float* x, const float* base, float* g
         if (blend) return launch_tiles(ee::edge_bwd_step125_tiles<0, true, 4, 64>, L, B, f, map, s, "edge_bwd_step125_tiles");
         return launch_tiles(ee::edge_bwd_step125_tiles<0, false, 4, 64>, L, B, f, map, s, "edge_bwd_step125_tiles");
     }
-    if (p->variant == EE_VARIANT_STEP125 && fast_eligible(a, vec_ok)) {
+    if (fast_eligible(a, vec_ok)) {
         rc = plan_fast(H, W, 4, 3, 18, 8, 62 * 1024, g_th_bwd.load(), L);
         if (rc) return rc;
         ee::FastArgs f;
@@ -554,12 +574,27 @@ int edge_backward(const float* g_in, const float* x, const float* base, float* g
         if (blend) EE_DISPATCH_FAST(ee::edge_bwd_step125_fast, true, L, B, f, s, "edge_bwd_step125_fast");
         else EE_DISPATCH_FAST(ee::edge_bwd_step125_fast, false, L, B, f, s, "edge_bwd_step125_fast");
     }
-    if (p->variant == EE_VARIANT_STEP125) {
-        rc = plan(H, W, vec_ok, 3, 18, 8, 56 * 1024, g_th_bwd.load(), L);
+    rc = plan(H, W, vec_ok, 3, 18, 8, 56 * 1024, g_th_bwd.load(), L);
+    if (rc) return rc;
+    a.TH = L.TH; a.tiles_per_img = L.tiles; a.GX = L.GX; a.RY = L.RY;
+    if (blend) EE_DISPATCH(ee::edge_bwd_step125_kernel, true, L, B, a, s, "edge_bwd_step125");
+    else EE_DISPATCH(ee::edge_bwd_step125_kernel, false, L, B, a, s, "edge_bwd_step125");
+}
+#endif
+
+#if EE_HAS(5)
+int ee_shared::bwd_canny(ee::EdgeArgs& a, const EEParams* p, int B, bool blend, bool vec_ok, bool nhwc, cudaStream_t s) {
+    const int C = a.C, H = a.H, W = a.W;
+    Launch L;
+    int rc;
+    if (nhwc) {
+        if (!(blend && C == 3 && fast_eligible(a, vec_ok))) return fail(EE_ERR_UNSUPPORTED, EE_NHWC_MSG);
+        rc = plan_fast(H, W, 4, ee::kCannyFastBwdRowsPerTH, ee::kCannyFastBwdRowsFixed, 12, 104 * 1024, g_th_bwd.load(), L, 8, 128, 48);
         if (rc) return rc;
-        a.TH = L.TH; a.tiles_per_img = L.tiles; a.GX = L.GX; a.RY = L.RY;
-        if (blend) EE_DISPATCH(ee::edge_bwd_step125_kernel, true, L, B, a, s, "edge_bwd_step125");
-        else EE_DISPATCH(ee::edge_bwd_step125_kernel, false, L, B, a, s, "edge_bwd_step125");
+        L.even_planes = 4;      // whole-image Canny backward: gy1 reuses the blurred plane's region
+        ee::FastArgs f;
+        fill_fast(f, a, L);
+        EE_DISPATCH_FAST_NHWC(ee::edge_bwd_canny_fast, L, B, f, s, "edge_bwd_canny_fast_nhwc");
     }
     if (canny_tiles_ok(a, vec_ok, g_th_bwd.load())) {
         // wide images, hysteresis mode: chunk-aligned 48 x 48 tiles with an 8-pixel halo (ee_edge_canny_tiles.cuh)
@@ -596,6 +631,41 @@ int edge_backward(const float* g_in, const float* x, const float* base, float* g
     a.TH = L.TH; a.tiles_per_img = L.tiles; a.GX = L.GX; a.RY = L.RY;
     if (blend) EE_DISPATCH(ee::edge_bwd_canny_kernel, true, L, B, a, s, "edge_bwd_canny");
     else EE_DISPATCH(ee::edge_bwd_canny_kernel, false, L, B, a, s, "edge_bwd_canny");
+}
+#endif
+
+#if EE_HAS(1)
+namespace {
+
+int edge_forward(const float* x, const float* base, float* out, float* edge, int B, int C, int H, int W,
+                 const EEParams* p, float w, bool blend, void* stream) {
+    ee::EdgeArgs a;
+    int rc = fill_args(a, B, C, H, W, p, w);
+    if (rc) return rc;
+    if (!x) return fail(EE_ERR_INVALID_ARG, "x is null");
+    if (blend && (!base || !out)) return fail(EE_ERR_INVALID_ARG, "base/out is null");
+    if (!blend && !edge) return fail(EE_ERR_INVALID_ARG, "edge is null");
+    a.x = x; a.base = base; a.out = out; a.edge = edge;
+    const bool vec_ok = (W % 4 == 0) && aligned16(x) && aligned16(base) && aligned16(out) && aligned16(edge);
+    const bool nhwc = (p->layout == EE_LAYOUT_NHWC) && C > 1;       // with one channel the layouts coincide
+    if (p->variant == EE_VARIANT_STEP125) return ee_shared::fwd_step125(a, p, B, blend, vec_ok, nhwc, (cudaStream_t)stream);
+    return ee_shared::fwd_canny(a, p, B, blend, vec_ok, nhwc, (cudaStream_t)stream);
+}
+
+int edge_backward(const float* g_in, const float* x, const float* base, float* g_x, float* g_base, int B, int C,
+                  int H, int W, const EEParams* p, float w, bool blend, void* stream) {
+    ee::EdgeArgs a;
+    int rc = fill_args(a, B, C, H, W, p, w);
+    if (rc) return rc;
+    if (!x || !g_in) return fail(EE_ERR_INVALID_ARG, "x/g is null");
+    if (blend && !base) return fail(EE_ERR_INVALID_ARG, "base is null");
+    if (!blend && !g_x) return fail(EE_ERR_INVALID_ARG, "g_x is null");
+    if (blend && !g_x && !g_base) return EE_OK;   // nothing requested
+    a.x = x; a.base = base; a.g_in = g_in; a.g_x = g_x; a.g_base = g_base;
+    const bool vec_ok = (W % 4 == 0) && aligned16(x) && aligned16(base) && aligned16(g_in) && aligned16(g_x) && aligned16(g_base);
+    const bool nhwc = (p->layout == EE_LAYOUT_NHWC) && C > 1;
+    if (p->variant == EE_VARIANT_STEP125) return ee_shared::bwd_step125(a, p, B, blend, vec_ok, nhwc, (cudaStream_t)stream);
+    return ee_shared::bwd_canny(a, p, B, blend, vec_ok, nhwc, (cudaStream_t)stream);
 }
 
 // ---- elementwise launcher ----------------------------------------------------------------
@@ -753,3 +823,4 @@ int ee_set_tuning(int strip_rows_fwd, int strip_rows_bwd, int staging) {
 }
 
 }  // extern "C"
+#endif  // EE_HAS(1)
