@@ -440,7 +440,7 @@ def run_ours(args):
                          % (args.cpu_images, S, S, n_cpu, secs * n_cpu)}
 
     if args.sweep and rank == 0:
-        run_sweep(torch, F_ee, canny, dev, peak)
+        run_sweep(torch, F_ee, canny, dev, peak, args.variant)
 
     if rank == 0:
         line = {
@@ -580,10 +580,10 @@ def run_e2e_attack_api(args, torch, dist, dev, world, rank, core, attacks, canny
                    "%d chunks on %d streams, pinned host buffers" % (len(bounds), N_STREAMS)}
 
 
-def run_sweep(torch, F_ee, canny, dev, peak):
+def run_sweep(torch, F_ee, canny, dev, peak, variant="step125"):
     """configs[4]: standalone kernel sweep (batch x side), printed on stderr as a table."""
-    p = canny.params(None, HIGH, False)
-    print("sweep: B side | fwd GB/s (frac) | bwd GB/s (frac) | pgd GB/s (frac)", file=sys.stderr)
+    p = canny.params(None if variant == "step125" else LOW, HIGH, True)
+    print("sweep (%s): B side | fwd GB/s (frac) | bwd GB/s (frac) | pgd GB/s (frac)" % variant, file=sys.stderr)
     for side in (32, 64, 224):
         for B in (64, 256, 1024, 4096):
             shape = (B, 3, side, side)

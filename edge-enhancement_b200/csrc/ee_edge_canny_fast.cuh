@@ -198,8 +198,15 @@ __device__ __forceinline__ void cfast_stage_nms(const FastArgs& a, const Geo geo
 // -------------------------------------------------------------------------------------------
 // VAR / MODE: 0 / -1 = read variant and output mode from the arguments; the hot configuration (models always
 // call the filter with both thresholds and hysteresis=True) is compiled with them as constants.
+#ifndef EE_MINB_CANNY_FWD
+#define EE_MINB_CANNY_FWD 3
+#endif
+// L2 bulk prefetch of `base` (consumed by the last stage): 0 off, 1 after the x loads, 2 after the blur, 3 after mag/dir
+#ifndef EE_L2_PREFETCH_FWD_CANNY
+#define EE_L2_PREFETCH_FWD_CANNY 1
+#endif
 template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false, int HT = 0, int VAR = 0, int MODE = -1>
-__global__ void __launch_bounds__(256, 3) edge_fwd_canny_fast(const FastArgs a) {
+__global__ void __launch_bounds__(256, EE_MINB_CANNY_FWD) edge_fwd_canny_fast(const FastArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int DIVM = (NC == 1) ? 0 : (NC == 3 ? 1 : 2);
     constexpr bool EVEN = (HT != 0);
@@ -228,15 +235,24 @@ __global__ void __launch_bounds__(256, 3) edge_fwd_canny_fast(const FastArgs a) 
     const int m_lo = max(r0 - 1 - hc, 0), m_hi = min(r1 + 1 + hc, H);
 
     float* S = R1; float* Bl = R2;
+    auto prefetch_base = [&]() {
+        if (BLEND && (!NHWC || (r0 == 0 && r1 == H)) && one_tile && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
+    };
     if (active) fast_stage_sum<NC, R, NHWC, EVEN>(a, geo, a.e.x + (size_t)b * C * hw, S, s_lo, s_hi, tx, ty);
-#if EE_L2_PREFETCH
-    if (BLEND && (!NHWC || (r0 == 0 && r1 == H)) && one_tile && threadIdx.x < 32 && C <= 32) prefetch_rows(a.e.base, b, C, H, W, r0, r1, threadIdx.x);
+#if EE_L2_PREFETCH_FWD_CANNY == 1
+    prefetch_base();
 #endif
     __syncthreads();
     if (active) fast_stage_blur<R, EVEN>(a, geo, S, s_lo, Bl, b_lo, b_hi, tx, ty);
+#if EE_L2_PREFETCH_FWD_CANNY == 2
+    prefetch_base();
+#endif
     __syncthreads();
     float* M = R1; float* META = R3;
     if (active) cfast_stage_mag_dir<DIVM, R, EVEN>(a, geo, Bl, b_lo, M, META, m_lo, m_hi, tx, ty, variant);
+#if EE_L2_PREFETCH_FWD_CANNY == 3
+    prefetch_base();
+#endif
     __syncthreads();
     if (mode != MODE_HYST) {
         if (active) cfast_stage_nms<NC, BLEND, R, true, NHWC, EVEN>(a, geo, M, META, m_lo, r0, r1, b, mode, tx, ty, variant);
