@@ -72,6 +72,46 @@ class PreActResNet18(nn.Module):
         return self.fc(F.adaptive_avg_pool2d(o, 1).flatten(1))
 
 
+class Bottleneck(nn.Module):
+    def __init__(self, cin, mid, stride):
+        super().__init__()
+        cout = mid * 4
+        self.c1, self.b1 = nn.Conv2d(cin, mid, 1, bias=False), nn.BatchNorm2d(mid)
+        self.c2, self.b2 = nn.Conv2d(mid, mid, 3, stride, 1, bias=False), nn.BatchNorm2d(mid)
+        self.c3, self.b3 = nn.Conv2d(mid, cout, 1, bias=False), nn.BatchNorm2d(cout)
+        self.down = None
+        if stride != 1 or cin != cout:
+            self.down = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
+
+    def forward(self, x):
+        o = F.relu(self.b1(self.c1(x)))
+        o = F.relu(self.b2(self.c2(o)))
+        o = self.b3(self.c3(o))
+        return F.relu(o + (x if self.down is None else self.down(x)))
+
+
+class ResNet50(nn.Module):
+    """stock ResNet-50 (ImageNet/models_imagenet/resnet_EE.py is the reference's), front end applied to the input"""
+
+    def __init__(self, front, n_class=1000):
+        super().__init__()
+        self.front = front
+        self.conv1, self.bn1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False), nn.BatchNorm2d(64)
+        layers, cin = [], 64
+        for mid, n, stride in ((64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)):
+            for i in range(n):
+                layers.append(Bottleneck(cin, mid, stride if i == 0 else 1))
+                cin = mid * 4
+        self.layers = nn.Sequential(*layers)
+        self.fc = nn.Linear(2048, n_class)
+
+    def forward(self, x):
+        x = self.front(x)
+        o = F.max_pool2d(F.relu(self.bn1(self.conv1(x))), 3, 2, 1)
+        o = self.layers(o)
+        return self.fc(F.adaptive_avg_pool2d(o, 1).flatten(1))
+
+
 # ---- eager front end: the reference's composition out of stock torch ops ----
 class _ThresholdSTE(torch.autograd.Function):
     """binary mask `v > thr` with the straight-through window (thr, 1.001] in the backward"""
@@ -152,7 +192,14 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU")
     ap.add_argument("--side", type=int, default=64)
     ap.add_argument("--pgd-steps", type=int, default=10)
+    ap.add_argument("--config", default="tiny_pgd", choices=["tiny_pgd", "imagenet_free"],
+                    help="tiny_pgd: BASELINE configs[1] (default); imagenet_free: configs[3], ResNet-50, 3x224x224, 32 images per GPU, "
+                         "free adversarial training with n_repeats = 4, clip_eps = fgsm_step = 4/255 "
+                         "(ImageNet/free_imagenet/AT_hfs_canny_free_imagenet_ddp.py:288-334)")
     args = ap.parse_args()
+    free = (args.config == "imagenet_free")
+    if free:
+        args.side, args.batch = 224, (32 if args.batch == 256 else args.batch)
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -173,15 +220,42 @@ def main():
         torch.manual_seed(0)
         if front_name == "ours":
             with contextlib.redirect_stdout(io.StringIO()):
-                front = core.EdgeEnhance(cize=args.side, r=8, w=1.0, low=38.0, high=76.0, alpha=0.0, sigma=1,
+                front = core.EdgeEnhance(cize=args.side, r=16 if free else 8, w=1.0, low=38.0, high=76.0, alpha=0.0, sigma=1,
                                          type_canny='CannyFilter_step125_1')
         else:
-            front = EagerFront(args.side, 8, 1.0, HIGH, dev, faithful=(front_name == "eager"))
-        model = PreActResNet18(front).to(dev)
+            front = EagerFront(args.side, 16 if free else 8, 1.0, HIGH, dev, faithful=(front_name == "eager"))
+        model = (ResNet50(front) if free else PreActResNet18(front)).to(dev)
+        if free and world > 1:
+            model = nn.SyncBatchNorm.convert_sync_batchnorm(model)          # as the reference does (:170)
         net = nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
         opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9, weight_decay=2e-4)
 
+        noise = torch.zeros((args.batch, 3, args.side, args.side), device=dev)      # the reference's global_noise_data
+        clip_eps = fgsm_step = 4 / 255
+
+        def free_iteration():
+            """one mini-batch of free adversarial training: n_repeats = 4 replays, each a forward/backward that updates the
+            weights AND the persistent noise (AT_hfs_canny_free_imagenet_ddp.py:311-334)"""
+            net.train()
+            in1 = torch.clamp(x + noise, 0, 1.0)
+            for _ in range(4):
+                in1 = in1.detach().requires_grad_()
+                loss = F.cross_entropy(net(in1), y)
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                if front_name == "ours":
+                    in1 = attacks.free_at_update_(noise, in1.grad, x, fgsm_step, clip_eps)      # delta update + next input, one kernel
+                else:
+                    noise.add_(fgsm_step * torch.sign(in1.grad))
+                    noise.clamp_(-clip_eps, clip_eps)
+                    in1 = x + noise
+                    in1.clamp_(0, 1.0)
+                opt.step()
+            return loss
+
         def iteration():
+            if free:
+                return free_iteration()
             net.eval()                                       # attack in eval mode keeps BN statistics out of the inner loop
             if front_name == "ours":
                 x_adv = attacks.PGD(net, A, x, y, args.pgd_steps, ALPHA)
@@ -212,11 +286,13 @@ def main():
         ips = world * args.batch * args.iters / (float(ms.item()) / 1e3)
         results.append((front_name, ips))
         if rank == 0:
-            print(json.dumps({"metric": "edge-enhanced PGD-%d adversarial training images/sec" % args.pgd_steps, "front_end": front_name,
+            print(json.dumps({"metric": ("edge-enhanced free adversarial training (n_repeats 4) images/sec" if free else
+                                         "edge-enhanced PGD-%d adversarial training images/sec" % args.pgd_steps), "front_end": front_name,
                               "value": ips, "unit": "images/s", "n_gpus": world, "ms_per_iteration": float(ms.item()) / args.iters,
-                              "config": "PreAct-ResNet18 (stock torch ops, fp32, cudnn TF32 default), 3x%dx%d, batch %d per GPU, "
-                                        "CannyFilter_step125_1 + torch.fft low-pass, eps 16/255, step 2/255, SGD; DDP/NCCL for N > 1"
-                                        % (args.side, args.side, args.batch),
+                              "config": "%s (stock torch ops, fp32, cudnn TF32 default), 3x%dx%d, batch %d per GPU, "
+                                        "CannyFilter_step125_1 + torch.fft low-pass, %s, SGD; DDP/NCCL for N > 1"
+                                        % ("ResNet-50 + SyncBN" if free else "PreAct-ResNet18", args.side, args.side, args.batch,
+                                           "clip_eps = fgsm_step = 4/255, 4 replays per batch" if free else "eps 16/255, step 2/255"),
                               "final_loss": float(loss.item()), "data": "synthetic"}), flush=True)
         del net, model, opt
         torch.cuda.empty_cache()
