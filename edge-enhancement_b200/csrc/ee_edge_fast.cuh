@@ -329,10 +329,14 @@ template <int NC, bool BLEND, int R, int WT, int WG, bool NHWC = false, int HT =
 #ifndef EE_MINB_FWD
 #define EE_MINB_FWD 3
 #endif
+#ifndef EE_MINB_FWD_EVEN
+#define EE_MINB_FWD_EVEN 4
+#endif
 #ifndef EE_MINB_BWD
 #define EE_MINB_BWD 3
 #endif
-__global__ void __launch_bounds__(256, EE_MINB_FWD) edge_fwd_step125_fast(const FastArgs a) {
+// whole-image tiles: 64 registers / 4 CTAs per SM measured +3 % (6.47 -> 6.69 TB/s at 64 px); strips keep 80 registers / 3
+__global__ void __launch_bounds__(256, HT ? EE_MINB_FWD_EVEN : EE_MINB_FWD) edge_fwd_step125_fast(const FastArgs a) {
     extern __shared__ __align__(16) float smem[];
     constexpr int DIVM = (NC == 1) ? 0 : (NC == 3 ? 1 : 2);
     constexpr bool EVEN = (HT != 0);

@@ -229,3 +229,28 @@ def test_reference_scripts_import_on_top_of_the_dropins():
             if k not in saved_mods:
                 del sys.modules[k]
         sys.modules.update(saved_mods)
+
+
+def test_high_freq_suppress_equals_its_spatial_form():
+    """Independent restatement of the low-pass (still UNPINNED against the reference, whose torch.rfft cannot run):
+    keeping rows k1 in [-r, r-1] of the full spectrum and columns k2 in [0, r-1] of the one-sided half, then a C2R
+    inverse that drops Im at k2 = 0, is the real symmetric operator  y = A x Qc - Bm x Qs  with circulant factors
+    a(d) = (1 + 2 sum_{k<r} cos(2 pi k d/N) + cos(2 pi r d/N))/N, b(d) = -sin(2 pi r d/N)/N over rows and
+    qc(d) = (1 + 2 sum_{k<r} cos(2 pi k d/N))/N, qs(d) = 2 sum_{k<r} sin(2 pi k d/N)/N over columns."""
+    for N, r in ((28, 4), (64, 8), (32, 16 - 1)):
+        d = np.arange(N)[:, None] - np.arange(N)[None, :]
+        k = np.arange(1, r)
+        cos_sum = np.cos(2 * np.pi * d[..., None] * k / N).sum(-1)
+        sin_sum = np.sin(2 * np.pi * d[..., None] * k / N).sum(-1)
+        A = (1 + 2 * cos_sum + np.cos(2 * np.pi * r * d / N)) / N
+        Bm = -np.sin(2 * np.pi * r * d / N) / N
+        Qc = (1 + 2 * cos_sum) / N
+        Qs = 2 * sin_sum / N
+        x = np.random.default_rng(N).random((2, 3, N, N))
+        want = A @ x @ Qc.T - Bm @ x @ Qs.T                    # Qc symmetric, Qs antisymmetric: x[h', w'] q(w - w')
+        got = core.HighFreqSuppress(N, N, r)(torch.from_numpy(x).float()).double().numpy()
+        assert np.abs(got - want).max() < 2e-5, (N, r, np.abs(got - want).max())
+        # the operator is symmetric: <H a, b> == <a, H b>
+        a, b = torch.rand(1, 1, N, N), torch.rand(1, 1, N, N)
+        h = core.HighFreqSuppress(N, N, r)
+        assert abs(float((h(a) * b).sum() - (a * h(b)).sum())) < 1e-3
