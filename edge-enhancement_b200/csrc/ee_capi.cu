@@ -10,6 +10,7 @@
 #include "ee_edge_fast.cuh"
 #include "ee_edge_step125.cuh"
 #include "ee_square.cuh"
+#include "ee_hfs.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -692,6 +693,21 @@ int launch_ew(const float* i0, const float* i1, const float* i2, const float* i3
 
 }  // namespace
 
+template <int N, int R, int P>
+static int launch_hfs(const ee::HfsArgs& a, cudaStream_t s) {
+    using D_ = ee::HfsDims<N, R>;
+    const size_t smem = (size_t)(D_::kTables + P * D_::kPlane) * sizeof(float);
+    auto kernel = ee::hfs_kernel<N, R, P>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+    }
+    kernel<<<(unsigned)((a.planes + P - 1) / P), 256, smem, s>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ee_hfs_f32");
+    return EE_OK;
+}
+
 extern "C" {
 
 int ee_edge_fwd_f32(const float* x, float* edge, int B, int C, int H, int W, const EEParams* p, void* stream) {
@@ -811,6 +827,24 @@ int ee_add_square_fwd_f32(const float* x, const float* stripe, const float* tabl
 int ee_add_square_bwd_f32(const float* g, const float* x, const float* stripe, const float* table, float* g_x, int B, int C,
                           int H, int W, int n_sq, float eps, void* stream) {
     return add_square(true, g, x, stripe, table, g_x, B, C, H, W, n_sq, eps, stream);
+}
+
+int ee_hfs_supported(int N, int r) { return (N == 64 && r == 8) || (N == 28 && r == 4) || (N == 32 && r == 8); }
+int ee_hfs_f32(const float* x, float* y, int planes, int N, int r, const float* cb, const float* rb, const float* w,
+               float gamma, void* stream) {
+    if (planes < 0) return fail(EE_ERR_INVALID_ARG, "ee_hfs_f32: negative plane count");
+    if (planes == 0) return EE_OK;
+    if (!x || !y || !cb || !rb || !w) return fail(EE_ERR_INVALID_ARG, "ee_hfs_f32: null pointer");
+    if (x == y) return fail(EE_ERR_INVALID_ARG, "ee_hfs_f32: y must not alias x");
+    if (!aligned16(x) || !aligned16(y) || !aligned16(cb) || !aligned16(rb) || !aligned16(w))
+        return fail(EE_ERR_INVALID_ARG, "ee_hfs_f32: pointers must be 16-byte aligned");
+    ee::HfsArgs a;
+    a.x = x; a.y = y; a.cb = cb; a.rb = rb; a.w = w; a.gamma = gamma; a.planes = planes;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (N == 64 && r == 8) return launch_hfs<64, 8, 4>(a, s);
+    if (N == 28 && r == 4) return launch_hfs<28, 4, 16>(a, s);
+    if (N == 32 && r == 8) return launch_hfs<32, 8, 8>(a, s);
+    return fail(EE_ERR_UNSUPPORTED, "ee_hfs_f32: no kernel for a %d x %d plane with radius %d (ee_hfs_supported)", N, N, r);
 }
 
 const char* ee_last_error(void) { return g_err; }

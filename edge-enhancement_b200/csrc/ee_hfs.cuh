@@ -1,0 +1,233 @@
+// ee_hfs.cuh -- HighFreqSuppress (utils/core.py:15-55), the square low-pass in front of every *_EE model, as ONE
+// kernel per direction instead of torch.fft's rfft2 -> mask multiply -> irfft2 (three library passes over complex
+// intermediates; measured 621 us forward at 4096x3x64x64, against 91 us for the fused edge forward next to it).
+//
+// The low-pass keeps the frequency rows k1 in [-r, r-1] and the one-sided columns k2 in [0, r-1]; with the C2R inverse's
+// treatment of the k2 = 0 column it is the real SYMMETRIC operator (tests/test_host_logic.py)
+//     y = A x Qc^T - Bm x Qs^T ,
+// whose circulant factors have rank 2r+1 / 2 (rows) and 2r-1 / 2r-2 (columns).  With the real Fourier bases
+//     CB[w][j] : 1, cos(k th_w) (k = 1..r-1), sin(k th_w) (k = 1..r-1)                 (NJ = 2r-1 columns)
+//     RB[h][i] : 1, cos(k th_h) (k = 1..r),   sin(k th_h) (k = 1..r)                   (NI = 2r+1 columns)
+// it is five small dense products per N x N plane, all in shared memory (fp32 FFMA, ~38 multiply-adds per element):
+//     T = x CB      D = RB^T T      G = W o D (+ four cross terms of the -r row)      V = RB G      y = V CB^T
+// The operator is self-adjoint, so the backward is the same kernel applied to the upstream gradient.
+//
+// Work decomposition: P planes per 256-thread CTA (256 / P threads each), whole planes resident in shared memory.
+// The two large products use 4 x 4 register tiles whose 4 rows (resp. columns) are INTERLEAVED with stride N/4, so
+// that the threads of a warp touch consecutive shared-memory rows (row strides = 4 mod 32 floats: every 128-bit load of
+// a quarter warp hits 8 distinct bank groups).  Every sum is one fmaf chain in ascending index order: the C oracle
+// (oracle/ee_oracle.c) evaluates the same chains on the same tables, so kernel and oracle agree bit for bit.
+#pragma once
+#include "ee_device.cuh"
+
+namespace ee {
+
+template <int N, int R>
+struct HfsDims {
+    static constexpr int NJ = 2 * R - 1, NI = 2 * R + 1;
+    static constexpr int NJp = (NJ + 3) / 4 * 4, NIp = (NI + 3) / 4 * 4;
+    static constexpr int XS = (N % 32 == 0) ? N + 4 : ((N + 31) / 32 * 32 + 4);   // == 4 (mod 32), >= N
+    static constexpr int JS = NJp + 4;        // row stride of CB, T, V
+    static constexpr int IS = NIp + 4;        // row stride of RB
+    // floats of shared memory: tables (CB, RB, W) + per plane (X, T, V, D, G)
+    static constexpr int kTables = N * JS + N * IS + NIp * NJp;
+    static constexpr int kPlane = N * XS + N * JS + 2 * NIp * NJp;      // V reuses T's region (T is dead after stage 2)
+};
+
+struct HfsArgs {
+    const float* x;      // [planes][N][N]
+    float* y;            // [planes][N][N]
+    const float* cb;     // [N][NJp]   column bases (zero padded)
+    const float* rb;     // [N][NIp]   row bases
+    const float* w;      // [NIp][NJp] alpha_i * beta_j
+    float gamma;         // 2 / N^2
+    int planes;
+};
+
+template <int N, int R, int P>
+__global__ void __launch_bounds__(256) hfs_kernel(const HfsArgs a) {
+    using D_ = HfsDims<N, R>;
+    constexpr int NJp = D_::NJp, NIp = D_::NIp, NI = D_::NI, NJ = D_::NJ, XS = D_::XS, JS = D_::JS, IS = D_::IS;
+    constexpr int TP = 256 / P, N4 = N / 4;
+    static_assert(N % 4 == 0 && 256 % P == 0, "whole float4 rows, whole thread groups");
+    extern __shared__ __align__(16) float smem_hfs[];
+    float* CB = smem_hfs;                       // [N][JS]
+    float* RB = CB + N * JS;                    // [N][IS]
+    float* Wm = RB + N * IS;                    // [NIp][NJp]
+    const int p = threadIdx.x / TP, lt = threadIdx.x - p * TP;
+    float* X = Wm + NIp * NJp + (size_t)p * D_::kPlane;      // [N][XS]
+    float* T = X + N * XS;                      // [N][JS]
+    float* V = T;                               // [N][JS]  (stage 4 onwards)
+    float* Dm = T + N * JS;                     // [NIp][NJp]
+    float* G = Dm + NIp * NJp;                  // [NIp][NJp]
+    const int plane = blockIdx.x * P + p;
+    const bool live = plane < a.planes;
+
+    // ---- stage 0: tables (all threads) and the planes (each group its own), 128-bit coalesced -----------------
+    for (int i = threadIdx.x; i < N * (NJp / 4); i += 256) {
+        const int w = i / (NJp / 4), q = i - w * (NJp / 4);
+        *reinterpret_cast<float4*>(CB + w * JS + 4 * q) = __ldg(reinterpret_cast<const float4*>(a.cb + w * NJp) + q);
+    }
+    for (int i = threadIdx.x; i < N * (NIp / 4); i += 256) {
+        const int h = i / (NIp / 4), q = i - h * (NIp / 4);
+        *reinterpret_cast<float4*>(RB + h * IS + 4 * q) = __ldg(reinterpret_cast<const float4*>(a.rb + h * NIp) + q);
+    }
+    for (int i = threadIdx.x; i < NIp * NJp / 4; i += 256)
+        reinterpret_cast<float4*>(Wm)[i] = __ldg(reinterpret_cast<const float4*>(a.w) + i);
+    if (live) {
+        const float4* px = reinterpret_cast<const float4*>(a.x + (size_t)plane * N * N);
+        for (int i = lt; i < N * N4; i += TP) {
+            const int h = i / N4, q = i - h * N4;
+            *reinterpret_cast<float4*>(X + h * XS + 4 * q) = __ldcs(px + i);
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 1: T = X CB   (N x NJp, K = N): tile = rows {hg + N4*i} x columns 4jg..4jg+3 -------------------
+    if (live) {
+        for (int t = lt; t < N4 * (NJp / 4); t += TP) {
+            const int hg = t % N4, jg = t / N4;
+            float acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
+#pragma unroll 4
+            for (int w4 = 0; w4 < N4; ++w4) {
+                float4 xv[4], cv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(X + (hg + N4 * i) * XS + 4 * w4);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) cv[q] = *reinterpret_cast<const float4*>(CB + (4 * w4 + q) * JS + 4 * jg);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float xs[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        acc[i][0] = fmaf(xs[q], cv[q].x, acc[i][0]);
+                        acc[i][1] = fmaf(xs[q], cv[q].y, acc[i][1]);
+                        acc[i][2] = fmaf(xs[q], cv[q].z, acc[i][2]);
+                        acc[i][3] = fmaf(xs[q], cv[q].w, acc[i][3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(T + (hg + N4 * i) * JS + 4 * jg) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 2: D = RB^T T   (NIp x NJp, K = N): tile = 4 basis rows x 4 columns ------------------------------
+    if (live) {
+        for (int t = lt; t < (NIp / 4) * (NJp / 4); t += TP) {
+            const int ig = t % (NIp / 4), jg = t / (NIp / 4);
+            float acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
+#pragma unroll 4
+            for (int h = 0; h < N; ++h) {
+                const float4 rv = *reinterpret_cast<const float4*>(RB + h * IS + 4 * ig);
+                const float4 tv = *reinterpret_cast<const float4*>(T + h * JS + 4 * jg);
+                const float rs[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc[i][0] = fmaf(rs[i], tv.x, acc[i][0]);
+                    acc[i][1] = fmaf(rs[i], tv.y, acc[i][1]);
+                    acc[i][2] = fmaf(rs[i], tv.z, acc[i][2]);
+                    acc[i][3] = fmaf(rs[i], tv.w, acc[i][3]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(Dm + (4 * ig + i) * NJp + 4 * jg) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 3: G = W o D, plus the four cross terms that the unpaired frequency row -r contributes -----------
+    //      basis order: rows  i = 0..R : cos(k), i = R+k : sin(k) (k = 1..R);  columns j = 0..R-1 : cos(k), j = R-1+k : sin(k)
+    if (live) {
+        for (int e = lt; e < NIp * NJp; e += TP) {
+            const int i = e / NJp, j = e - i * NJp;
+            float g = Wm[e] * Dm[e];
+            if (j >= 1 && j < NJ) {
+                const bool jcos = (j < R);
+                const int k = jcos ? j : j - (R - 1);                    // frequency of column j (1..R-1)
+                const int jc = k, js = R - 1 + k;
+                if (i == 2 * R) g = jcos ? fmaf(-a.gamma, Dm[R * NJp + js], g) : fmaf(a.gamma, Dm[R * NJp + jc], g);      // row sin(R)
+                if (i == R) g = jcos ? fmaf(a.gamma, Dm[2 * R * NJp + js], g) : fmaf(-a.gamma, Dm[2 * R * NJp + jc], g);   // row cos(R)
+            }
+            G[e] = (i < NI && j < NJ) ? g : 0.0f;
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 4: V = RB G   (N x NJp, K = NI): tile = rows {hg + N4*i} x columns 4jg..4jg+3 --------------------
+    if (live) {
+        for (int t = lt; t < N4 * (NJp / 4); t += TP) {
+            const int hg = t % N4, jg = t / N4;
+            float acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < NI; ++k) {
+                const float4 gv = *reinterpret_cast<const float4*>(G + k * NJp + 4 * jg);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float rv = RB[(hg + N4 * i) * IS + k];
+                    acc[i][0] = fmaf(rv, gv.x, acc[i][0]);
+                    acc[i][1] = fmaf(rv, gv.y, acc[i][1]);
+                    acc[i][2] = fmaf(rv, gv.z, acc[i][2]);
+                    acc[i][3] = fmaf(rv, gv.w, acc[i][3]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(V + (hg + N4 * i) * JS + 4 * jg) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 5: y = V CB^T   (N x N, K = NJp): tile = rows {hg + N4*i} x columns {wg + N4*c} -------------------
+    if (live) {
+        float* py = a.y + (size_t)plane * N * N;
+        for (int t = lt; t < N4 * N4; t += TP) {
+            const int wg = t % N4, hg = t / N4;
+            float acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
+#pragma unroll
+            for (int q = 0; q < NJp / 4; ++q) {
+                float4 vv[4], cv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) vv[i] = *reinterpret_cast<const float4*>(V + (hg + N4 * i) * JS + 4 * q);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) cv[c] = *reinterpret_cast<const float4*>(CB + (wg + N4 * c) * JS + 4 * q);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float s = acc[i][c];
+                        s = fmaf(vv[i].x, cv[c].x, s);
+                        s = fmaf(vv[i].y, cv[c].y, s);
+                        s = fmaf(vv[i].z, cv[c].z, s);
+                        s = fmaf(vv[i].w, cv[c].w, s);
+                        acc[i][c] = s;
+                    }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) __stcs(py + (hg + N4 * i) * N + wg + N4 * c, acc[i][c]);
+        }
+    }
+}
+
+}  // namespace ee

@@ -300,6 +300,54 @@ def pgd_l2_step(x, grad, x0, step, eps):
     return out
 
 
+_HFS_TABLES = {}
+
+
+def hfs_tables(N, r, device):
+    """Device copies of the real Fourier bases / mixing weights of HighFreqSuppress(N, N, r) (cached per device)."""
+    key = (N, r, str(device))
+    t = _HFS_TABLES.get(key)
+    if t is None:
+        n = np.arange(N)
+        th = 2 * np.pi * n / N
+        NJ, NI = 2 * r - 1, 2 * r + 1
+        NJp, NIp = (NJ + 3) // 4 * 4, (NI + 3) // 4 * 4
+        cb = np.zeros((N, NJp)); rb = np.zeros((N, NIp))
+        cb[:, 0] = 1.0; rb[:, 0] = 1.0
+        for k in range(1, r):
+            cb[:, k] = np.cos(k * th); cb[:, r - 1 + k] = np.sin(k * th)
+        for k in range(1, r + 1):
+            rb[:, k] = np.cos(k * th); rb[:, r + k] = np.sin(k * th)
+        alpha = np.zeros(NIp); beta = np.zeros(NJp)
+        alpha[0] = 1.0 / N; alpha[1:r] = 2.0 / N; alpha[r] = 1.0 / N; alpha[r + 1:2 * r] = 2.0 / N; alpha[2 * r] = 1.0 / N
+        beta[0] = 1.0 / N; beta[1:NJ] = 2.0 / N
+        w = np.outer(alpha, beta)
+        t = tuple(torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(device) for a in (cb, rb, w)) + (float(np.float32(2.0 / (N * N))),)
+        _HFS_TABLES[key] = t
+    return t
+
+
+def hfs_supported(N, r):
+    return bool(_lib.load().ee_hfs_supported(int(N), int(r)))
+
+
+def hfs(x, r, out=None):
+    """y = HighFreqSuppress(N, N, r)(x) for [..., N, N] planes -- ee_hfs_f32 (one kernel; self-adjoint, so the same call
+    on the upstream gradient is the backward)."""
+    x = _chk(x, "x")
+    N = x.shape[-1]
+    if x.dim() < 2 or x.shape[-2] != N:
+        raise ValueError("edge_b200: hfs needs square [..., N, N] planes")
+    out = _out_like(x, out)
+    if x.numel():
+        cb, rb, w, gamma = hfs_tables(N, r, x.device)
+        with _on_device(x):
+            rc = _lib.load().ee_hfs_f32(_ptr(x), _ptr(out), x.numel() // (N * N), N, int(r), _ptr(cb), _ptr(rb), _ptr(w),
+                                        gamma, _stream(x))
+        _lib.check(rc, "ee_hfs_f32")
+    return out
+
+
 def _square_operands(x, stripe, table):
     x = _chk(x, "x")
     if x.dim() != 4:
@@ -393,6 +441,19 @@ class EdgeEnhanceFn(torch.autograd.Function):
         need_x, need_base = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         g_x, g_base = edge_blend_backward(g_out, img, base, ctx.params, ctx.w, need_x, need_base)
         return g_x, g_base, None, None
+
+
+class HfsFn(torch.autograd.Function):
+    """x_hfs = HighFreqSuppress(x); the operator is symmetric, so the backward applies it to the upstream gradient."""
+
+    @staticmethod
+    def forward(ctx, x, r):
+        ctx.r = r
+        return hfs(x, r)
+
+    @staticmethod
+    def backward(ctx, g):
+        return hfs(g, ctx.r), None
 
 
 class AddSquareFn(torch.autograd.Function):

@@ -160,6 +160,18 @@ int ee_add_square_fwd_f32(const float* x, const float* stripe, const float* tabl
 int ee_add_square_bwd_f32(const float* g, const float* x, const float* stripe, const float* table, float* g_x,
                           int B, int C, int H, int W, int n_sq, float eps, void* stream);
 
+/* ---- HighFreqSuppress: the square low-pass in front of the *_EE models ---------------- */
+
+/* y[planes][N][N] = HighFreqSuppress(N, N, r)(x), replaces utils/core.py:47-52 (rfft -> mask -> irfft; the reference's
+ * torch.rfft no longer exists, so parity is pinned to the torch.fft restatement only).  The operator is the real
+ * symmetric  y = A x Qc^T - Bm x Qs^T ; it is evaluated as five small dense products per plane on the caller-supplied
+ * tables cb[N][NJp] (1, cos k, sin k for k < r; NJp = 2r-1 rounded up to 4), rb[N][NIp] (1, cos k, sin k for k <= r),
+ * w[NIp][NJp] = alpha_i * beta_j and gamma = 2/N^2 (core.HighFreqSuppress builds them).  Self-adjoint: the backward is the
+ * same call on the upstream gradient.  y must not alias x.  ee_hfs_supported(N, r) tells whether a kernel exists. */
+int ee_hfs_f32(const float* x, float* y, int planes, int N, int r, const float* cb, const float* rb, const float* w,
+               float gamma, void* stream);
+int ee_hfs_supported(int N, int r);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 const char* ee_last_error(void); /* thread-local, never NULL */
 int ee_version(void);            /* EE_VERSION */

@@ -702,6 +702,68 @@ void ee_oracle_add_square(const float *g, const float *x, const float *stripe, c
     }
 }
 
+/* ------------------------------------------------------------------------------------
+ * HighFreqSuppress, utils/core.py:15-55.  PARITY UNPINNED against the reference (its
+ * torch.rfft / irfft calls cannot run on any torch that exists here); pinned against the torch.fft restatement
+ * and against the closed form y = A x Qc^T - Bm x Qs^T (tests/test_host_logic.py).  Same five products, same
+ * tables and the same fmaf chains (ascending index) as the CUDA kernel ee_hfs.cuh:
+ *   T = x CB ; D = RB^T T ; G = W o D (+ the four cross terms of frequency row -r) ; V = RB G ; y = V CB^T
+ * cb[N][NJp], rb[N][NIp], w[NIp][NJp]; NJ = 2r-1, NI = 2r+1, padded to multiples of 4 with zeros.
+ * ---------------------------------------------------------------------------------- */
+int ee_oracle_hfs(const float *x, float *y, int planes, int N, int r, const float *cb, const float *rb,
+                  const float *w, float gamma)
+{
+    const int NJ = 2 * r - 1, NI = 2 * r + 1;
+    const int NJp = (NJ + 3) / 4 * 4, NIp = (NI + 3) / 4 * 4;
+    int failed = 0;
+#pragma omp parallel for schedule(static)
+    for (int p = 0; p < planes; ++p) {
+        float *T = (float *)malloc(sizeof(float) * ((size_t)2 * N * NJp + 2 * NIp * NJp));
+        if (!T) { failed = 1; continue; }
+        float *V = T + (size_t)N * NJp, *D = V + (size_t)N * NJp, *G = D + NIp * NJp;
+        const float *X = x + (size_t)p * N * N;
+        float *Y = y + (size_t)p * N * N;
+        for (int h = 0; h < N; ++h)
+            for (int j = 0; j < NJp; ++j) {
+                float acc = 0.0f;
+                for (int q = 0; q < N; ++q) acc = fmaf(X[h * N + q], cb[q * NJp + j], acc);
+                T[h * NJp + j] = acc;
+            }
+        for (int i = 0; i < NIp; ++i)
+            for (int j = 0; j < NJp; ++j) {
+                float acc = 0.0f;
+                for (int h = 0; h < N; ++h) acc = fmaf(rb[h * NIp + i], T[h * NJp + j], acc);
+                D[i * NJp + j] = acc;
+            }
+        for (int i = 0; i < NIp; ++i)
+            for (int j = 0; j < NJp; ++j) {
+                float g = w[i * NJp + j] * D[i * NJp + j];
+                if (j >= 1 && j < NJ) {
+                    const int jcos = (j < r);
+                    const int k = jcos ? j : j - (r - 1);
+                    const int jc = k, js = r - 1 + k;
+                    if (i == 2 * r) g = jcos ? fmaf(-gamma, D[r * NJp + js], g) : fmaf(gamma, D[r * NJp + jc], g);
+                    if (i == r) g = jcos ? fmaf(gamma, D[2 * r * NJp + js], g) : fmaf(-gamma, D[2 * r * NJp + jc], g);
+                }
+                G[i * NJp + j] = (i < NI && j < NJ) ? g : 0.0f;
+            }
+        for (int h = 0; h < N; ++h)
+            for (int j = 0; j < NJp; ++j) {
+                float acc = 0.0f;
+                for (int i = 0; i < NI; ++i) acc = fmaf(rb[h * NIp + i], G[i * NJp + j], acc);
+                V[h * NJp + j] = acc;
+            }
+        for (int h = 0; h < N; ++h)
+            for (int q = 0; q < N; ++q) {
+                float acc = 0.0f;
+                for (int j = 0; j < NJp; ++j) acc = fmaf(V[h * NJp + j], cb[q * NJp + j], acc);
+                Y[h * N + q] = acc;
+            }
+        free(T);
+    }
+    return failed;
+}
+
 int ee_oracle_version(void) { return 1; }
 
 /* number of host threads the parallel loops above will use (reported as `cores` by bench.py) */

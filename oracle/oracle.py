@@ -91,6 +91,8 @@ def lib():
     L.ee_oracle_add_clamp.restype = None
     L.ee_oracle_avmixup_mix.argtypes = [fp, fp, ctypes.POINTER(ctypes.c_double), fp, i, i64, f]
     L.ee_oracle_avmixup_mix.restype = None
+    L.ee_oracle_hfs.argtypes = [fp, fp, i, i, i, fp, fp, fp, f]
+    L.ee_oracle_hfs.restype = i
     L.ee_oracle_add_square.argtypes = [fp, fp, fp, fp, fp, i, i, i, i, i, f]
     L.ee_oracle_add_square.restype = None
     for name in ("to_compare",):
@@ -212,6 +214,39 @@ def avmixup_mix(x_adv, inputs, weight, gamma):
     lib().ee_oracle_avmixup_mix(_p(x_adv), _p(inputs), w.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), _p(out), B,
                                 x_adv.size // B, float(np.float32(gamma)))
     return out
+
+
+def hfs_tables(N, r):
+    """Real Fourier bases and mixing weights of HighFreqSuppress(N, N, r) (float64 -> float32), shared by the oracle, the
+    CUDA kernel and core.HighFreqSuppress: cb[N][NJp] = 1, cos(k th), sin(k th) (k < r); rb[N][NIp] = 1, cos, sin (k <= r);
+    w[NIp][NJp] = alpha_i * beta_j with alpha = (1, 2.., 1 at k = r)/N, beta = (1, 2..)/N; gamma = 2/N^2."""
+    n = np.arange(N)
+    th = 2 * np.pi * n / N
+    NJ, NI = 2 * r - 1, 2 * r + 1
+    NJp, NIp = (NJ + 3) // 4 * 4, (NI + 3) // 4 * 4
+    cb = np.zeros((N, NJp)); rb = np.zeros((N, NIp))
+    cb[:, 0] = 1.0; rb[:, 0] = 1.0
+    for k in range(1, r):
+        cb[:, k] = np.cos(k * th); cb[:, r - 1 + k] = np.sin(k * th)
+    for k in range(1, r + 1):
+        rb[:, k] = np.cos(k * th); rb[:, r + k] = np.sin(k * th)
+    alpha = np.zeros(NIp); beta = np.zeros(NJp)
+    alpha[0] = 1.0 / N; alpha[1:r] = 2.0 / N; alpha[r] = 1.0 / N; alpha[r + 1:2 * r] = 2.0 / N; alpha[2 * r] = 1.0 / N
+    beta[0] = 1.0 / N; beta[1:NJ] = 2.0 / N
+    w = np.outer(alpha, beta)
+    return (np.ascontiguousarray(cb, np.float32), np.ascontiguousarray(rb, np.float32),
+            np.ascontiguousarray(w, np.float32), float(np.float32(2.0 / (N * N))))
+
+
+def hfs(x, r):
+    """HighFreqSuppress(N, N, r) on [..., N, N] planes (C restatement of the five-product form)."""
+    x = _f32(x)
+    N = x.shape[-1]
+    assert x.shape[-2] == N
+    cb, rb, w, gamma = hfs_tables(N, r)
+    y = np.empty_like(x)
+    _chk(lib().ee_oracle_hfs(_p(x), _p(y), x.size // (N * N), N, r, _p(cb), _p(rb), _p(w), gamma))
+    return y
 
 
 def add_square(x, stripe, table, eps, g=None):

@@ -1,0 +1,61 @@
+"""-m gpu: native HighFreqSuppress kernel (ee_hfs_f32) against the C oracle (bit for bit: same
+tables, same fmaf chains), against the torch.fft restatement (1e-5; the reference's own torch.rfft version cannot run,
+so parity with the reference is UNPINNED), and through the drop-in module incl. autograd (the operator is symmetric)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from edge_enhancement_b200 import core, functional as F_ee   # noqa: E402
+from oracle import oracle as O                               # noqa: E402
+
+DEV = "cuda:0"
+SUPPORTED = [(64, 8), (28, 4), (32, 8)]
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize("N,r", SUPPORTED)
+@pytest.mark.parametrize("planes", [(1, 1), (2, 3), (37, 3), (5, 1)], ids=str)
+def test_kernel_matches_oracle_bit_for_bit(N, r, planes):
+    B, C = planes
+    x = np.random.default_rng(N + B).standard_normal((B, C, N, N)).astype(np.float32)
+    x[0, 0, :3] = 0.0
+    assert F_ee.hfs_supported(N, r)
+    got = F_ee.hfs(cu(x), r).cpu().numpy()
+    assert np.array_equal(got, O.hfs(x, r))
+
+
+@pytest.mark.parametrize("N,r", SUPPORTED)
+def test_module_matches_torch_fft_and_autograd(N, r):
+    m = core.HighFreqSuppress(N, N, r)
+    gen = torch.Generator(device=DEV).manual_seed(N)
+    x = torch.rand((6, 3, N, N), device=DEV, generator=gen, requires_grad=True)
+    g = torch.randn((6, 3, N, N), device=DEV, generator=gen)
+    y = m(x)                                   # native kernel (autograd.Function)
+    y.backward(g)
+    x2 = x.detach().clone().requires_grad_()
+    y2 = m._fft_forward(x2)                    # torch.fft restatement
+    y2.backward(g)
+    scale = float(y2.abs().max())
+    assert float((y - y2).abs().max()) <= 1e-5 * scale
+    assert float((x.grad - x2.grad).abs().max()) <= 1e-5 * float(x2.grad.abs().max())
+    # low-pass sanity: the mean passes, a checkerboard (Nyquist) is removed
+    assert torch.allclose(y.mean((2, 3)), x.mean((2, 3)), atol=1e-5)
+    cb = ((torch.arange(N, device=DEV)[:, None] + torch.arange(N, device=DEV)[None, :]) % 2).float()[None, None]
+    assert float(m(cb - 0.5).abs().max()) < 1e-5
+
+
+def test_unsupported_shapes_take_the_fft_path_and_non_contiguous_inputs_work():
+    assert not F_ee.hfs_supported(224, 16)
+    m = core.HighFreqSuppress(224, 224, 16)
+    x = torch.rand((2, 3, 224, 224), device=DEV)
+    assert torch.equal(m(x), m._fft_forward(x))
+    with pytest.raises(RuntimeError):
+        F_ee.hfs(x, 16)
+    m64 = core.HighFreqSuppress(64, 64, 8)
+    xt = torch.rand((2, 64, 64, 3), device=DEV).permute(0, 3, 1, 2)           # channels_last view: copied to NCHW planes
+    assert float((m64(xt) - m64._fft_forward(xt)).abs().max()) < 1e-5

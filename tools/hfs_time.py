@@ -7,10 +7,11 @@ for B, S, r in ((4096, 64, 8), (256, 64, 8), (512, 224, 16), (32, 224, 16), (163
     h = core.HighFreqSuppress(S, S, r)
     x = torch.rand(B, C, S, S, device="cuda")
     g = torch.randn_like(x)
-    tf = timeit(lambda: h(x))
-    xr = x.clone().requires_grad_()
-    def fb():
-        y = h(xr); y.backward(g); xr.grad = None
-    tfb = timeit(fb)
     n = x.numel()
-    print("HFS torch.fft B=%d %dx%d C=%d: fwd %.1f us (%.0f GB/s at 8 B/elt), fwd+bwd %.1f us" % (B, S, S, C, tf * 1e3, 8 * n / tf / 1e6, tfb * 1e3), flush=True)
+    for name, fn in (("torch.fft", h._fft_forward), ("native   ", h)):
+        tf = timeit(lambda: fn(x))
+        xr = x.clone().requires_grad_()
+        def fb():
+            y = fn(xr); y.backward(g); xr.grad = None
+        tfb = timeit(fb)
+        print("HFS %s B=%d %dx%d C=%d: fwd %.1f us (%.0f GB/s at 8 B/elt), fwd+bwd %.1f us" % (name, B, S, S, C, tf * 1e3, 8 * n / tf / 1e6, tfb * 1e3), flush=True)
