@@ -702,7 +702,15 @@ static int launch_hfs(const ee::HfsArgs& a, cudaStream_t s) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
     }
-    kernel<<<(unsigned)((a.planes + P - 1) / P), 256, smem, s>>>(a);
+    // persistent CTAs: as many as can be resident (shared-memory limited), each loops over groups of P planes
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
+    const int groups = (a.planes + P - 1) / P;
+    int grid = sms * (per_sm < 1 ? 1 : per_sm);
+    if (grid > groups) grid = groups;
+    kernel<<<(unsigned)grid, 256, smem, s>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "ee_hfs_f32");
     return EE_OK;

@@ -17,7 +17,14 @@
 // that the threads of a warp touch consecutive shared-memory rows (row strides = 4 mod 32 floats: every 128-bit load of
 // a quarter warp hits 8 distinct bank groups).  Every sum is one fmaf chain in ascending index order: the C oracle
 // (oracle/ee_oracle.c) evaluates the same chains on the same tables, so kernel and oracle agree bit for bit.
+//
+// The CTAs are PERSISTENT (grid = resident CTAs): a CTA loops over groups of P planes, and as soon as stage 1 has
+// consumed a group's planes it starts the asynchronous copy (cp.async, LDGSTS) of the NEXT group's planes into the same
+// buffer, so the global-load latency -- 43 % of the stall samples of the first, non-persistent version -- overlaps
+// with stages 2-5 (two thirds of the arithmetic).
 #pragma once
+#include <cuda_pipeline.h>
+
 #include "ee_device.cuh"
 
 namespace ee {
@@ -60,10 +67,21 @@ __global__ void __launch_bounds__(256) hfs_kernel(const HfsArgs a) {
     float* V = T;                               // [N][JS]  (stage 4 onwards)
     float* Dm = T + N * JS;                     // [NIp][NJp]
     float* G = Dm + NIp * NJp;                  // [NIp][NJp]
-    const int plane = blockIdx.x * P + p;
-    const bool live = plane < a.planes;
+    const int groups = (a.planes + P - 1) / P;
+    auto load_planes_async = [&](int g) {        // this thread group's plane of group g -> X (16-byte cp.async)
+        const int pl = g * P + p;
+        if (g < groups && pl < a.planes) {
+            const float4* px = reinterpret_cast<const float4*>(a.x + (size_t)pl * N * N);
+            for (int i = lt; i < N * N4; i += TP) {
+                const int h = i / N4, q = i - h * N4;
+                __pipeline_memcpy_async(X + h * XS + 4 * q, px + i, sizeof(float4));
+            }
+        }
+        __pipeline_commit();
+    };
 
-    // ---- stage 0: tables (all threads) and the planes (each group its own), 128-bit coalesced -----------------
+    // ---- prologue: tables (all threads) and the first group's planes --------------------------------------------
+    load_planes_async(blockIdx.x);
     for (int i = threadIdx.x; i < N * (NJp / 4); i += 256) {
         const int w = i / (NJp / 4), q = i - w * (NJp / 4);
         *reinterpret_cast<float4*>(CB + w * JS + 4 * q) = __ldg(reinterpret_cast<const float4*>(a.cb + w * NJp) + q);
@@ -74,14 +92,12 @@ __global__ void __launch_bounds__(256) hfs_kernel(const HfsArgs a) {
     }
     for (int i = threadIdx.x; i < NIp * NJp / 4; i += 256)
         reinterpret_cast<float4*>(Wm)[i] = __ldg(reinterpret_cast<const float4*>(a.w) + i);
-    if (live) {
-        const float4* px = reinterpret_cast<const float4*>(a.x + (size_t)plane * N * N);
-        for (int i = lt; i < N * N4; i += TP) {
-            const int h = i / N4, q = i - h * N4;
-            *reinterpret_cast<float4*>(X + h * XS + 4 * q) = __ldcs(px + i);
-        }
-    }
-    __syncthreads();
+
+  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const int plane = grp * P + p;
+    const bool live = plane < a.planes;
+    __pipeline_wait_prior(0);
+    __syncthreads();                             // this group's planes (and, the first time, the tables) are in shared memory
 
     // ---- stage 1: T = X CB   (N x NJp, K = N): tile = rows {hg + N4*i} x columns 4jg..4jg+3 -------------------
     if (live) {
@@ -117,6 +133,7 @@ __global__ void __launch_bounds__(256) hfs_kernel(const HfsArgs a) {
         }
     }
     __syncthreads();
+    load_planes_async(grp + gridDim.x);          // X is dead: fetch the next group's planes behind stages 2-5
 
     // ---- stage 2: D = RB^T T   (NIp x NJp, K = N): tile = 4 basis rows x 4 columns ------------------------------
     if (live) {
@@ -228,6 +245,7 @@ __global__ void __launch_bounds__(256) hfs_kernel(const HfsArgs a) {
                 for (int c = 0; c < 4; ++c) __stcs(py + (hg + N4 * i) * N + wg + N4 * c, acc[i][c]);
         }
     }
+  }   // persistent loop over plane groups (the barrier at its top also protects V against the next stage 1)
 }
 
 }  // namespace ee
