@@ -716,6 +716,24 @@ static int launch_hfs(const ee::HfsArgs& a, cudaStream_t s) {
     return EE_OK;
 }
 
+template <int N, int R>
+static int launch_hfs_rows(const ee::HfsArgs& a, cudaStream_t s) {
+    const size_t smem = (size_t)ee::HfsRowsDims<N, R>::kFloats * sizeof(float);
+    auto kernel = ee::hfs_rows_kernel<N, R>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
+    int grid = sms * (per_sm < 1 ? 1 : per_sm);
+    if (grid > a.planes) grid = a.planes;
+    kernel<<<(unsigned)grid, 256, smem, s>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ee_hfs_f32");
+    return EE_OK;
+}
+
 extern "C" {
 
 int ee_edge_fwd_f32(const float* x, float* edge, int B, int C, int H, int W, const EEParams* p, void* stream) {
@@ -837,7 +855,9 @@ int ee_add_square_bwd_f32(const float* g, const float* x, const float* stripe, c
     return add_square(true, g, x, stripe, table, g_x, B, C, H, W, n_sq, eps, stream);
 }
 
-int ee_hfs_supported(int N, int r) { return (N == 64 && r == 8) || (N == 28 && r == 4) || (N == 32 && r == 8); }
+int ee_hfs_supported(int N, int r) {
+    return (N == 64 && r == 8) || (N == 28 && r == 4) || (N == 32 && r == 8) || (N == 224 && (r == 16 || r == 18));
+}
 int ee_hfs_f32(const float* x, float* y, int planes, int N, int r, const float* cb, const float* rb, const float* w,
                float gamma, void* stream) {
     if (planes < 0) return fail(EE_ERR_INVALID_ARG, "ee_hfs_f32: negative plane count");
@@ -852,6 +872,8 @@ int ee_hfs_f32(const float* x, float* y, int planes, int N, int r, const float* 
     if (N == 64 && r == 8) return launch_hfs<64, 8, 4>(a, s);
     if (N == 28 && r == 4) return launch_hfs<28, 4, 16>(a, s);
     if (N == 32 && r == 8) return launch_hfs<32, 8, 8>(a, s);
+    if (N == 224 && r == 16) return launch_hfs_rows<224, 16>(a, s);      // ImageNet: row-blocked, one plane per CTA
+    if (N == 224 && r == 18) return launch_hfs_rows<224, 18>(a, s);
     return fail(EE_ERR_UNSUPPORTED, "ee_hfs_f32: no kernel for a %d x %d plane with radius %d (ee_hfs_supported)", N, N, r);
 }
 

@@ -249,3 +249,241 @@ __global__ void __launch_bounds__(256) hfs_kernel(const HfsArgs a) {
 }
 
 }  // namespace ee
+
+namespace ee {
+
+// -------------------------------------------------------------------------------------------------------------------
+// Large planes (ImageNet 224 px, r = 16 / 18): the plane does not fit in shared memory.  One plane per (persistent) CTA;
+// x is STREAMED through two cp.async row-block buffers of RBK = 16 rows while T (N x NJp) is accumulated block by block;
+// D, G, V live in shared memory as above; y is produced row block by row block straight into global memory.
+// A 16-row block only offers 4 x NJp/4 register tiles, so the K range (w) of stage 1 is split over the 8 lanes that share
+// a tile and reduced with an xor-butterfly ((p0+p1)+(p2+p3))+((p4+p5)+(p6+p7)); stage 2 splits its K range (h) over 2
+// lanes.  The oracle evaluates the same partial chains and the same trees (ks1 = 8, ks2 = 2).
+// -------------------------------------------------------------------------------------------------------------------
+template <int N, int R>
+struct HfsRowsDims {
+    using D_ = HfsDims<N, R>;
+    static constexpr int RBK = 16, KS2 = 2;
+    static constexpr int KS1 = ((RBK / 4) * (D_::NJp / 4) * 8 <= 256) ? 8 : 4;     // lanes sharing a stage-1 tile
+    static constexpr int kFloats = N * D_::JS + N * D_::IS + D_::NIp * D_::NJp     // CB, RB, W
+                                   + N * D_::JS + 2 * D_::NIp * D_::NJp           // T (= V), D, G
+                                   + 2 * RBK * D_::XS;                            // two x row-block buffers
+};
+
+template <int N, int R>
+__global__ void __launch_bounds__(256, 1) hfs_rows_kernel(const HfsArgs a) {
+    using D_ = HfsDims<N, R>;
+    using Q_ = HfsRowsDims<N, R>;
+    constexpr int NJp = D_::NJp, NIp = D_::NIp, NI = D_::NI, NJ = D_::NJ, XS = D_::XS, JS = D_::JS, IS = D_::IS;
+    constexpr int RBK = Q_::RBK, KS1 = Q_::KS1, KS2 = Q_::KS2, N4 = N / 4, NBLK = N / RBK;
+    static_assert(N % RBK == 0 && N % (4 * KS1) == 0 && N % KS2 == 0, "row blocks and K splits divide the plane");
+    static_assert((RBK / 4) * (NJp / 4) * KS1 <= 256, "stage 1 fits one pass of the CTA");
+    extern __shared__ __align__(16) float smem_hfs[];
+    float* CB = smem_hfs;
+    float* RB = CB + N * JS;
+    float* Wm = RB + N * IS;
+    float* T = Wm + NIp * NJp;                 // [N][JS], later V
+    float* V = T;
+    float* Dm = T + N * JS;
+    float* G = Dm + NIp * NJp;
+    float* XB = G + NIp * NJp;                 // [2][RBK][XS]
+    const int tid = threadIdx.x;
+
+    auto load_block_async = [&](int plane, int blk, int buf) {       // rows [blk*RBK, +RBK) of `plane` -> XB[buf]
+        if (plane < a.planes) {
+            const float4* px = reinterpret_cast<const float4*>(a.x + (size_t)plane * N * N + (size_t)blk * RBK * N);
+            float* dst = XB + buf * RBK * XS;
+            for (int i = tid; i < RBK * N4; i += 256) {
+                const int h = i / N4, q = i - h * N4;
+                __pipeline_memcpy_async(dst + h * XS + 4 * q, px + i, sizeof(float4));
+            }
+        }
+        __pipeline_commit();
+    };
+
+    load_block_async(blockIdx.x, 0, 0);
+    for (int i = tid; i < N * (NJp / 4); i += 256) {
+        const int w = i / (NJp / 4), q = i - w * (NJp / 4);
+        *reinterpret_cast<float4*>(CB + w * JS + 4 * q) = __ldg(reinterpret_cast<const float4*>(a.cb + w * NJp) + q);
+    }
+    for (int i = tid; i < N * (NIp / 4); i += 256) {
+        const int h = i / (NIp / 4), q = i - h * (NIp / 4);
+        *reinterpret_cast<float4*>(RB + h * IS + 4 * q) = __ldg(reinterpret_cast<const float4*>(a.rb + h * NIp) + q);
+    }
+    for (int i = tid; i < NIp * NJp / 4; i += 256) reinterpret_cast<float4*>(Wm)[i] = __ldg(reinterpret_cast<const float4*>(a.w) + i);
+
+    for (int plane = blockIdx.x; plane < a.planes; plane += gridDim.x) {
+        // ---- stage 1: T = x CB, row block by row block; block b+1 (or block 0 of the next plane) streams in meanwhile ----
+        for (int blk = 0; blk < NBLK; ++blk) {
+            __pipeline_wait_prior(0);
+            __syncthreads();                   // block `blk` is in XB[blk & 1]; the other buffer is free again
+            if (blk + 1 < NBLK) load_block_async(plane, blk + 1, (blk + 1) & 1);
+            else load_block_async(plane + gridDim.x, 0, (blk + 1) & 1);
+            const float* X = XB + (blk & 1) * RBK * XS;
+            const int ks = tid % KS1;
+            const bool tile_ok = (tid / KS1) < (RBK / 4) * (NJp / 4);      // lanes without a tile still take part in the shuffles
+            const int tile = tile_ok ? tid / KS1 : 0;
+            {
+                const int hg = tile % (RBK / 4), jg = tile / (RBK / 4);
+                float acc[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
+                constexpr int W4S = N4 / KS1;                      // float4 steps per K split
+#pragma unroll
+                for (int s = 0; s < W4S; ++s) {
+                    const int w4 = ks * W4S + s;
+                    float4 xv[4], cv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(X + (hg + (RBK / 4) * i) * XS + 4 * w4);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) cv[q] = *reinterpret_cast<const float4*>(CB + (4 * w4 + q) * JS + 4 * jg);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float xs[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            acc[i][0] = fmaf(xs[q], cv[q].x, acc[i][0]);
+                            acc[i][1] = fmaf(xs[q], cv[q].y, acc[i][1]);
+                            acc[i][2] = fmaf(xs[q], cv[q].z, acc[i][2]);
+                            acc[i][3] = fmaf(xs[q], cv[q].w, acc[i][3]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int st = 1; st < KS1; st <<= 1)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[i][c] = acc[i][c] + __shfl_xor_sync(0xffffffffu, acc[i][c], st);
+                if (ks == 0 && tile_ok) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<float4*>(T + (blk * RBK + hg + (RBK / 4) * i) * JS + 4 * jg) =
+                            make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- stage 2: D = RB^T T, K (= h) split over two adjacent lanes --------------------------------------------
+        {
+            const int ks = tid % KS2;
+            const bool t_ok = (tid / KS2) < (NIp / 4) * (NJp / 4);
+            const int t = t_ok ? tid / KS2 : 0;
+            {
+                const int ig = t % (NIp / 4), jg = t / (NIp / 4);
+                float acc[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
+#pragma unroll 4
+                for (int hh = 0; hh < N / KS2; ++hh) {
+                    const int h = ks * (N / KS2) + hh;
+                    const float4 rv = *reinterpret_cast<const float4*>(RB + h * IS + 4 * ig);
+                    const float4 tv = *reinterpret_cast<const float4*>(T + h * JS + 4 * jg);
+                    const float rs[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        acc[i][0] = fmaf(rs[i], tv.x, acc[i][0]);
+                        acc[i][1] = fmaf(rs[i], tv.y, acc[i][1]);
+                        acc[i][2] = fmaf(rs[i], tv.z, acc[i][2]);
+                        acc[i][3] = fmaf(rs[i], tv.w, acc[i][3]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[i][c] = acc[i][c] + __shfl_xor_sync(0xffffffffu, acc[i][c], 1);
+                if (ks == 0 && t_ok) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<float4*>(Dm + (4 * ig + i) * NJp + 4 * jg) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- stage 3: G = W o D + cross terms of the frequency row -r (as in hfs_kernel) ---------------------------
+        for (int e = tid; e < NIp * NJp; e += 256) {
+            const int i = e / NJp, j = e - i * NJp;
+            float g = Wm[e] * Dm[e];
+            if (j >= 1 && j < NJ) {
+                const bool jcos = (j < R);
+                const int k = jcos ? j : j - (R - 1);
+                const int jc = k, js = R - 1 + k;
+                if (i == 2 * R) g = jcos ? fmaf(-a.gamma, Dm[R * NJp + js], g) : fmaf(a.gamma, Dm[R * NJp + jc], g);
+                if (i == R) g = jcos ? fmaf(a.gamma, Dm[2 * R * NJp + js], g) : fmaf(-a.gamma, Dm[2 * R * NJp + jc], g);
+            }
+            G[e] = (i < NI && j < NJ) ? g : 0.0f;
+        }
+        __syncthreads();
+
+        // ---- stage 4: V = RB G (overwrites T) -----------------------------------------------------------------------
+        for (int t = tid; t < N4 * (NJp / 4); t += 256) {
+            const int hg = t % N4, jg = t / N4;
+            float acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < NI; ++k) {
+                const float4 gv = *reinterpret_cast<const float4*>(G + k * NJp + 4 * jg);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float rv = RB[(hg + N4 * i) * IS + k];
+                    acc[i][0] = fmaf(rv, gv.x, acc[i][0]);
+                    acc[i][1] = fmaf(rv, gv.y, acc[i][1]);
+                    acc[i][2] = fmaf(rv, gv.z, acc[i][2]);
+                    acc[i][3] = fmaf(rv, gv.w, acc[i][3]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(V + (hg + N4 * i) * JS + 4 * jg) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        }
+        __syncthreads();
+
+        // ---- stage 5: y = V CB^T, tiles of rows {hg + N4*i} x columns {wg + N4*c} ------------------------------------
+        {
+            float* py = a.y + (size_t)plane * N * N;
+            for (int t = tid; t < N4 * N4; t += 256) {
+                const int wg = t % N4, hg = t / N4;
+                float acc[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
+#pragma unroll
+                for (int q = 0; q < NJp / 4; ++q) {
+                    float4 vv[4], cv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) vv[i] = *reinterpret_cast<const float4*>(V + (hg + N4 * i) * JS + 4 * q);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) cv[c] = *reinterpret_cast<const float4*>(CB + (wg + N4 * c) * JS + 4 * q);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            float s = acc[i][c];
+                            s = fmaf(vv[i].x, cv[c].x, s);
+                            s = fmaf(vv[i].y, cv[c].y, s);
+                            s = fmaf(vv[i].z, cv[c].z, s);
+                            s = fmaf(vv[i].w, cv[c].w, s);
+                            acc[i][c] = s;
+                        }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) __stcs(py + (hg + N4 * i) * N + wg + N4 * c, acc[i][c]);
+            }
+        }
+        // the barrier at the top of the next plane's first row block protects V (= T) and the x buffers
+    }
+}
+
+}  // namespace ee

@@ -710,8 +710,18 @@ void ee_oracle_add_square(const float *g, const float *x, const float *stripe, c
  *   T = x CB ; D = RB^T T ; G = W o D (+ the four cross terms of frequency row -r) ; V = RB G ; y = V CB^T
  * cb[N][NJp], rb[N][NIp], w[NIp][NJp]; NJ = 2r-1, NI = 2r+1, padded to multiples of 4 with zeros.
  * ---------------------------------------------------------------------------------- */
+/* sum of ks partial chains in the order of an xor-butterfly seen from lane 0: ((p0+p1)+(p2+p3))+((p4+p5)+(p6+p7)) */
+static float tree_sum(float *p, int ks)
+{
+    for (int st = 1; st < ks; st <<= 1)
+        for (int i = 0; i + st < ks; i += 2 * st) p[i] = p[i] + p[i + st];
+    return p[0];
+}
+
+/* ks1 / ks2: the large-plane kernel (hfs_rows_kernel) splits the K range of T = x CB over ks1 lanes and that of
+ * D = RB^T T over ks2 lanes and reduces the partial chains with a butterfly; 1 / 1 for the whole-plane kernel. */
 int ee_oracle_hfs(const float *x, float *y, int planes, int N, int r, const float *cb, const float *rb,
-                  const float *w, float gamma)
+                  const float *w, float gamma, int ks1, int ks2)
 {
     const int NJ = 2 * r - 1, NI = 2 * r + 1;
     const int NJp = (NJ + 3) / 4 * 4, NIp = (NI + 3) / 4 * 4;
@@ -725,15 +735,23 @@ int ee_oracle_hfs(const float *x, float *y, int planes, int N, int r, const floa
         float *Y = y + (size_t)p * N * N;
         for (int h = 0; h < N; ++h)
             for (int j = 0; j < NJp; ++j) {
-                float acc = 0.0f;
-                for (int q = 0; q < N; ++q) acc = fmaf(X[h * N + q], cb[q * NJp + j], acc);
-                T[h * NJp + j] = acc;
+                float part[8] = {0.0f};
+                for (int s = 0; s < ks1; ++s) {
+                    float acc = 0.0f;
+                    for (int q = s * (N / ks1); q < (s + 1) * (N / ks1); ++q) acc = fmaf(X[h * N + q], cb[q * NJp + j], acc);
+                    part[s] = acc;
+                }
+                T[h * NJp + j] = tree_sum(part, ks1);
             }
         for (int i = 0; i < NIp; ++i)
             for (int j = 0; j < NJp; ++j) {
-                float acc = 0.0f;
-                for (int h = 0; h < N; ++h) acc = fmaf(rb[h * NIp + i], T[h * NJp + j], acc);
-                D[i * NJp + j] = acc;
+                float part[8] = {0.0f};
+                for (int s = 0; s < ks2; ++s) {
+                    float acc = 0.0f;
+                    for (int h = s * (N / ks2); h < (s + 1) * (N / ks2); ++h) acc = fmaf(rb[h * NIp + i], T[h * NJp + j], acc);
+                    part[s] = acc;
+                }
+                D[i * NJp + j] = tree_sum(part, ks2);
             }
         for (int i = 0; i < NIp; ++i)
             for (int j = 0; j < NJp; ++j) {

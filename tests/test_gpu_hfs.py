@@ -11,7 +11,7 @@ from edge_enhancement_b200 import core, functional as F_ee   # noqa: E402
 from oracle import oracle as O                               # noqa: E402
 
 DEV = "cuda:0"
-SUPPORTED = [(64, 8), (28, 4), (32, 8)]
+SUPPORTED = [(64, 8), (28, 4), (32, 8), (224, 16), (224, 18)]
 
 
 def cu(a):
@@ -50,12 +50,12 @@ def test_module_matches_torch_fft_and_autograd(N, r):
 
 
 def test_unsupported_shapes_take_the_fft_path_and_non_contiguous_inputs_work():
-    assert not F_ee.hfs_supported(224, 16)
-    m = core.HighFreqSuppress(224, 224, 16)
-    x = torch.rand((2, 3, 224, 224), device=DEV)
+    assert not F_ee.hfs_supported(96, 12)
+    m = core.HighFreqSuppress(96, 96, 12)
+    x = torch.rand((2, 3, 96, 96), device=DEV)
     assert torch.equal(m(x), m._fft_forward(x))
     with pytest.raises(RuntimeError):
-        F_ee.hfs(x, 16)
+        F_ee.hfs(x, 12)
     m64 = core.HighFreqSuppress(64, 64, 8)
     xt = torch.rand((2, 64, 64, 3), device=DEV).permute(0, 3, 1, 2)           # channels_last view: copied to NCHW planes
     assert float((m64(xt) - m64._fft_forward(xt)).abs().max()) < 1e-5
