@@ -46,7 +46,7 @@ SIGNATURES = {
     "ee_safe_sign_bwd_f32": [_vp, _vp, _vp, _i64, _vp],
     "ee_add_square_fwd_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
     "ee_add_square_bwd_f32": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
-    "ee_hfs_f32": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _f, _vp],
+    "ee_hfs_f32": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _f, _vp],
     "ee_hfs_supported": [_i, _i],
     "ee_last_error": [],
     "ee_version": [],

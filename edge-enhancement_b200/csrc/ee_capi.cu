@@ -858,16 +858,16 @@ int ee_add_square_bwd_f32(const float* g, const float* x, const float* stripe, c
 int ee_hfs_supported(int N, int r) {
     return (N == 64 && r == 8) || (N == 28 && r == 4) || (N == 32 && r == 8) || (N == 224 && (r == 16 || r == 18));
 }
-int ee_hfs_f32(const float* x, float* y, int planes, int N, int r, const float* cb, const float* rb, const float* w,
-               float gamma, void* stream) {
+int ee_hfs_f32(const float* x, float* y, const float* add_or_null, int planes, int N, int r, const float* cb, const float* rb,
+               const float* w, float gamma, void* stream) {
     if (planes < 0) return fail(EE_ERR_INVALID_ARG, "ee_hfs_f32: negative plane count");
     if (planes == 0) return EE_OK;
     if (!x || !y || !cb || !rb || !w) return fail(EE_ERR_INVALID_ARG, "ee_hfs_f32: null pointer");
     if (x == y) return fail(EE_ERR_INVALID_ARG, "ee_hfs_f32: y must not alias x");
-    if (!aligned16(x) || !aligned16(y) || !aligned16(cb) || !aligned16(rb) || !aligned16(w))
+    if (!aligned16(x) || !aligned16(y) || !aligned16(add_or_null) || !aligned16(cb) || !aligned16(rb) || !aligned16(w))
         return fail(EE_ERR_INVALID_ARG, "ee_hfs_f32: pointers must be 16-byte aligned");
     ee::HfsArgs a;
-    a.x = x; a.y = y; a.cb = cb; a.rb = rb; a.w = w; a.gamma = gamma; a.planes = planes;
+    a.x = x; a.y = y; a.add = add_or_null; a.cb = cb; a.rb = rb; a.w = w; a.gamma = gamma; a.planes = planes;
     cudaStream_t s = (cudaStream_t)stream;
     if (N == 64 && r == 8) return launch_hfs<64, 8, 4>(a, s);
     if (N == 28 && r == 4) return launch_hfs<28, 4, 16>(a, s);

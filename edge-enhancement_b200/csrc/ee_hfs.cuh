@@ -44,6 +44,7 @@ struct HfsDims {
 struct HfsArgs {
     const float* x;      // [planes][N][N]
     float* y;            // [planes][N][N]
+    const float* add;    // optional [planes][N][N]: y = H x + add (the backward accumulates into the edge-path gradient)
     const float* cb;     // [N][NJp]   column bases (zero padded)
     const float* rb;     // [N][NIp]   row bases
     const float* w;      // [NIp][NJp] alpha_i * beta_j
@@ -213,6 +214,7 @@ __global__ void __launch_bounds__(256) hfs_kernel(const HfsArgs a) {
     // ---- stage 5: y = V CB^T   (N x N, K = NJp): tile = rows {hg + N4*i} x columns {wg + N4*c} -------------------
     if (live) {
         float* py = a.y + (size_t)plane * N * N;
+        const float* pa = a.add ? a.add + (size_t)plane * N * N : nullptr;
         for (int t = lt; t < N4 * N4; t += TP) {
             const int wg = t % N4, hg = t / N4;
             float acc[4][4];
@@ -242,7 +244,10 @@ __global__ void __launch_bounds__(256) hfs_kernel(const HfsArgs a) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) __stcs(py + (hg + N4 * i) * N + wg + N4 * c, acc[i][c]);
+                for (int c = 0; c < 4; ++c) {
+                        const int o = (hg + N4 * i) * N + wg + N4 * c;
+                        __stcs(py + o, pa ? acc[i][c] + __ldcs(pa + o) : acc[i][c]);
+                    }
         }
     }
   }   // persistent loop over plane groups (the barrier at its top also protects V against the next stage 1)
@@ -450,6 +455,7 @@ __global__ void __launch_bounds__(256, 1) hfs_rows_kernel(const HfsArgs a) {
         // ---- stage 5: y = V CB^T, tiles of rows {hg + N4*i} x columns {wg + N4*c} ------------------------------------
         {
             float* py = a.y + (size_t)plane * N * N;
+            const float* pa = a.add ? a.add + (size_t)plane * N * N : nullptr;
             for (int t = tid; t < N4 * N4; t += 256) {
                 const int wg = t % N4, hg = t / N4;
                 float acc[4][4];
@@ -479,7 +485,10 @@ __global__ void __launch_bounds__(256, 1) hfs_rows_kernel(const HfsArgs a) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) __stcs(py + (hg + N4 * i) * N + wg + N4 * c, acc[i][c]);
+                    for (int c = 0; c < 4; ++c) {
+                        const int o = (hg + N4 * i) * N + wg + N4 * c;
+                        __stcs(py + o, pa ? acc[i][c] + __ldcs(pa + o) : acc[i][c]);
+                    }
             }
         }
         // the barrier at the top of the next plane's first row block protects V (= T) and the x buffers

@@ -331,10 +331,12 @@ def hfs_supported(N, r):
     return bool(_lib.load().ee_hfs_supported(int(N), int(r)))
 
 
-def hfs(x, r, out=None):
-    """y = HighFreqSuppress(N, N, r)(x) for [..., N, N] planes -- ee_hfs_f32 (one kernel; self-adjoint, so the same call
-    on the upstream gradient is the backward)."""
+def hfs(x, r, out=None, add=None):
+    """y = HighFreqSuppress(N, N, r)(x) [+ add] for [..., N, N] planes -- ee_hfs_f32 (one kernel; self-adjoint, so the same
+    call on the upstream gradient is the backward; `add` lets it accumulate into another gradient, and may be `out`)."""
     x = _chk(x, "x")
+    if add is not None:
+        add = _chk(add, "add", x.shape)
     N = x.shape[-1]
     if x.dim() < 2 or x.shape[-2] != N:
         raise ValueError("edge_b200: hfs needs square [..., N, N] planes")
@@ -342,8 +344,8 @@ def hfs(x, r, out=None):
     if x.numel():
         cb, rb, w, gamma = hfs_tables(N, r, x.device)
         with _on_device(x):
-            rc = _lib.load().ee_hfs_f32(_ptr(x), _ptr(out), x.numel() // (N * N), N, int(r), _ptr(cb), _ptr(rb), _ptr(w),
-                                        gamma, _stream(x))
+            rc = _lib.load().ee_hfs_f32(_ptr(x), _ptr(out), _ptr(add), x.numel() // (N * N), N, int(r), _ptr(cb), _ptr(rb),
+                                        _ptr(w), gamma, _stream(x))
         _lib.check(rc, "ee_hfs_f32")
     return out
 
@@ -454,6 +456,26 @@ class HfsFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         return hfs(g, ctx.r), None
+
+
+class EdgeEnhanceFrontFn(torch.autograd.Function):
+    """The whole front end of the *_EE models (resnet_EE.py:176-191) as three kernels per direction:
+        forward : base = HFS(x) ; out = clamp(base + w * edge(x), 0, 1)
+        backward: (g_x, g_base) = edge_blend_backward(g) ; g_x = HFS(g_base) + g_x     (HFS is symmetric; the sum is fused
+                  into the low-pass kernel's store, so autograd never runs a separate accumulation pass)"""
+
+    @staticmethod
+    def forward(ctx, x, r, params, w):
+        base = hfs(x, r)
+        ctx.r, ctx.params, ctx.w = r, params, w
+        ctx.save_for_backward(x, base)
+        return edge_blend(x, base, params, w)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, base = ctx.saved_tensors
+        g_x, g_base = edge_blend_backward(g, x, base, ctx.params, ctx.w)
+        return hfs(g_base, ctx.r, out=g_x, add=g_x), None, None, None
 
 
 class AddSquareFn(torch.autograd.Function):

@@ -167,9 +167,11 @@ int ee_add_square_bwd_f32(const float* g, const float* x, const float* stripe, c
  * symmetric  y = A x Qc^T - Bm x Qs^T ; it is evaluated as five small dense products per plane on the caller-supplied
  * tables cb[N][NJp] (1, cos k, sin k for k < r; NJp = 2r-1 rounded up to 4), rb[N][NIp] (1, cos k, sin k for k <= r),
  * w[NIp][NJp] = alpha_i * beta_j and gamma = 2/N^2 (core.HighFreqSuppress builds them).  Self-adjoint: the backward is the
- * same call on the upstream gradient.  y must not alias x.  ee_hfs_supported(N, r) tells whether a kernel exists. */
-int ee_hfs_f32(const float* x, float* y, int planes, int N, int r, const float* cb, const float* rb, const float* w,
-               float gamma, void* stream);
+ * same call on the upstream gradient; with add_or_null != NULL the result is y = H x + add (elementwise, may alias y), which
+ * lets the backward of the *_EE front end accumulate H(g_base) into the edge-path gradient without an extra pass.
+ * y must not alias x.  ee_hfs_supported(N, r) tells whether a kernel exists. */
+int ee_hfs_f32(const float* x, float* y, const float* add_or_null, int planes, int N, int r, const float* cb,
+               const float* rb, const float* w, float gamma, void* stream);
 int ee_hfs_supported(int N, int r);
 
 /* ---- misc -------------------------------------------------------------------------------- */

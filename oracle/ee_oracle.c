@@ -720,8 +720,8 @@ static float tree_sum(float *p, int ks)
 
 /* ks1 / ks2: the large-plane kernel (hfs_rows_kernel) splits the K range of T = x CB over ks1 lanes and that of
  * D = RB^T T over ks2 lanes and reduces the partial chains with a butterfly; 1 / 1 for the whole-plane kernel. */
-int ee_oracle_hfs(const float *x, float *y, int planes, int N, int r, const float *cb, const float *rb,
-                  const float *w, float gamma, int ks1, int ks2)
+int ee_oracle_hfs(const float *x, float *y, const float *add, int planes, int N, int r, const float *cb,
+                  const float *rb, const float *w, float gamma, int ks1, int ks2)
 {
     const int NJ = 2 * r - 1, NI = 2 * r + 1;
     const int NJp = (NJ + 3) / 4 * 4, NIp = (NI + 3) / 4 * 4;
@@ -775,7 +775,7 @@ int ee_oracle_hfs(const float *x, float *y, int planes, int N, int r, const floa
             for (int q = 0; q < N; ++q) {
                 float acc = 0.0f;
                 for (int j = 0; j < NJp; ++j) acc = fmaf(V[h * NJp + j], cb[q * NJp + j], acc);
-                Y[h * N + q] = acc;
+                Y[h * N + q] = add ? acc + add[(size_t)p * N * N + h * N + q] : acc;    /* y = H x + add */
             }
         free(T);
     }

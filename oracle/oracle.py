@@ -91,7 +91,7 @@ def lib():
     L.ee_oracle_add_clamp.restype = None
     L.ee_oracle_avmixup_mix.argtypes = [fp, fp, ctypes.POINTER(ctypes.c_double), fp, i, i64, f]
     L.ee_oracle_avmixup_mix.restype = None
-    L.ee_oracle_hfs.argtypes = [fp, fp, i, i, i, fp, fp, fp, f, i, i]
+    L.ee_oracle_hfs.argtypes = [fp, fp, fp, i, i, i, fp, fp, fp, f, i, i]
     L.ee_oracle_hfs.restype = i
     L.ee_oracle_add_square.argtypes = [fp, fp, fp, fp, fp, i, i, i, i, i, f]
     L.ee_oracle_add_square.restype = None
@@ -238,9 +238,10 @@ def hfs_tables(N, r):
             np.ascontiguousarray(w, np.float32), float(np.float32(2.0 / (N * N))))
 
 
-def hfs(x, r):
-    """HighFreqSuppress(N, N, r) on [..., N, N] planes (C restatement of the five-product form)."""
+def hfs(x, r, add=None):
+    """HighFreqSuppress(N, N, r) on [..., N, N] planes (C restatement of the five-product form); + add if given."""
     x = _f32(x)
+    add = None if add is None else _f32(add)
     N = x.shape[-1]
     assert x.shape[-2] == N
     cb, rb, w, gamma = hfs_tables(N, r)
@@ -248,7 +249,7 @@ def hfs(x, r):
     # summation trees of the kernel that serves this shape (ee_hfs.cuh): whole-plane kernel 1 / 1; row-blocked kernel for
     # large planes: stage 1 over 8 lanes (4 when 2r-1 > 32), stage 2 over 2 lanes
     ks1, ks2 = (1, 1) if N < 128 else ((8 if cb.shape[1] <= 32 else 4), 2)
-    _chk(lib().ee_oracle_hfs(_p(x), _p(y), x.size // (N * N), N, r, _p(cb), _p(rb), _p(w), gamma, ks1, ks2))
+    _chk(lib().ee_oracle_hfs(_p(x), _p(y), _p(add), x.size // (N * N), N, r, _p(cb), _p(rb), _p(w), gamma, ks1, ks2))
     return y
 
 

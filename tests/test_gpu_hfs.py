@@ -59,3 +59,37 @@ def test_unsupported_shapes_take_the_fft_path_and_non_contiguous_inputs_work():
     m64 = core.HighFreqSuppress(64, 64, 8)
     xt = torch.rand((2, 64, 64, 3), device=DEV).permute(0, 3, 1, 2)           # channels_last view: copied to NCHW planes
     assert float((m64(xt) - m64._fft_forward(xt)).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("N,r", [(64, 8), (28, 4), (224, 16)])
+def test_accumulate_mode_matches_oracle(N, r):
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((4, 3, N, N)).astype(np.float32)
+    add = rng.standard_normal((4, 3, N, N)).astype(np.float32)
+    want = O.hfs(x, r, add=add)
+    assert np.array_equal(F_ee.hfs(cu(x), r, add=cu(add)).cpu().numpy(), want)
+    buf = cu(add)                                         # in place: out aliases add
+    F_ee.hfs(cu(x), r, out=buf, add=buf)
+    assert np.array_equal(buf.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("cize,r,variant", [(64, 8, "CannyFilter_step125_1"), (64, 8, "CannyFilter"), (28, 4, "CannyFilter_step125_1")])
+def test_fused_front_end_equals_the_three_separate_nodes(cize, r, variant):
+    """core.EdgeEnhance on a supported shape runs low-pass + edge filter + blend as ONE autograd node (the low-pass of the
+    backward accumulates into the edge-path gradient inside the kernel); results and gradients are identical to composing
+    HighFreqSuppress, the filter and the blend as separate nodes."""
+    import contextlib, io
+    C = 1 if cize == 28 else 3
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = core.EdgeEnhance(cize=cize, r=r, w=1.0, low=38.0, high=76.0, alpha=0.0, sigma=1, type_canny=variant)
+    gen = torch.Generator(device=DEV).manual_seed(cize)
+    x = torch.rand((8, C, cize, cize), device=DEV, generator=gen, requires_grad=True)
+    g = torch.randn((8, C, cize, cize), device=DEV, generator=gen)
+    y = m(x)
+    y.backward(g)
+    x2 = x.detach().clone().requires_grad_()
+    base = m.hfs(x2)
+    y2 = core.edge_enhance(x2, base, m.canny, m.w, m.low, m.high, True)
+    y2.backward(g)
+    assert torch.equal(y, y2)
+    assert torch.equal(x.grad, x2.grad)
