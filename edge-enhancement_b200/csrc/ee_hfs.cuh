@@ -272,7 +272,8 @@ struct HfsRowsDims {
     static constexpr int KS1 = ((RBK / 4) * (D_::NJp / 4) * 8 <= 256) ? 8 : 4;     // lanes sharing a stage-1 tile
     static constexpr int kFloats = N * D_::JS + N * D_::IS + D_::NIp * D_::NJp     // CB, RB, W
                                    + N * D_::JS + 2 * D_::NIp * D_::NJp           // T (= V), D, G
-                                   + 2 * RBK * D_::XS;                            // two x row-block buffers
+                                   + 2 * RBK * D_::XS                             // two x row-block buffers
+                                   + D_::NJp * D_::XS;                            // CB transposed (stage 1)
 };
 
 template <int N, int R>
@@ -292,6 +293,10 @@ __global__ void __launch_bounds__(256, 1) hfs_rows_kernel(const HfsArgs a) {
     float* Dm = T + N * JS;
     float* G = Dm + NIp * NJp;
     float* XB = G + NIp * NJp;                 // [2][RBK][XS]
+    // CB transposed, [NJp][XS]: the lanes that split stage 1's K range read x AND the basis at offsets of N/KS1 floats
+    // along w (distinct bank groups); with the [w][j] layout their rows would sit 16 or 0 banks apart (4-way conflicts:
+    // 43 % of all shared-memory wavefronts in the first version, profiles/r1g_ncu_full_hfs224_first.txt)
+    float* CBt = XB + 2 * RBK * XS;
     const int tid = threadIdx.x;
 
     auto load_block_async = [&](int plane, int blk, int buf) {       // rows [blk*RBK, +RBK) of `plane` -> XB[buf]
@@ -316,6 +321,10 @@ __global__ void __launch_bounds__(256, 1) hfs_rows_kernel(const HfsArgs a) {
         *reinterpret_cast<float4*>(RB + h * IS + 4 * q) = __ldg(reinterpret_cast<const float4*>(a.rb + h * NIp) + q);
     }
     for (int i = tid; i < NIp * NJp / 4; i += 256) reinterpret_cast<float4*>(Wm)[i] = __ldg(reinterpret_cast<const float4*>(a.w) + i);
+    for (int i = tid; i < N * NJp; i += 256) {
+        const int w = i / NJp, j = i - w * NJp;
+        CBt[j * XS + w] = __ldg(a.cb + i);
+    }
 
     for (int plane = blockIdx.x; plane < a.planes; plane += gridDim.x) {
         // ---- stage 1: T = x CB, row block by row block; block b+1 (or block 0 of the next plane) streams in meanwhile ----
@@ -339,20 +348,19 @@ __global__ void __launch_bounds__(256, 1) hfs_rows_kernel(const HfsArgs a) {
 #pragma unroll
                 for (int s = 0; s < W4S; ++s) {
                     const int w4 = ks * W4S + s;
-                    float4 xv[4], cv[4];
+                    float4 xv[4], ct[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(X + (hg + (RBK / 4) * i) * XS + 4 * w4);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) cv[q] = *reinterpret_cast<const float4*>(CB + (4 * w4 + q) * JS + 4 * jg);
+                    for (int c = 0; c < 4; ++c) ct[c] = *reinterpret_cast<const float4*>(CBt + (4 * jg + c) * XS + 4 * w4);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float xs[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            acc[i][0] = fmaf(xs[q], cv[q].x, acc[i][0]);
-                            acc[i][1] = fmaf(xs[q], cv[q].y, acc[i][1]);
-                            acc[i][2] = fmaf(xs[q], cv[q].z, acc[i][2]);
-                            acc[i][3] = fmaf(xs[q], cv[q].w, acc[i][3]);
+                        for (int c = 0; c < 4; ++c) {
+                            const float cs[4] = {ct[c].x, ct[c].y, ct[c].z, ct[c].w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) acc[i][c] = fmaf(xs[q], cs[q], acc[i][c]);
                         }
                     }
                 }
