@@ -55,10 +55,15 @@ class GraphedPGD:
 
         pgd = GraphedPGD(model, args, inputs, targets, step_size)      # captures
         x_adv = pgd(inputs, targets, num_steps)                        # replays
+
+    `loss_fn(logits, targets)` replaces the cross-entropy (e.g. the KL loss of Trades.PGD_Linf, attacks.py:412, with
+    `targets` = the clean softmax), a negative `step_size` gives the targeted variants (:52, :505), and `x_init` in the call
+    overrides the start point (ALP / TRADES start from x + 0.001 * randn, :254, :406).
     """
 
-    def __init__(self, model, args, example_inputs, example_targets, step_size, warmup=3):
+    def __init__(self, model, args, example_inputs, example_targets, step_size, warmup=3, loss_fn=None):
         self.model, self.args, self.step_size = model, args, step_size
+        self.loss_fn = loss_fn if loss_fn is not None else (lambda logits, y: F.cross_entropy(logits, y, reduction='sum'))
         self.x0 = example_inputs.detach().clone()
         self.x = self.x0.clone()
         self.y = example_targets.detach().clone()
@@ -78,14 +83,16 @@ class GraphedPGD:
         x = self.x.detach().requires_grad_()
         with torch.enable_grad():
             logits = self.model(x)
-            loss = F.cross_entropy(logits, self.y, reduction='sum')
+            loss = self.loss_fn(logits, self.y)
         grad = torch.autograd.grad(loss, [x])[0]
         F_ee.pgd_linf_step(self.x, grad, self.x0, self.step_size, self.args.epsilon, 0.0, 1.0, out=self.x)
 
-    def __call__(self, inputs, targets, num_steps):
+    def __call__(self, inputs, targets, num_steps, x_init=None):
         self.x0.copy_(inputs.detach())
         self.y.copy_(targets)
-        if self.args.random:
+        if x_init is not None:
+            self.x.copy_(x_init.detach())
+        elif self.args.random:
             self.x.copy_(_random_start(self.x0, self.args.epsilon))
         else:
             self.x.copy_(self.x0)

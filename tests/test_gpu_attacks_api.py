@@ -232,3 +232,38 @@ def test_graphed_pgd_matches_eager_pgd():
     x2 = torch.rand((B, C, S, S), device=DEV, generator=gen)
     y2 = torch.randint(0, n_class, (B,), device=DEV, generator=gen)
     assert torch.equal(pgd(x2, y2, 5), attacks.PGD(model, A, x2, y2, 5, 2 / 255))
+
+
+def test_graphed_pgd_with_the_trades_kl_loss():
+    """GraphedPGD with loss_fn = the KL loss of Trades.PGD_Linf (attacks.py:409-416) and its start point reproduces
+    the eager TRADES inner loop bit for bit."""
+    B, C, S, n_class = 32, 3, 32, 10
+    gen = torch.Generator(device=DEV).manual_seed(33)
+    x = torch.rand((B, C, S, S), device=DEV, generator=gen)
+    with contextlib.redirect_stdout(io.StringIO()):
+        canny = core.CannyFilter_step125_1(use_cuda=False, alpha=0.0)
+    weight = torch.randn((n_class, C * S * S), device=DEV, generator=gen) * 0.05
+
+    def model(inp):
+        z = core.edge_enhance(inp, inp, canny, 1.0, None, 76 / 255, True)
+        return z.reshape(z.shape[0], -1) @ weight.t()
+
+    eps, step, steps = 8 / 255, 2 / 255, 5
+    with torch.no_grad():
+        preds = model(x)
+    x_init = x + 0.001 * torch.randn(x.shape, device=DEV, generator=gen)
+    kl = nn.KLDivLoss(reduction='sum')
+
+    # eager loop exactly as Trades.PGD_Linf writes it (with the fused update)
+    xa = x_init.clone()
+    for _ in range(steps):
+        xa.requires_grad_()
+        with torch.enable_grad():
+            loss = kl(F.log_softmax(model(xa), dim=1), F.softmax(preds, dim=1))
+        g = torch.autograd.grad(loss, [xa])[0]
+        xa = attacks._linf_step(xa, g, x, step, eps)
+
+    args = types.SimpleNamespace(random=False, epsilon=eps)
+    soft = F.softmax(preds, dim=1)
+    pgd = attacks.GraphedPGD(model, args, x, soft, step, loss_fn=lambda logits, y: kl(F.log_softmax(logits, dim=1), y))
+    assert torch.equal(pgd(x, soft, steps, x_init=x_init), xa)
