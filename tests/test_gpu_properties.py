@@ -225,3 +225,32 @@ def test_repeated_launches_are_bit_identical(variant, shape, staging):
             for a, b in zip(ref, cur):
                 assert torch.equal(a, b)
     L.ee_set_tuning(0, 0, 0)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_tensors_on_a_second_device_while_device_0_is_current():
+    """DataParallel replicas and DDP ranks hand the library tensors of a device that is not the thread's current one: the
+    wrappers switch device and stream per call (functional._on_device / _stream), per-device state (function attributes
+    for > 48 KB of shared memory, the low-pass tables) must follow."""
+    from edge_enhancement_b200 import core
+    assert torch.cuda.current_device() == 0
+    d1 = torch.device("cuda:1")
+    x, base, g_out, _ = T.make_inputs(77, 6, 3, 64, 64)
+    for variant in ("step125", "canny"):
+        low = None if variant == "step125" else T.LOW
+        p = F_ee.make_params(variant, O.gaussian3(), 0.0, low, T.HIGH, True)
+        po = O.make_params(variant, alpha=0.0, low=low, high=T.HIGH, hysteresis=True)
+        out = F_ee.edge_blend(torch.from_numpy(x).to(d1), torch.from_numpy(base).to(d1), p, 1.0)
+        g_x, g_base = F_ee.edge_blend_backward(torch.from_numpy(g_out).to(d1), torch.from_numpy(x).to(d1), torch.from_numpy(base).to(d1), p, 1.0)
+        assert out.device == d1 and np.array_equal(out.cpu().numpy(), O.edge_blend_fwd(x, base, po, 1.0))
+        o_gx, o_gb = O.edge_blend_bwd(g_out, x, base, po, 1.0)
+        assert np.array_equal(g_x.cpu().numpy(), o_gx) and np.array_equal(g_base.cpu().numpy(), o_gb)
+    y = F_ee.hfs(torch.from_numpy(x).to(d1), 8)
+    assert y.device == d1 and np.array_equal(y.cpu().numpy(), O.hfs(x, 8))
+    xw = torch.rand(2, 3, 224, 224, device=d1)
+    gw = torch.randn_like(xw)
+    p = F_ee.make_params("step125", O.gaussian3(), 0.0, None, T.HIGH, True)
+    gx1, _ = F_ee.edge_blend_backward(gw, xw, xw, p, 1.0)                       # TMA-staged tiles on device 1
+    gx0, _ = F_ee.edge_blend_backward(gw.to("cuda:0"), xw.to("cuda:0"), xw.to("cuda:0"), p, 1.0)
+    assert torch.equal(gx1.cpu(), gx0.cpu())
+    assert torch.cuda.current_device() == 0
