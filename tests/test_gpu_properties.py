@@ -254,3 +254,34 @@ def test_tensors_on_a_second_device_while_device_0_is_current():
     gx0, _ = F_ee.edge_blend_backward(gw.to("cuda:0"), xw.to("cuda:0"), xw.to("cuda:0"), p, 1.0)
     assert torch.equal(gx1.cpu(), gx0.cpu())
     assert torch.cuda.current_device() == 0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_dataparallel_replicas_use_the_fused_front_end():
+    """The reference wraps its MNIST / Tiny-ImageNet models in nn.DataParallel (experiments_tinyimagenet.py:110): the
+    front end then runs on worker THREADS, one per device, each with its own current device and stream."""
+    import contextlib, io
+    from edge_enhancement_b200 import core
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            with contextlib.redirect_stdout(io.StringIO()):
+                self.front = core.EdgeEnhance(cize=64, r=8, w=1.0, low=38.0, high=76.0, alpha=0.0, sigma=1,
+                                              type_canny='CannyFilter_step125_1')
+            self.conv = torch.nn.Conv2d(3, 4, 3, padding=1)
+
+        def forward(self, x):
+            return self.conv(self.front(x)).mean((1, 2, 3))
+
+    torch.manual_seed(0)
+    net = Net().to("cuda:0")
+    x = torch.rand(16, 3, 64, 64, device="cuda:0")
+    xa = x.clone().requires_grad_()
+    net(xa).sum().backward()
+    dp = torch.nn.DataParallel(net, device_ids=[0, 1])
+    xb = x.clone().requires_grad_()
+    dp(xb).sum().backward()
+    assert torch.allclose(xa.grad, xb.grad, rtol=1e-5, atol=1e-7)
+    with torch.no_grad():
+        assert torch.allclose(net(x), dp(x), rtol=1e-5, atol=1e-6)
