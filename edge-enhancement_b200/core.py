@@ -265,7 +265,7 @@ class HighFreqSuppress(torch.nn.Module):
     """utils/core.py:15-55: square low-pass in the 2-D Fourier domain.  The reference calls
     torch.rfft / torch.irfft (removed in torch 1.8) and hard-codes .cuda(); `_fft_forward` is the
     torch.fft restatement (onesided=False forward, C2R inverse that reads the one-sided half).
-    On CUDA tensors of the reference's shapes (64 px / r 8, 28 px / r 4, 224 px / r 16 or 18) the same operator runs as ONE
+    On CUDA tensors of the reference's shapes (64 px / r 8, 28 px / r 4, 224 px / r 16, 128 px / r 12, 288 px / r 18) the same operator runs as ONE
     kernel per direction (libedge_b200.so: ee_hfs_f32, five small real-DFT products per plane in shared
     memory; 2.3-5x faster than the three cuFFT / elementwise passes) registered as an autograd.Function whose
     backward is the same kernel (the operator is symmetric).  Parity for this module is UNPINNED against

@@ -856,7 +856,9 @@ int ee_add_square_bwd_f32(const float* g, const float* x, const float* stripe, c
 }
 
 int ee_hfs_supported(int N, int r) {
-    return (N == 64 && r == 8) || (N == 28 && r == 4) || (N == 32 && r == 8) || (N == 224 && (r == 16 || r == 18));
+    // the reference's configurations: MNIST 28 / 4, Tiny-ImageNet 64 / 8, ImageNet 224 / 16, fast-AT schedule 128 / 12 and 288 / 18
+    return (N == 64 && r == 8) || (N == 28 && r == 4) || (N == 32 && r == 8) || (N == 224 && r == 16) || (N == 128 && r == 12) ||
+           (N == 288 && r == 18);
 }
 int ee_hfs_f32(const float* x, float* y, const float* add_or_null, int planes, int N, int r, const float* cb, const float* rb,
                const float* w, float gamma, void* stream) {
@@ -873,7 +875,8 @@ int ee_hfs_f32(const float* x, float* y, const float* add_or_null, int planes, i
     if (N == 28 && r == 4) return launch_hfs<28, 4, 16>(a, s);
     if (N == 32 && r == 8) return launch_hfs<32, 8, 8>(a, s);
     if (N == 224 && r == 16) return launch_hfs_rows<224, 16>(a, s);      // ImageNet: row-blocked, one plane per CTA
-    if (N == 224 && r == 18) return launch_hfs_rows<224, 18>(a, s);
+    if (N == 128 && r == 12) return launch_hfs<128, 12, 2>(a, s);          // 2 whole planes per CTA still fit (208 KB)
+    if (N == 288 && r == 18) return launch_hfs_rows<288, 18>(a, s);
     return fail(EE_ERR_UNSUPPORTED, "ee_hfs_f32: no kernel for a %d x %d plane with radius %d (ee_hfs_supported)", N, N, r);
 }
 

@@ -258,8 +258,9 @@ __global__ void __launch_bounds__(256) hfs_kernel(const HfsArgs a) {
 namespace ee {
 
 // -------------------------------------------------------------------------------------------------------------------
-// Large planes (ImageNet 224 px, r = 16 / 18): the plane does not fit in shared memory.  One plane per (persistent) CTA;
-// x is STREAMED through two cp.async row-block buffers of RBK = 16 rows while T (N x NJp) is accumulated block by block;
+// Large planes (the fast-AT schedule of ImageNet/fgsm_imagenet: 128 px / r 12, 224 px / r 16, 288 px / r 18): the plane does not fit
+// in shared memory next to the tables.  One plane per (persistent) CTA;
+// x is STREAMED through two cp.async row-block buffers of RBK = 16 (8 at 288 px, 32 at 128 px) rows while T (N x NJp) is accumulated block by block;
 // D, G, V live in shared memory as above; y is produced row block by row block straight into global memory.
 // A 16-row block only offers 4 x NJp/4 register tiles, so the K range (w) of stage 1 is split over the 8 lanes that share
 // a tile and reduced with an xor-butterfly ((p0+p1)+(p2+p3))+((p4+p5)+(p6+p7)); stage 2 splits its K range (h) over 2
@@ -268,7 +269,7 @@ namespace ee {
 template <int N, int R>
 struct HfsRowsDims {
     using D_ = HfsDims<N, R>;
-    static constexpr int RBK = 16, KS2 = 2;
+    static constexpr int RBK = (N >= 256) ? 8 : (N <= 128 ? 32 : 16), KS2 = 2;     // 288 px: smaller row blocks (227 KB of shared memory)
     static constexpr int KS1 = ((RBK / 4) * (D_::NJp / 4) * 8 <= 256) ? 8 : 4;     // lanes sharing a stage-1 tile
     static constexpr int kFloats = N * D_::JS + N * D_::IS + D_::NIp * D_::NJp     // CB, RB, W
                                    + N * D_::JS + 2 * D_::NIp * D_::NJp           // T (= V), D, G

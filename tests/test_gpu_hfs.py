@@ -11,7 +11,7 @@ from edge_enhancement_b200 import core, functional as F_ee   # noqa: E402
 from oracle import oracle as O                               # noqa: E402
 
 DEV = "cuda:0"
-SUPPORTED = [(64, 8), (28, 4), (32, 8), (224, 16), (224, 18)]
+SUPPORTED = [(64, 8), (28, 4), (32, 8), (224, 16), (128, 12), (288, 18)]
 
 
 def cu(a):

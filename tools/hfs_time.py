@@ -2,7 +2,7 @@ import torch, sys
 sys.path.insert(0, "/root/repo")
 from edge_enhancement_b200 import core
 from tools.tune import timeit
-for B, S, r in ((4096, 64, 8), (256, 64, 8), (512, 224, 16), (32, 224, 16), (16384, 28, 4)):
+for B, S, r in ((4096, 64, 8), (256, 64, 8), (512, 224, 16), (32, 224, 16), (16384, 28, 4), (1024, 128, 12), (256, 288, 18)):
     C = 1 if S == 28 else 3
     h = core.HighFreqSuppress(S, S, r)
     x = torch.rand(B, C, S, S, device="cuda")
