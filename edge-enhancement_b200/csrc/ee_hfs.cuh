@@ -269,12 +269,16 @@ namespace ee {
 template <int N, int R>
 struct HfsRowsDims {
     using D_ = HfsDims<N, R>;
-    static constexpr int RBK = (N >= 256) ? 8 : (N <= 128 ? 32 : 16), KS2 = 2;     // 288 px: smaller row blocks (227 KB of shared memory)
-    static constexpr int KS1 = ((RBK / 4) * (D_::NJp / 4) * 8 <= 256) ? 8 : 4;     // lanes sharing a stage-1 tile
+    // 224 px: HALF planes (112 rows, 102 KB) fit next to the tables, so stage 1 runs like the whole-plane kernel (one 4 x 4
+    // tile per thread, no lane split) on a single buffer; the second half's load is exposed (~1.5 us per plane), the next
+    // plane's first half streams in behind stages 2-5.  288 px: 8-row blocks, double buffered, K range split over lanes.
+    static constexpr bool HALF = (N == 224);
+    static constexpr int RBK = HALF ? N / 2 : ((N >= 256) ? 8 : 16), KS2 = 2, NBUF = HALF ? 1 : 2;
+    static constexpr int KS1 = HALF ? 1 : (((RBK / 4) * (D_::NJp / 4) * 8 <= 256) ? 8 : 4);     // lanes sharing a stage-1 tile
     static constexpr int kFloats = N * D_::JS + N * D_::IS + D_::NIp * D_::NJp     // CB, RB, W
                                    + N * D_::JS + 2 * D_::NIp * D_::NJp           // T (= V), D, G
-                                   + 2 * RBK * D_::XS                             // two x row-block buffers
-                                   + D_::NJp * D_::XS;                            // CB transposed (stage 1)
+                                   + NBUF * RBK * D_::XS                          // x row-block buffer(s)
+                                   + (KS1 > 1 ? D_::NJp * D_::XS : 0);            // CB transposed (lane-split stage 1)
 };
 
 template <int N, int R>
@@ -282,9 +286,10 @@ __global__ void __launch_bounds__(256, 1) hfs_rows_kernel(const HfsArgs a) {
     using D_ = HfsDims<N, R>;
     using Q_ = HfsRowsDims<N, R>;
     constexpr int NJp = D_::NJp, NIp = D_::NIp, NI = D_::NI, NJ = D_::NJ, XS = D_::XS, JS = D_::JS, IS = D_::IS;
-    constexpr int RBK = Q_::RBK, KS1 = Q_::KS1, KS2 = Q_::KS2, N4 = N / 4, NBLK = N / RBK;
+    constexpr int RBK = Q_::RBK, KS1 = Q_::KS1, KS2 = Q_::KS2, NBUF = Q_::NBUF, N4 = N / 4, NBLK = N / RBK;
     static_assert(N % RBK == 0 && N % (4 * KS1) == 0 && N % KS2 == 0, "row blocks and K splits divide the plane");
     static_assert((RBK / 4) * (NJp / 4) * KS1 <= 256, "stage 1 fits one pass of the CTA");
+    static_assert(NBUF == 1 || NBLK % 2 == 0, "double buffering: the next plane's first block lands in buffer 0");
     extern __shared__ __align__(16) float smem_hfs[];
     float* CB = smem_hfs;
     float* RB = CB + N * JS;
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(256, 1) hfs_rows_kernel(const HfsArgs a) {
     // CB transposed, [NJp][XS]: the lanes that split stage 1's K range read x AND the basis at offsets of N/KS1 floats
     // along w (distinct bank groups); with the [w][j] layout their rows would sit 16 or 0 banks apart (4-way conflicts:
     // 43 % of all shared-memory wavefronts in the first version, profiles/r1g_ncu_full_hfs224_first.txt)
-    float* CBt = XB + 2 * RBK * XS;
+    float* CBt = XB + NBUF * RBK * XS;
     const int tid = threadIdx.x;
 
     auto load_block_async = [&](int plane, int blk, int buf) {       // rows [blk*RBK, +RBK) of `plane` -> XB[buf]
@@ -322,19 +327,63 @@ __global__ void __launch_bounds__(256, 1) hfs_rows_kernel(const HfsArgs a) {
         *reinterpret_cast<float4*>(RB + h * IS + 4 * q) = __ldg(reinterpret_cast<const float4*>(a.rb + h * NIp) + q);
     }
     for (int i = tid; i < NIp * NJp / 4; i += 256) reinterpret_cast<float4*>(Wm)[i] = __ldg(reinterpret_cast<const float4*>(a.w) + i);
-    for (int i = tid; i < N * NJp; i += 256) {
-        const int w = i / NJp, j = i - w * NJp;
-        CBt[j * XS + w] = __ldg(a.cb + i);
+    if (KS1 > 1) {
+        for (int i = tid; i < N * NJp; i += 256) {
+            const int w = i / NJp, j = i - w * NJp;
+            CBt[j * XS + w] = __ldg(a.cb + i);
+        }
     }
 
     for (int plane = blockIdx.x; plane < a.planes; plane += gridDim.x) {
         // ---- stage 1: T = x CB, row block by row block; block b+1 (or block 0 of the next plane) streams in meanwhile ----
         for (int blk = 0; blk < NBLK; ++blk) {
             __pipeline_wait_prior(0);
-            __syncthreads();                   // block `blk` is in XB[blk & 1]; the other buffer is free again
-            if (blk + 1 < NBLK) load_block_async(plane, blk + 1, (blk + 1) & 1);
-            else load_block_async(plane + gridDim.x, 0, (blk + 1) & 1);
-            const float* X = XB + (blk & 1) * RBK * XS;
+            __syncthreads();                   // block `blk` is in its buffer; with two buffers the other one is free again
+            constexpr int kNextBuf = 0;
+            (void)kNextBuf;
+            if (NBUF == 2) {
+                if (blk + 1 < NBLK) load_block_async(plane, blk + 1, (blk + 1) & 1);
+                else load_block_async(plane + gridDim.x, 0, (blk + 1) & 1);
+            }
+            const float* X = XB + (NBUF == 2 ? (blk & 1) : 0) * RBK * XS;
+            if constexpr (KS1 == 1) {
+                // one 4 x 4 tile per thread over the whole K range, exactly the whole-plane kernel's stage 1
+                for (int t = tid; t < (RBK / 4) * (NJp / 4); t += 256) {
+                    const int hg = t % (RBK / 4), jg = t / (RBK / 4);
+                    float acc[4][4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
+#pragma unroll 4
+                    for (int w4 = 0; w4 < N4; ++w4) {
+                        float4 xv[4], cv[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(X + (hg + (RBK / 4) * i) * XS + 4 * w4);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) cv[q] = *reinterpret_cast<const float4*>(CB + (4 * w4 + q) * JS + 4 * jg);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float xs[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                acc[i][0] = fmaf(xs[q], cv[q].x, acc[i][0]);
+                                acc[i][1] = fmaf(xs[q], cv[q].y, acc[i][1]);
+                                acc[i][2] = fmaf(xs[q], cv[q].z, acc[i][2]);
+                                acc[i][3] = fmaf(xs[q], cv[q].w, acc[i][3]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<float4*>(T + (blk * RBK + hg + (RBK / 4) * i) * JS + 4 * jg) =
+                            make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                }
+                __syncthreads();               // every thread is done with the single buffer: refill it
+                if (blk + 1 < NBLK) load_block_async(plane, blk + 1, 0);
+                else load_block_async(plane + gridDim.x, 0, 0);
+                continue;
+            }
             const int ks = tid % KS1;
             const bool tile_ok = (tid / KS1) < (RBK / 4) * (NJp / 4);      // lanes without a tile still take part in the shuffles
             const int tile = tile_ok ? tid / KS1 : 0;

@@ -248,8 +248,9 @@ def hfs(x, r, add=None):
     y = np.empty_like(x)
     # summation trees of the kernel that serves this shape (ee_hfs.cuh): whole-plane kernel 1 / 1; row-blocked kernel for
     # large planes: stage 1 over 8 lanes (4 when 2r-1 > 32), stage 2 over 2 lanes
-    rbk = 8 if N >= 256 else (32 if N <= 128 else 16)
-    ks1, ks2 = (1, 1) if N <= 128 else ((8 if (rbk // 4) * (cb.shape[1] // 4) * 8 <= 256 else 4), 2)
+    # 224 px: half-plane blocks, no lane split in stage 1; 288 px: 8-row blocks with the lane split
+    rbk = 8 if N >= 256 else 16
+    ks1, ks2 = (1, 1) if N <= 128 else ((1 if N == 224 else (8 if (rbk // 4) * (cb.shape[1] // 4) * 8 <= 256 else 4)), 2)
     _chk(lib().ee_oracle_hfs(_p(x), _p(y), _p(add), x.size // (N * N), N, r, _p(cb), _p(rb), _p(w), gamma, ks1, ks2))
     return y
 
