@@ -19,7 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 
-// The library is compiled as five translation units from this one source (edge-enhancement_b200/_build.py, in
+// The library is compiled as five translation units from this one source (edge_enhancement_b200/_build.py, in
 // parallel): -DEE_PART=1 the C ABI + elementwise kernels, 2 / 3 the step125 forward / backward kernel families,
 // 4 / 5 the Canny + BPDA forward / backward families.  EE_PART undefined (0) builds everything in one unit.
 #ifndef EE_PART

@@ -3,7 +3,7 @@
  *
  * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
- * this file's shared object.  The product (edge-enhancement_b200/) never does and has no
+ * this file's shared object.  The product (edge_enhancement_b200/) never does and has no
  * CPU fallback.
  *
  * What it is: a plain-C, whole-image, full-plane restatement of the reference's algorithm
