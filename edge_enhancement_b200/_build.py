@@ -12,12 +12,12 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libedge_b200.so")
 SOURCES = ["ee_capi.cu"]
-HEADERS = ["ee_device.cuh", "ee_edge_step125.cuh", "ee_edge_canny.cuh", "ee_edge_fast.cuh", "ee_edge_canny_fast.cuh", "ee_attack.cuh", "ee_square.cuh", "ee_hfs.cuh", "ee_edge_cluster.cuh", "ee_edge_tiles.cuh", "ee_edge_canny_tiles.cuh",
+HEADERS = ["ee_device.cuh", "ee_edge_step125.cuh", "ee_edge_canny.cuh", "ee_edge_fast.cuh", "ee_edge_canny_fast.cuh", "ee_attack.cuh", "ee_square.cuh", "ee_hfs.cuh", "ee_edge_cluster.cuh", "ee_edge_tiles.cuh", "ee_edge_canny_tiles.cuh", "ee_edge_stream.cuh",
            os.path.join("..", "..", "include", "edge_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-std=c++17", "-lineinfo",
+    "-O3", "-std=c++17", "-lineinfo", "-diag-suppress", "177",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
     "-Xcompiler", "-fPIC", "-shared",
 ]
@@ -38,7 +38,7 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-PARTS = (1, 2, 3, 4, 5)      # ee_capi.cu is compiled once per kernel family (-DEE_PART=k), in parallel, then linked
+PARTS = (1, 2, 3, 4, 5, 6)      # ee_capi.cu is compiled once per kernel family (-DEE_PART=k), in parallel, then linked
 
 
 def build(force=False, verbose=False, extra_flags=()):

@@ -7,6 +7,7 @@
 #include "ee_edge_cluster.cuh"
 #include "ee_edge_tiles.cuh"
 #include "ee_edge_canny_tiles.cuh"
+#include "ee_edge_stream.cuh"
 #include "ee_edge_fast.cuh"
 #include "ee_edge_step125.cuh"
 #include "ee_square.cuh"
@@ -19,9 +20,10 @@
 #include <cstdlib>
 #include <cstring>
 
-// The library is compiled as five translation units from this one source (edge_enhancement_b200/_build.py, in
+// The library is compiled as six translation units from this one source (edge_enhancement_b200/_build.py, in
 // parallel): -DEE_PART=1 the C ABI + elementwise kernels, 2 / 3 the step125 forward / backward kernel families,
-// 4 / 5 the Canny + BPDA forward / backward families.  EE_PART undefined (0) builds everything in one unit.
+// 4 / 5 the Canny + BPDA forward / backward families, 6 the row-streaming Canny + BPDA kernels for wide images.
+// EE_PART undefined (0) builds everything in one unit.
 #ifndef EE_PART
 #define EE_PART 0
 #endif
@@ -39,6 +41,7 @@ int fwd_step125(ee::EdgeArgs& a, const EEParams* p, int B, bool blend, bool vec_
 int bwd_step125(ee::EdgeArgs& a, const EEParams* p, int B, bool blend, bool vec_ok, bool nhwc, cudaStream_t s);
 int fwd_canny(ee::EdgeArgs& a, const EEParams* p, int B, bool blend, bool vec_ok, bool nhwc, cudaStream_t s);
 int bwd_canny(ee::EdgeArgs& a, const EEParams* p, int B, bool blend, bool vec_ok, bool nhwc, cudaStream_t s);
+int canny_stream(ee::EdgeArgs& a, const EEParams* p, int B, bool blend, bool bwd, cudaStream_t s);
 }  // namespace ee_shared
 
 namespace {
@@ -253,6 +256,21 @@ void plan_tiles(int H, int W, Launch& L, int max_tile = 56, int planes = 3) {
 bool canny_tiles_ok(const ee::EdgeArgs& a, bool vec_ok, int th_forced) {
     return fast_eligible(a, vec_ok) && a.W > 128 && a.H % 4 == 0 && a.H >= 16 && th_forced == 0 && g_staging.load() != 3 &&
            a.has_low && a.has_high && a.hyst;
+}
+
+// Row-streaming kernels (ee_edge_stream.cuh): full-width bands, hysteresis mode, C == 3.  Measured on B200
+// (profiles/r2a_stream_sweep.txt, 3x224x224, us streaming / tiles): backward B = 512: 440 / 644, 128: 132 / 167, 64: 78 / 87,
+// 32: 55 / 44; forward 512: 229 / 221, 128: 79 / 64.  So by default they take the backward of batches with >= 64 * 224 image
+// rows; staging 8 forces them for every eligible shape and direction (tests), staging 9 disables them.
+bool canny_stream_ok(const ee::EdgeArgs& a, bool vec_ok, bool nhwc, bool bwd) {
+    const int st = g_staging.load();
+    if (st == 9 || st == 1 || st == 3 || st == 4 || nhwc) return false;
+    if (!(fast_eligible(a, vec_ok) && a.C == 3 && a.has_low && a.has_high && a.hyst && a.W >= 8 && a.W <= 1024 && a.H >= 2)) return false;
+    if (st == 8) return true;
+    // a role's warps cover W / 4 column groups: 224 px fills 56 of 64 lanes, 288 px only 72 of 96 (and its 192-thread CTAs fit
+    // twice per SM) -- measured 516 us streaming vs 477 us tiles at 256x3x288x288, so such widths stay on the tiles
+    const int gx = a.W / 4, lanes = ((gx + 31) / 32) * 32;
+    return bwd && a.W > 128 && 8 * gx >= 7 * lanes && (long long)a.B * a.H >= 64LL * 224;
 }
 
 // Tensor map of x as [B*C, H, W] fp32 with a (64 + 8) x (TH + 8) x 1 box for the TMA-staged tile kernel.  The driver
@@ -482,6 +500,7 @@ int ee_shared::fwd_canny(ee::EdgeArgs& a, const EEParams* p, int B, bool blend, 
         fill_fast(f, a, L);
         EE_DISPATCH_FAST_NHWC(ee::edge_fwd_canny_fast, L, B, f, s, "edge_fwd_canny_fast_nhwc");
     }
+    if (canny_stream_ok(a, vec_ok, nhwc, false)) return ee_shared::canny_stream(a, p, B, blend, false, s);
     if (canny_tiles_ok(a, vec_ok, g_th_fwd.load())) {
         // wide images, hysteresis mode: chunk-aligned 56 x 56 tiles (ee_edge_canny_tiles.cuh)
         plan_tiles(H, W, L, 56, 3);
@@ -597,6 +616,7 @@ int ee_shared::bwd_canny(ee::EdgeArgs& a, const EEParams* p, int B, bool blend, 
         fill_fast(f, a, L);
         EE_DISPATCH_FAST_NHWC(ee::edge_bwd_canny_fast, L, B, f, s, "edge_bwd_canny_fast_nhwc");
     }
+    if (a.g_x != nullptr && canny_stream_ok(a, vec_ok, nhwc, true)) return ee_shared::canny_stream(a, p, B, blend, true, s);
     if (canny_tiles_ok(a, vec_ok, g_th_bwd.load())) {
         // wide images, hysteresis mode: chunk-aligned 48 x 48 tiles with an 8-pixel halo (ee_edge_canny_tiles.cuh)
         plan_tiles(H, W, L, 48, 4);
@@ -632,6 +652,67 @@ int ee_shared::bwd_canny(ee::EdgeArgs& a, const EEParams* p, int B, bool blend, 
     a.TH = L.TH; a.tiles_per_img = L.tiles; a.GX = L.GX; a.RY = L.RY;
     if (blend) EE_DISPATCH(ee::edge_bwd_canny_kernel, true, L, B, a, s, "edge_bwd_canny");
     else EE_DISPATCH(ee::edge_bwd_canny_kernel, false, L, B, a, s, "edge_bwd_canny");
+}
+#endif
+
+#if EE_HAS(6)
+namespace {
+template <typename K>
+int launch_stream(K kernel, const ee::StreamArgs& sa, unsigned grid, int threads, size_t smem, cudaStream_t s, const char* name) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+    }
+    kernel<<<grid, threads, smem, s>>>(sa);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, name);
+    return EE_OK;
+}
+template <bool BLEND, int VAR, bool BWD>
+int stream_by_width(const ee::StreamArgs& sa, int W, unsigned grid, int threads, size_t smem, cudaStream_t s) {
+    const char* name = BWD ? "edge_bwd_canny_stream" : "edge_fwd_canny_stream";
+    // ImageNet sizes with the width as a compile-time constant; <.., WT, max threads, min CTAs per SM>
+    if (W == 224) return launch_stream(ee::edge_canny_stream<3, BLEND, VAR, BWD, 224, 128, BWD ? 4 : 6>, sa, grid, threads, smem, s, name);
+    if (W == 288) return launch_stream(ee::edge_canny_stream<3, BLEND, VAR, BWD, 288, 192, BWD ? 2 : 4>, sa, grid, threads, smem, s, name);
+    if (threads <= 64) return launch_stream(ee::edge_canny_stream<3, BLEND, VAR, BWD, 0, 64, 8>, sa, grid, threads, smem, s, name);
+    if (threads <= 128) return launch_stream(ee::edge_canny_stream<3, BLEND, VAR, BWD, 0, 128, 4>, sa, grid, threads, smem, s, name);
+    if (threads <= 256) return launch_stream(ee::edge_canny_stream<3, BLEND, VAR, BWD, 0, 256, 2>, sa, grid, threads, smem, s, name);
+    return launch_stream(ee::edge_canny_stream<3, BLEND, VAR, BWD, 0, 512, 1>, sa, grid, threads, smem, s, name);
+}
+}  // namespace
+
+int ee_shared::canny_stream(ee::EdgeArgs& a, const EEParams* p, int B, bool blend, bool bwd, cudaStream_t s) {
+    const int H = a.H, W = a.W, GX = W / 4;
+    ee::StreamArgs sa;
+    Launch L;
+    L.vec = 4; L.TH = H; L.tiles = 1; L.GX = GX; L.RY = 1; L.TW = W; L.tiles_x = 1; L.planeW = W; L.halo = 0;
+    fill_fast(sa.f, a, L);
+    const int threads = 2 * (((GX + 31) / 32) * 32);          // front + back role
+    const int rows = 3 + (blend ? 3 : 0) + (bwd ? (blend ? 3 : 1) : 0);
+    const size_t smem = ee::stream_smem_bytes(W, rows, bwd);
+    if (smem > (size_t)kMaxSmem) return fail(EE_ERR_TOO_LARGE, "row-streaming kernel: a %d-column row ring does not fit in shared memory", W);
+    // band height: about two bands per resident-CTA slot (4 CTAs per SM), but never shorter than 28 rows -- a band warms
+    // its pipeline up on 2 * halo = 8 / 12 extra rows; measured flat between 56 and 224 rows at B = 512
+    int bh = bwd ? g_th_bwd.load() : g_th_fwd.load();
+    if (bh <= 0) {
+        const int slots = 148 * 4;
+        int bands = (2 * slots + B - 1) / B;
+        if (bands < 1) bands = 1;
+        bh = (H + bands - 1) / bands;
+        if (bh < 28) bh = 28;
+    }
+    if (bh > H) bh = H;
+    sa.BH = bh;
+    sa.bands_per_img = (H + bh - 1) / bh;
+    const long long grid = (long long)B * sa.bands_per_img;
+    if (grid > 0x7fffffffLL) return fail(EE_ERR_TOO_LARGE, "too many bands");
+    const bool cn = (p->variant == EE_VARIANT_CANNY);
+    if (bwd) {
+        if (blend) return cn ? stream_by_width<true, 1, true>(sa, W, (unsigned)grid, threads, smem, s) : stream_by_width<true, 2, true>(sa, W, (unsigned)grid, threads, smem, s);
+        return cn ? stream_by_width<false, 1, true>(sa, W, (unsigned)grid, threads, smem, s) : stream_by_width<false, 2, true>(sa, W, (unsigned)grid, threads, smem, s);
+    }
+    if (blend) return cn ? stream_by_width<true, 1, false>(sa, W, (unsigned)grid, threads, smem, s) : stream_by_width<true, 2, false>(sa, W, (unsigned)grid, threads, smem, s);
+    return cn ? stream_by_width<false, 1, false>(sa, W, (unsigned)grid, threads, smem, s) : stream_by_width<false, 2, false>(sa, W, (unsigned)grid, threads, smem, s);
 }
 #endif
 

@@ -61,7 +61,7 @@ VARIANT_MODES = [("step125", "hyst")] + [(v, m) for v in ("canny", "bpda") for m
 
 # staging knob of ee_set_tuning: 0 = auto, 1 = generic kernels only, 3 = strip kernels instead of the chunk-aligned
 # tiles for wide images, 4 = tuned kernels also for wide images, 6 / 7 = always / never stage x tiles by TMA tensor copies
-@pytest.mark.parametrize("staging", [0, 1, 3, 4, 6, 7])
+@pytest.mark.parametrize("staging", [0, 1, 3, 4, 6, 7, 8, 9])
 @pytest.mark.parametrize("strip", [0, 1, 3, 7])
 @pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("variant,mode", VARIANT_MODES)

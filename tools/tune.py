@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--variant", default="step125")
     ap.add_argument("--ths", default="0,4,8,16,32,64,112,224")
     ap.add_argument("--channels-last", action="store_true")
+    ap.add_argument("--staging", type=int, default=0, help="ee_set_tuning staging knob (8 / 9 = always / never row-streaming)")
     args = ap.parse_args()
     L = _lib.load()
     with contextlib.redirect_stdout(io.StringIO()):
@@ -47,7 +48,7 @@ def main():
         for th in [int(t) for t in args.ths.split(",")]:
             if th > S:
                 continue
-            L.ee_set_tuning(th, th, 0)
+            L.ee_set_tuning(th, th, args.staging)
             tf = timeit(lambda: F.edge_blend(x, base, p, 1.0, out=o1))
             tb = timeit(lambda: F.edge_blend_backward(g, x, base, p, 1.0, g_x=o2, g_base=o3))
             print("%-8s B=%5d C=%d side=%3d TH=%3d | fwd %7.1f us %6.0f GB/s | bwd %7.1f us %6.0f GB/s"
