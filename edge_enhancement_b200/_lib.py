@@ -5,11 +5,13 @@ this module raises; if a call fails, `check` raises RuntimeError with ee_last_er
 """
 import ctypes
 import os
+import threading
 
 from . import _build
 
 EE_VARIANT_STEP125, EE_VARIANT_CANNY, EE_VARIANT_BPDA = 0, 1, 2
 EE_LAYOUT_NCHW = 0
+EE_FLAG_NAN_COMPAT = 1
 
 
 class EEParams(ctypes.Structure):
@@ -18,7 +20,7 @@ class EEParams(ctypes.Structure):
                 ("gauss", ctypes.c_float * 9), ("sobel", ctypes.c_float * 9),
                 ("alpha", ctypes.c_float), ("low_thr", ctypes.c_float), ("high_thr", ctypes.c_float),
                 ("has_low", ctypes.c_int32), ("has_high", ctypes.c_int32),
-                ("hysteresis", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("hysteresis", ctypes.c_int32), ("flags", ctypes.c_int32)]
 
 
 _vp, _i, _i64, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
@@ -36,6 +38,9 @@ SIGNATURES = {
     "ee_free_at_step_f32": [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _vp],
     "ee_cw_linf_step_f32": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _vp],
     "ee_pgd_l2_step_f32": [_vp, _vp, _vp, _vp, _i, _i64, _f, _f, _vp],
+    "ee_gf_blend_fwd_f32": [_vp, _vp, _vp, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_float), _f, _vp],
+    "ee_gf_blend_bwd_f32": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_float), _f, _vp],
+    "ee_edge_pgd_iteration_f32": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _pp, _f, _f, _f, _vp],
     "ee_add_clamp_f32": [_vp, _vp, _vp, _i64, _f, _f, _vp],
     "ee_avmixup_mix_f32": [_vp, _vp, _vp, _vp, _i, _i64, _f, _vp],
     "ee_to_compare_fwd_f32": [_vp, _vp, _i64, _f, _vp],
@@ -55,6 +60,7 @@ SIGNATURES = {
 _RESTYPE = {"ee_last_error": ctypes.c_char_p, "ee_aux_bytes": ctypes.c_size_t}
 
 _LIB = None
+_LOCK = threading.Lock()
 
 
 def lib_path():
@@ -62,19 +68,24 @@ def lib_path():
 
 
 def load():
-    """Load (building first if the .so is missing) and type every exported symbol."""
+    """Load (building first if the .so is missing) and type every exported symbol.  Thread-safe: DataParallel
+    worker threads and autograd engine threads may race for the first call."""
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = os.environ.get("EDGE_B200_LIB") or _build.LIB     # env override: A/B testing of kernel builds
-    if not os.path.exists(path):
-        path = _build.build()            # raises if nvcc is unavailable: no silent fallback
-    L = ctypes.CDLL(path)
-    for name, argtypes in SIGNATURES.items():
-        fn = getattr(L, name)            # AttributeError if the library lacks a declared symbol
-        fn.argtypes = argtypes
-        fn.restype = _RESTYPE.get(name, ctypes.c_int)
-    _LIB = L
+    with _LOCK:
+        if _LIB is not None:
+            return _LIB
+        # EDGE_B200_LIB is a TEST-ONLY override (A/B timing of two kernel builds): it loads whatever .so it names
+        path = os.environ.get("EDGE_B200_LIB") or _build.LIB
+        if not os.path.exists(path):
+            path = _build.build()            # raises if nvcc is unavailable: no silent fallback
+        L = ctypes.CDLL(path)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(L, name)            # AttributeError if the library lacks a declared symbol
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPE.get(name, ctypes.c_int)
+        _LIB = L
     return L
 
 

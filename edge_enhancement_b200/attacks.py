@@ -1,10 +1,12 @@
 """Drop-in for the reference's ``utils/attacks.py`` -- same names and call signatures.
 
-Every attack keeps the reference's control flow (random start, model forward, loss,
-``torch.autograd.grad``) on stock PyTorch -- the CNN is outside the product -- and replaces the
-update lines (``x + a*sign(g)`` / eps-ball projection / [0,1] clamp; 6-14 eager kernels in the
-reference) with ONE fused CUDA kernel from libedge_b200.so.  Random numbers are drawn with the same
-torch calls in the same order as the reference, so a seeded run follows the same trajectory.
+The reference spells the same L-inf loop out eleven times (PGD :19-27, targeted_PGD :48-54, targeted_PGD_trick :78-84,
+ALP :252-259, targeted_ALP :293-300 / :313-320, tar_alp_imagenet :348-355, Trades :408-416, AVmixup :458-468 / :497-507)
+and its update lines cost 6-14 eager kernels per iteration.  Here every attack is a thin description -- start point,
+loss, sign of the step -- handed to ONE loop (`_linf_attack`) whose update is ONE fused CUDA kernel
+(libedge_b200.so: ee_pgd_linf_step_f32).  The model forward / backward in between stays on stock PyTorch: the CNN is
+outside the product.  Random numbers are drawn with the same torch / numpy calls in the same order as the reference, so
+a seeded run follows the same trajectory.
 """
 import numpy as np
 import torch
@@ -14,33 +16,85 @@ import torch.nn.functional as F
 from . import functional as F_ee
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# the pieces every attack is assembled from
+# --------------------------------------------------------------------------------------------------------------------
+def _ce_sum(labels):
+    return lambda logits: F.cross_entropy(logits, labels, reduction='sum')
+
+
+def _ce_mean(labels):
+    return lambda logits: F.cross_entropy(logits, labels)
+
+
+def _linf_attack(model, loss_of_logits, inputs, x, num_steps, step_signed, epsilon):
+    """num_steps times: g = d loss(model(x)) / dx ; x = clamp(min(max(x + step_signed*sign(g), inputs-eps), inputs+eps), 0, 1).
+    A positive step ascends the loss (untargeted), a negative one descends towards the target labels inside the loss."""
+    anchor = inputs.detach()
+    for _ in range(num_steps):
+        x.requires_grad_()
+        with torch.enable_grad():
+            loss = loss_of_logits(model(x))
+        grad = torch.autograd.grad(loss, [x])[0]
+        x = F_ee.pgd_linf_step(x.detach(), grad.detach(), anchor, step_signed, epsilon, 0.0, 1.0)
+    return x
+
+
 def _random_start(x, epsilon):
-    """utils/attacks.py:15-17: x + U(-eps, eps), clamped to [0, 1].  The noise is the reference's own draw
+    """x + U(-eps, eps) clamped to [0, 1] (utils/attacks.py:15-17).  The noise is the reference's own draw
     (zeros_like(x).uniform_ advances the generator identically); add + clamp are one kernel."""
     return F_ee.add_clamp(x, torch.empty_like(x).uniform_(-epsilon, epsilon), 0.0, 1.0)
 
 
-def _linf_step(x, grad, inputs, step_signed, epsilon):
-    """utils/attacks.py:25-27 fused: clamp(min(max(x + a*sign(g), x0-eps), x0+eps), 0, 1)."""
-    return F_ee.pgd_linf_step(x.detach(), grad.detach(), inputs.detach(), step_signed, epsilon, 0.0, 1.0)
+def _small_randn_start(x_natural):
+    """x + 0.001 * randn (ALP / TRADES).  The reference hard-codes device='cuda' (attacks.py:250, :291, :311, :383, :406);
+    the draw follows the input's device instead."""
+    return x_natural.detach() + 0.001 * torch.randn(x_natural.shape, device=x_natural.device).detach()
 
 
-# Projected Gradient Descent -- utils/attacks.py:12-29
-def PGD(model, args, inputs, targets, num_steps, step_size):
+def _random_targets(labels, n_class, device):
+    """A uniformly random label different from the true one (CPU randint, like the reference: attacks.py:35-36)."""
+    offset = torch.randint(low=1, high=n_class, size=labels.shape).to(device)
+    return torch.fmod(labels + offset, n_class)
+
+
+def _start(args, inputs):
     x = inputs.detach()
+    return _random_start(x, args.epsilon) if args.random else x
 
+
+# --------------------------------------------------------------------------------------------------------------------
+# utils/attacks.py:12-86 -- PGD and its targeted variants
+# --------------------------------------------------------------------------------------------------------------------
+def PGD(model, args, inputs, targets, num_steps, step_size):
+    return _linf_attack(model, _ce_sum(targets), inputs, _start(args, inputs), num_steps, step_size, args.epsilon)
+
+
+def targeted_PGD(model, args, inputs, labels, num_steps, step_size, nclass, device):
+    target_labels = _random_targets(labels, nclass, device)          # drawn before the random start, like :35-47
+    x = _linf_attack(model, _ce_sum(target_labels), inputs, _start(args, inputs), num_steps, -step_size, args.epsilon)
+    return x, target_labels
+
+
+def targeted_PGD_trick(model, args, inputs, labels, num_steps, step_size, nclass, device):
+    """As targeted_PGD, but the random start is skipped with probability args.prob_start_from_clean (:74-77; this start
+    keeps the reference's own draws -- torch.Tensor(shape).uniform_ on the CPU, then one torch.rand([]))."""
+    target_labels = _random_targets(labels, nclass, device)
+    x = inputs.detach()
     if args.random:
-        x = _random_start(x, args.epsilon)
+        noise = torch.Tensor(x.shape).uniform_(-args.epsilon, args.epsilon).to(device)
+        from_noise = torch.gt(torch.rand([]), args.prob_start_from_clean).type(torch.float32).to(device)
+        x = torch.clamp(x + from_noise * noise, 0.0, 1.0)
+    x = _linf_attack(model, _ce_sum(target_labels), inputs, x, num_steps, -step_size, args.epsilon)
+    return x, target_labels
 
-    for i in range(num_steps):
-        x.requires_grad_()
-        with torch.enable_grad():
-            logits = model(x)
-            loss = F.cross_entropy(logits, targets, reduction='sum')
-        grad = torch.autograd.grad(loss, [x])[0]
-        x = _linf_step(x, grad, inputs, step_size, args.epsilon)
 
-    return x
+def tar_alp_imagenet(model, args, inputs, labels, num_steps, step_size, device):
+    """utils/attacks.py:337-357: targeted, 1000 classes, start x + 0.001 * randn (a CPU draw moved to `device`)."""
+    target_labels = _random_targets(labels, 1000, device)
+    x = inputs.detach() + 0.001 * torch.randn(inputs.shape).to(device).detach()
+    x = _linf_attack(model, _ce_sum(target_labels), inputs, x, num_steps, -step_size, args.epsilon)
+    return x, target_labels
 
 
 class GraphedPGD:
@@ -82,8 +136,7 @@ class GraphedPGD:
     def _iteration(self):
         x = self.x.detach().requires_grad_()
         with torch.enable_grad():
-            logits = self.model(x)
-            loss = self.loss_fn(logits, self.y)
+            loss = self.loss_fn(self.model(x), self.y)
         grad = torch.autograd.grad(loss, [x])[0]
         F_ee.pgd_linf_step(self.x, grad, self.x0, self.step_size, self.args.epsilon, 0.0, 1.0, out=self.x)
 
@@ -101,171 +154,113 @@ class GraphedPGD:
         return self.x.clone()
 
 
-# targeted PGD with a random target label -- utils/attacks.py:33-56
-def targeted_PGD(model, args, inputs, labels, num_steps, step_size, nclass, device):
-    x = inputs.detach()
-    label_offset = torch.randint(low=1, high=nclass, size=labels.shape).to(device)
-    target_labels = torch.fmod(labels + label_offset, nclass)
-
-    if args.random:
-        x = _random_start(x, args.epsilon)
-
-    for i in range(num_steps):
-        x.requires_grad_()
-        with torch.enable_grad():
-            logits = model(x)
-            loss = F.cross_entropy(logits, target_labels, reduction='sum')
-        grad = torch.autograd.grad(loss, [x])[0]
-        x = _linf_step(x, grad, inputs, -step_size, args.epsilon)
-
-    return x, target_labels
-
-
-# utils/attacks.py:59-86
-def targeted_PGD_trick(model, args, inputs, labels, num_steps, step_size, nclass, device):
-    x = inputs.detach()
-    label_offset = torch.randint(low=1, high=nclass, size=labels.shape).to(device)
-    target_labels = torch.fmod(labels + label_offset, nclass)
-
-    if args.random:
-        init_start = torch.Tensor(x.shape).uniform_(-args.epsilon, args.epsilon).to(device)
-        start_from_noise_index = torch.gt(torch.rand([]), args.prob_start_from_clean).type(torch.float32).to(device)
-        x = x + start_from_noise_index * init_start
-        x = torch.clamp(x, 0.0, 1.0)
-
-    for i in range(num_steps):
-        x.requires_grad_()
-        with torch.enable_grad():
-            logits = model(x)
-            loss = F.cross_entropy(logits, target_labels, reduction='sum')
-        grad = torch.autograd.grad(loss, [x])[0]
-        x = _linf_step(x, grad, inputs, -step_size, args.epsilon)
-
-    return x, target_labels
-
-
-# utils/attacks.py:89-106
+# --------------------------------------------------------------------------------------------------------------------
+# utils/attacks.py:89-128 -- label smoothing, FGSM
+# --------------------------------------------------------------------------------------------------------------------
 class LabelSmoothLoss(torch.nn.Module):
+    """Cross-entropy against (1 - smoothing) on the label and smoothing / (n - 1) elsewhere (:89-101)."""
+
     def __init__(self, smoothing=0.0):
         super(LabelSmoothLoss, self).__init__()
         self.smoothing = smoothing
 
     def forward(self, input, target):
-        log_prob = F.log_softmax(input, dim=-1)
-        weight = input.new_ones(input.size()) * self.smoothing / (input.size(-1) - 1.)
-        weight.scatter_(-1, target.unsqueeze(-1), (1. - self.smoothing))
-        loss = (-weight * log_prob).sum(dim=-1).mean()
-        return loss
+        # the off-label weight is evaluated in the tensor's dtype, (1 * smoothing) / (n - 1), like the reference (:97)
+        soft = input.new_ones(input.size()) * self.smoothing / (input.size(-1) - 1.)
+        soft.scatter_(-1, target.unsqueeze(-1), 1. - self.smoothing)
+        return (-soft * F.log_softmax(input, dim=-1)).sum(dim=-1).mean()
 
 
 def compute_loss_and_error(logits, label, label_smoothing=0.):
-    loss_function = LabelSmoothLoss(label_smoothing)
-    loss = loss_function(logits, label.long())
-    return loss
+    return LabelSmoothLoss(label_smoothing)(logits, label.long())
 
 
-# FGSM -- utils/attacks.py:110-128 (single signed step + clamp, no eps projection)
 def FGSM(model, inputs, target, targeted=False, step_size=0.007):
-    x = inputs.detach()
-    x.requires_grad_()
-
+    """One signed step and the [0, 1] clamp, no eps projection (:110-128)."""
+    x = inputs.detach().requires_grad_()
     with torch.enable_grad():
-        logits = model(x)
-        loss = F.cross_entropy(logits, target, reduction='sum')
-
+        loss = F.cross_entropy(model(x), target, reduction='sum')
     grad = torch.autograd.grad(loss, [x])[0]
-    step = -step_size if targeted else step_size
-    return F_ee.fgsm_step(x.detach(), grad.detach(), step, 0.0, 1.0)
+    return F_ee.fgsm_step(x.detach(), grad.detach(), -step_size if targeted else step_size, 0.0, 1.0)
 
 
 def predict_from_logits(logits, dim=1):
     return logits.max(dim=dim, keepdim=False)[1]
 
 
-# CW with Linf norm -- utils/attacks.py:136-232
+# --------------------------------------------------------------------------------------------------------------------
+# utils/attacks.py:136-232 -- CW with L-inf norm (evaluation only)
+# --------------------------------------------------------------------------------------------------------------------
+def _as_batch(t, dims):
+    """`t[index]` with a 0-dim index drops the batch axis (one surviving sample): put it back (:150-152, :157)."""
+    return t if t.dim() == dims else t.unsqueeze(0)
+
+
+def _cw_margin_loss(outputs, one_hot_y, one_hot_target):
+    """-(sum relu(correct - wrong + 50)) with `wrong` = the target logit, or the best other logit (:190-203)."""
+    correct = torch.sum(one_hot_y * outputs, dim=1)
+    if one_hot_target is not None:
+        wrong = torch.sum(one_hot_target * outputs, dim=1)
+    else:
+        wrong, _ = torch.max((1 - one_hot_y) * outputs - 1e4 * one_hot_y, dim=1)
+    return -torch.sum(F.relu(correct - wrong + 50))
+
+
+def _one_hot(labels, n_class, device):
+    oh = torch.zeros(labels.size(0), n_class).to(device)
+    oh[torch.arange(labels.size(0)), labels] = 1
+    return oh
+
+
 def CWLinfAttack(x, y, model, magnitude, previous_p, max_eps, max_iters=20, target=None, _type='linf',
                  n_class=10, cur_device=None):
+    """Attacks only the samples the model still classifies correctly; the others are returned untouched.  Per iteration
+    the reference's four projection / clamp lines (:212-222, hard-coded step 0.00392) are ONE fused kernel.  Returns
+    (adv, perturbation); with `previous_p` the perturbation accumulates and the second projection is around x - previous_p."""
     model.eval()
     device = cur_device
-    x = x.to(device)
-    y = y.to(device)
+    x, y = x.to(device), y.to(device)
     if target is not None:
         target = target.to(device)
     adv = x.clone()
-    pred = predict_from_logits(model(x))
-    if torch.sum((pred == y)).item() == 0:
+    alive = predict_from_logits(model(x)) == y
+    if torch.sum(alive).item() == 0:
         return adv, previous_p
-    ind_non_suc = (pred == y).nonzero().squeeze()
-    x = x[ind_non_suc]
-    y = y[ind_non_suc]
-    target = target[ind_non_suc]
-    x = x if len(x.shape) == 4 else x.unsqueeze(0)
-    y = y if len(y.shape) == 1 else y.unsqueeze(0)
-    target = target if len(target.shape) == 1 else target.unsqueeze(0)
+    idx = alive.nonzero().squeeze()
+    x, y = _as_batch(x[idx], 4), _as_batch(y[idx], 1)
+    target = _as_batch(target[idx], 1)                       # like the reference, `target` is required in practice (:149)
+    carried = None
     if previous_p is not None:
-        previous_p = previous_p.to(device)
-        previous_p_c = previous_p.clone()
-        previous_p = previous_p[ind_non_suc]
-        previous_p = previous_p if len(previous_p.shape) == 4 else previous_p.unsqueeze(0)
+        carried = previous_p.to(device).clone()
+        previous_p = _as_batch(carried[idx], 4)
 
-    one_hot_y = torch.zeros(y.size(0), n_class).to(device)
-    one_hot_y[torch.arange(y.size(0)), y] = 1
-
-    # random start
-    x.requires_grad = True
+    one_hot_y = _one_hot(y, n_class, device)
+    one_hot_target = _one_hot(target, n_class, device) if target is not None else None
     mag = magnitude.item() if isinstance(magnitude, torch.Tensor) else magnitude
-    rand_perturb = torch.FloatTensor(x.shape).uniform_(-mag, mag)
-    rand_perturb = rand_perturb.to(device)
-    adv_imgs = x + rand_perturb
-    adv_imgs.clamp_(0, 1)
+    x_d = x.detach()
+    adv_imgs = (x_d + torch.FloatTensor(x.shape).uniform_(-mag, mag).to(device)).clamp_(0, 1)       # random start (:166-176)
+    centre = x_d - previous_p if previous_p is not None else x_d
+    min_x, max_x = (centre - max_eps).detach(), (centre + max_eps).detach()
 
-    if previous_p is not None:
-        max_x = x - previous_p + max_eps
-        min_x = x - previous_p - max_eps
-    else:
-        max_x = x + max_eps
-        min_x = x - max_eps
-
-    max_iters = int(max_iters)
-    x_d, min_d, max_d = x.detach(), min_x.detach(), max_x.detach()
-
-    with torch.enable_grad():
-        for _iter in range(max_iters):
-            if not adv_imgs.requires_grad:
-                adv_imgs.requires_grad_()
-            outputs = model(adv_imgs)
-
-            correct_logit = torch.sum(one_hot_y * outputs, dim=1)
-            if target is not None:
-                wrong_logit = torch.zeros(target.size(0), n_class).to(device)
-                wrong_logit[torch.arange(target.size(0)), target] = 1
-                wrong_logit = torch.sum(wrong_logit * outputs, dim=1)
-            else:
-                wrong_logit, _ = torch.max((1 - one_hot_y) * outputs - 1e4 * one_hot_y, dim=1)
-
-            loss = -torch.sum(F.relu(correct_logit - wrong_logit + 50))
-            grads = torch.autograd.grad(loss, adv_imgs, grad_outputs=None, only_inputs=True)[0]
-
-            # attacks.py:212-222 fused: step 0.00392, project to x +- magnitude, clamp, project to [min_x, max_x]
-            adv_imgs = F_ee.cw_linf_step(adv_imgs.detach(), grads.detach(), x_d, min_d, max_d, 0.00392, mag)
-
+    for _iter in range(int(max_iters)):
+        adv_imgs.requires_grad_()
+        with torch.enable_grad():
+            loss = _cw_margin_loss(model(adv_imgs), one_hot_y, one_hot_target)
+        grads = torch.autograd.grad(loss, adv_imgs, grad_outputs=None, only_inputs=True)[0]
+        adv_imgs = F_ee.cw_linf_step(adv_imgs.detach(), grads.detach(), x_d, min_x, max_x, 0.00392, mag)
     adv_imgs = adv_imgs.clamp(0, 1)
 
     now_p = adv_imgs - x_d
-    adv[ind_non_suc] = adv_imgs
-    if previous_p is not None:
-        previous_p_c[ind_non_suc] = previous_p + now_p
-        return adv, previous_p_c
-
+    adv[idx] = adv_imgs
+    if carried is not None:
+        carried[idx] = previous_p + now_p
+        return adv, carried
     return adv, now_p
 
 
-def _small_randn_start(x_natural):
-    # the reference hard-codes device='cuda' (attacks.py:250,:291,:311,:383,:406); follow the input instead
-    return x_natural.detach() + 0.001 * torch.randn(x_natural.shape, device=x_natural.device).detach()
-
-
-# ALP -- utils/attacks.py:236-272
+# --------------------------------------------------------------------------------------------------------------------
+# utils/attacks.py:236-333 -- ALP, targeted ALP
+# --------------------------------------------------------------------------------------------------------------------
 class ALP:
     def __init__(self, step_size=0.003, epsilon=0.047, perturb_steps=5, beta=1.0):
         self.step_size = step_size
@@ -276,106 +271,44 @@ class ALP:
     def reset_steps(self, k):
         self.perturb_steps = k
 
-    def PGD_Linf(self, model, x_natural, y):
+    def _attack(self, model, x_natural, labels, step_signed):
         model.eval()
-        x_adv = _small_randn_start(x_natural)
+        return _linf_attack(model, _ce_mean(labels), x_natural, _small_randn_start(x_natural), self.perturb_steps,
+                            step_signed, self.epsilon)
 
-        for _ in range(self.perturb_steps):
-            x_adv.requires_grad_()
-            with torch.enable_grad():
-                loss_c = F.cross_entropy(model(x_adv), y)
-            grad = torch.autograd.grad(loss_c, [x_adv])[0].detach()
-            x_adv = _linf_step(x_adv, grad, x_natural, self.step_size, self.epsilon)
-
-        return x_adv
+    def PGD_Linf(self, model, x_natural, y):
+        return self._attack(model, x_natural, y, self.step_size)
 
     def loss(self, model, logits, logits_adv, y, optimizer):
+        """0.5 CE(clean) + 0.5 CE(adv) + beta * MSE(logit pairing) (:263-272)."""
         model.train()
         optimizer.zero_grad()
         loss_robust = 0.5 * F.cross_entropy(logits, y) + 0.5 * F.cross_entropy(logits_adv, y)
-        loss_alp = F.mse_loss(logits, logits_adv)
-        return loss_robust + self.beta * loss_alp
+        return loss_robust + self.beta * F.mse_loss(logits, logits_adv)
 
 
-# Targeted ALP for Tiny ImageNet -- utils/attacks.py:276-333
-class targeted_ALP:
+class targeted_ALP(ALP):
     def __init__(self, step_size=0.003, epsilon=0.047, perturb_steps=5, beta=1.0, n_class=200):
-        self.step_size = step_size
-        self.epsilon = epsilon
-        self.perturb_steps = perturb_steps
-        self.beta = beta
+        super().__init__(step_size, epsilon, perturb_steps, beta)
         self.n_class = n_class
-
-    def reset_steps(self, k):
-        self.perturb_steps = k
-
-    def PGD_Linf(self, model, x_natural, y):
-        model.eval()
-        x_adv = _small_randn_start(x_natural)
-
-        for _ in range(self.perturb_steps):
-            x_adv.requires_grad_()
-            with torch.enable_grad():
-                loss_c = F.cross_entropy(model(x_adv), y)
-            grad = torch.autograd.grad(loss_c, [x_adv])[0].detach()
-            x_adv = _linf_step(x_adv, grad, x_natural, self.step_size, self.epsilon)
-
-        return x_adv
 
     def tarPGD_Linf(self, model, x_natural, y, device):
         model.eval()
-        label_offset = torch.randint(low=1, high=self.n_class, size=y.shape).to(device)
-        target_labels = torch.fmod(y + label_offset, self.n_class)
-
-        x_adv = _small_randn_start(x_natural)
-
-        for _ in range(self.perturb_steps):
-            x_adv.requires_grad_()
-            with torch.enable_grad():
-                loss_c = F.cross_entropy(model(x_adv), target_labels)
-            grad = torch.autograd.grad(loss_c, [x_adv])[0].detach()
-            x_adv = _linf_step(x_adv, grad, x_natural, -self.step_size, self.epsilon)
-
-        return x_adv
-
-    def loss(self, model, logits, logits_adv, y, optimizer):
-        model.train()
-        optimizer.zero_grad()
-        loss_robust = 0.5 * F.cross_entropy(logits, y) + 0.5 * F.cross_entropy(logits_adv, y)
-        loss_alp = F.mse_loss(logits, logits_adv)
-        return loss_robust + self.beta * loss_alp
+        target_labels = _random_targets(y, self.n_class, device)        # drawn before the randn start (:307-311)
+        return self._attack(model, x_natural, target_labels, -self.step_size)
 
 
-# Targeted ALP for ImageNet -- utils/attacks.py:337-357
-def tar_alp_imagenet(model, args, inputs, labels, num_steps, step_size, device):
-    x = inputs.detach()
-    label_offset = torch.randint(low=1, high=1000, size=labels.shape).to(device)
-    target_labels = torch.fmod(labels + label_offset, 1000)
-
-    x = x + 0.001 * torch.randn(x.shape).to(device).detach()
-
-    for i in range(num_steps):
-        x.requires_grad_()
-        with torch.enable_grad():
-            logits = model(x)
-            loss = F.cross_entropy(logits, target_labels, reduction='sum')
-        grad = torch.autograd.grad(loss, [x])[0]
-        x = _linf_step(x, grad, inputs, -step_size, args.epsilon)
-
-    return x, target_labels
-
-
-# utils/attacks.py:360-366
+# --------------------------------------------------------------------------------------------------------------------
+# utils/attacks.py:360-429 -- TRADES
+# --------------------------------------------------------------------------------------------------------------------
 def squared_l2_norm(x):
-    flattened = x.view(x.shape[0], -1)
-    return (flattened ** 2).mean(1)
+    return (x.view(x.shape[0], -1) ** 2).mean(1)          # mean, not sum (:360-362)
 
 
 def l2_norm(x):
     return squared_l2_norm(x).sqrt()
 
 
-# TRADES -- utils/attacks.py:369-429
 class Trades:
     def __init__(self, step_size=0.003, epsilon=0.047, perturb_steps=5, beta=1.0):
         self.step_size = step_size
@@ -387,45 +320,39 @@ class Trades:
     def reset_steps(self, k):
         self.perturb_steps = k
 
-    def PGD_L2(self, model, x_natural, logits):
-        model.eval()
-        x_adv = _small_randn_start(x_natural)
+    def _kl_to(self, logits):
         prob = F.softmax(logits, dim=-1)
-
-        for _ in range(self.perturb_steps):
-            with torch.enable_grad():
-                x_adv.requires_grad_()
-                loss_kl = self.criterion_kl(F.log_softmax(model(x_adv), dim=1), prob)
-            grad = torch.autograd.grad(loss_kl, [x_adv])[0].detach()
-            # attacks.py:391-399 fused (per-sample RMS norms, step, L2 re-projection, clamp)
-            x_adv = F_ee.pgd_l2_step(x_adv.detach(), grad, x_natural.detach(), self.step_size, self.epsilon)
-
-        return x_adv
+        return lambda adv_logits: self.criterion_kl(F.log_softmax(adv_logits, dim=1), prob)
 
     def PGD_Linf(self, model, x_natural, logits):
         model.eval()
-        x_adv = _small_randn_start(x_natural)
-        prob = F.softmax(logits, dim=-1)
+        return _linf_attack(model, self._kl_to(logits), x_natural, _small_randn_start(x_natural), self.perturb_steps,
+                            self.step_size, self.epsilon)
 
+    def PGD_L2(self, model, x_natural, logits):
+        """Normalised-gradient step with L2 re-projection (:381-401): per-sample RMS norms, step, projection and clamp are
+        ONE kernel (ee_pgd_l2_step_f32: the sample stays on chip between the two norms)."""
+        model.eval()
+        x_adv = _small_randn_start(x_natural)
+        kl = self._kl_to(logits)
+        anchor = x_natural.detach()
         for _ in range(self.perturb_steps):
             x_adv.requires_grad_()
             with torch.enable_grad():
-                loss_kl = self.criterion_kl(F.log_softmax(model(x_adv), dim=1), prob)
-            grad = torch.autograd.grad(loss_kl, [x_adv])[0].detach()
-            x_adv = _linf_step(x_adv, grad, x_natural, self.step_size, self.epsilon)
-
+                loss = kl(model(x_adv))
+            grad = torch.autograd.grad(loss, [x_adv])[0].detach()
+            x_adv = F_ee.pgd_l2_step(x_adv.detach(), grad, anchor, self.step_size, self.epsilon)
         return x_adv
 
     def loss(self, model, logits, x_adv, labels, optimizer):
         model.train()
         optimizer.zero_grad()
-        prob = F.softmax(logits, dim=-1)
-        loss_natural = F.cross_entropy(logits, labels)
-        loss_robust = self.criterion_kl(F.log_softmax(model(x_adv), dim=1), prob)
-        return loss_natural + self.beta * loss_robust
+        return F.cross_entropy(logits, labels) + self.beta * self._kl_to(logits)(model(x_adv))
 
 
-# AVmixup -- utils/attacks.py:433-518
+# --------------------------------------------------------------------------------------------------------------------
+# utils/attacks.py:433-518 -- AVmixup
+# --------------------------------------------------------------------------------------------------------------------
 class AVmixup:
     def __init__(self, args, gamma, lambda1, lambda2, step_size, num_steps, num_classes=200, device='cuda'):
         self.args = args
@@ -441,46 +368,34 @@ class AVmixup:
         return one_hot * factor + (one_hot - 1.) * ((factor - 1) / float(self.num_classes - 1))
 
     def _attack(self, model, inputs, soft_targets, step_signed):
-        x = inputs.detach()
-        if self.args.random:
-            x = _random_start(x, self.args.epsilon)
-        for i in range(self.num_steps):
-            x.requires_grad_()
-            with torch.enable_grad():
-                logits = model(x)
-                log_prob = F.log_softmax(logits, dim=1)
-                loss = -torch.sum(log_prob * soft_targets)
-            grad = torch.autograd.grad(loss, [x])[0]
-            x = _linf_step(x, grad, inputs, step_signed, self.args.epsilon)
-        return x
+        soft_ce = lambda logits: -torch.sum(F.log_softmax(logits, dim=1) * soft_targets)          # :462-463
+        return _linf_attack(model, soft_ce, inputs, _start(self.args, inputs), self.num_steps, step_signed,
+                            self.args.epsilon)
 
     def _mix(self, x, inputs, targets):
-        y_nat = self._label_smoothing(targets, self.lambda1)
-        y_vertex = self._label_smoothing(targets, self.lambda2)
+        """Adversarial vertex, per-sample Beta(1, 1) mix of inputs and labels (:469-478).  vertex, clamp, the float64 mix
+        and the cast back are one kernel; the weights are the reference's numpy draw."""
         x_weight = np.random.beta(1.0, 1.0, [x.shape[0], 1, 1, 1])
-        x_weight_torch = torch.from_numpy(x_weight).to(x.device)
         y_weight = torch.from_numpy(np.reshape(x_weight, [-1, 1])).to(x.device)
-        # attacks.py:469-471 + :476 (vertex, clamp, float64 mix, cast back) fused into one pass
-        x = F_ee.avmixup_mix(x.detach(), inputs.detach(), x_weight_torch, self.gamma)
-        y = y_nat * y_weight + y_vertex * (1 - y_weight)
+        x = F_ee.avmixup_mix(x.detach(), inputs.detach(), torch.from_numpy(x_weight).to(x.device), self.gamma)
+        y = self._label_smoothing(targets, self.lambda1) * y_weight + self._label_smoothing(targets, self.lambda2) * (1 - y_weight)
         return x, y
 
     def perturb(self, model, inputs, targets):
-        """attacks.py:447-479 (targets are soft / one-hot labels)."""
-        x = self._attack(model, inputs, targets, self.step_size)
-        return self._mix(x, inputs, targets)
+        """:447-479 (targets are soft / one-hot labels)."""
+        return self._mix(self._attack(model, inputs, targets, self.step_size), inputs, targets)
 
     def tar_perturb(self, model, inputs, targets):
-        """attacks.py:481-518: descends towards random target labels."""
-        label_offset = torch.randint(low=1, high=self.num_classes, size=targets.shape).to(self.device)
-        target_labels = torch.fmod(targets + label_offset, self.num_classes)
-        x = self._attack(model, inputs, target_labels, -self.step_size)
-        return self._mix(x, inputs, targets)
+        """:481-518: descends towards random target labels."""
+        target_labels = _random_targets(targets, self.num_classes, self.device)
+        return self._mix(self._attack(model, inputs, target_labels, -self.step_size), inputs, targets)
 
 
+# --------------------------------------------------------------------------------------------------------------------
 # free / fast adversarial training noise update (in-script loops of the reference):
-#   ImageNet/free_imagenet/AT_hfs_canny_free_imagenet_ddp.py:312-315,:330-332
-#   ImageNet/fgsm_imagenet/main_fast.py:233-235,:246-253 ; lib/utils.py:36-37
+#   ImageNet/free_imagenet/AT_hfs_canny_free_imagenet_ddp.py:312-315, :330-332
+#   ImageNet/fgsm_imagenet/main_fast.py:233-235, :246-253 ; lib/utils.py:36-37
+# --------------------------------------------------------------------------------------------------------------------
 def free_at_update_(global_noise, noise_grad, inputs, fgsm_step, clip_eps):
     """global_noise[0:B] += fgsm_step*sign(noise_grad); clamp to +-clip_eps (in place) and return the
     next repeat's input clamp(inputs + global_noise[0:B], 0, 1), all in one kernel."""

@@ -3,7 +3,7 @@
     CannyFilter, CannyFilter_BPDA, CannyFilter_step125_1      (utils/core.py:148, :386, :509)
     To_compare, To_eq, BinaryConnectDeterministic, safeSign   (utils/core.py:329, :361, :121, :115)
     get_gaussian_kernel, get_sobel_kernel, get_thin_kernels   (utils/core.py:58, :75, :87)
-    HighFreqSuppress, Add_Square                              (utils/core.py:15, :589; torch pass-through)
+    HighFreqSuppress, Add_Square                              (utils/core.py:15, :589; native kernels)
 
 plus the fused entry the *_EE models should call instead of ``clamp(x_hfs + w*canny(x), 0, 1)``:
 
@@ -131,6 +131,13 @@ def _kernel_tensors(k_gaussian, mu, sigma, k_sobel):
 
 class _EdgeFilterBase(nn.Module):
     _variant = None
+    # Reference-NaN compatibility of the backward (include/edge_b200.h, EE_FLAG_NAN_COMPAT).  The reference's autograd
+    # returns NaN on the 5 x 5 neighbourhood of every pixel whose gradient magnitude is exactly 0 (flat regions), and
+    # torch.sign(NaN) = 0 then freezes those pixels in PGD / FGSM; the kernels return the sub-gradient 0 instead, so an
+    # attack WITHOUT a random start (evaluation configs, MNIST backgrounds) moves pixels the reference leaves alone.
+    # Set `module.nan_compat = True` (or core.set_nan_compat(True) before building the model) to reproduce the
+    # reference's numbers there; it selects the shape-generic backward kernels.
+    nan_compat = False
 
     def _setup(self, k_gaussian, mu, sigma, k_sobel, use_cuda, alpha):
         self.device = 'cuda' if use_cuda else 'cpu'
@@ -146,11 +153,18 @@ class _EdgeFilterBase(nn.Module):
 
     def params(self, low_threshold=None, high_threshold=None, hysteresis=False):
         """EEParams for one forward() call (C-ABI struct, passed by value to the kernels)."""
+        if self._variant == "step125":       # the module ignores low_threshold / hysteresis (core.py:549-585)
+            low_threshold, hysteresis = None, False
         return F_ee.make_params(self._variant, self._gauss_np, self._alpha_f, low_threshold, high_threshold,
-                                hysteresis, sobel=self._sobel_np)
+                                hysteresis, sobel=self._sobel_np, nan_compat=self.nan_compat)
 
     def forward(self, img, low_threshold=None, high_threshold=None, hysteresis=False):
         return F_ee.EdgeMapFn.apply(img, self.params(low_threshold, high_threshold, hysteresis))
+
+
+def set_nan_compat(enabled=True):
+    """Default of `nan_compat` for every filter module that does not set its own (see _EdgeFilterBase.nan_compat)."""
+    _EdgeFilterBase.nan_compat = bool(enabled)
 
 
 class CannyFilter(_EdgeFilterBase):
@@ -210,19 +224,26 @@ class CannyFilter_step125_1(_PlainTensorFilter):
 # ---------------------------------------------------------------------------------------------
 # fused edge + blend (what the *_EE models should call)
 # ---------------------------------------------------------------------------------------------
-def edge_enhance(img, base, canny, w, low_threshold=None, high_threshold=None, hysteresis=False):
+def edge_enhance(img, base, canny, w, low_threshold=None, high_threshold=None, hysteresis=False, with_gf=False,
+                 weight_gaussian=None):
     """clamp(base + w * canny(img, low, high, hysteresis), 0, 1) as one kernel per direction.
 
-    Replaces e.g. Tiny_ImageNet/models_tinyimagenet/resnet_EE.py:182-191 (gf=False):
+    Replaces e.g. Tiny_ImageNet/models_tinyimagenet/resnet_EE.py:182-191:
         x_canny = self.canny(x, ...); x = x_hfs + self.w * x_canny; x = torch.clamp(x, 0.0, 1.0)
     `base` is x_hfs (any tensor shaped like img); gradients flow to both img and base.
+    with_gf=True (resnet_EE.py:185-187; no reference YAML enables it) passes the edge map through the zero-padded 3x3
+    Gaussian `weight_gaussian` (default get_gaussian_kernel(3, 0, 1), resnet_EE.py:133-136) first: two kernels per
+    direction (edge map, then Gaussian + blend) instead of one.
     """
-    if isinstance(canny, CannyFilter_step125_1):
-        if high_threshold is None:
-            raise UnboundLocalError("CannyFilter_step125_1 needs high_threshold")
-        p = canny.params(None, high_threshold, False)
-    else:
-        p = canny.params(low_threshold, high_threshold, hysteresis)
+    if isinstance(canny, CannyFilter_step125_1) and high_threshold is None:
+        raise UnboundLocalError("CannyFilter_step125_1 needs high_threshold")
+    p = canny.params(low_threshold, high_threshold, hysteresis)
+    if with_gf:
+        g = get_gaussian_kernel(3, 0., 1.) if weight_gaussian is None else weight_gaussian
+        if isinstance(g, torch.Tensor):
+            g = g.detach().cpu().numpy()
+        g = np.asarray(g, dtype=np.float32).reshape(3, 3)
+        return F_ee.GfBlendFn.apply(F_ee.EdgeMapFn.apply(img, p), base, g, float(w))
     return F_ee.EdgeEnhanceFn.apply(img, base, p, float(w))
 
 
@@ -232,9 +253,10 @@ class EdgeEnhance(nn.Module):
     ImageNet/models_imagenet/resnet_EE.py:167-179, AWP/.../preactresnet_EE*.py:145-159)."""
 
     def __init__(self, cize=224, r=16, w=0.5, low=60.0, high=120.0, alpha=0.0, sigma=1,
-                 type_canny='CannyFilter', hfs=True):
+                 type_canny='CannyFilter', hfs=True, with_gf=False):
         super(EdgeEnhance, self).__init__()
         self.w = w
+        self.with_gf = with_gf
         self.low = low / 255
         self.high = high / 255
         self.hfs = HighFreqSuppress(cize, cize, r) if hfs else None
@@ -249,34 +271,51 @@ class EdgeEnhance(nn.Module):
 
     def forward(self, x):
         h = self.hfs
-        if (h is not None and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and h.w == h.h == x.shape[-1] == x.shape[-2]
-                and x.is_contiguous() and F_ee.hfs_supported(h.w, h.r)):
+        if (h is not None and not self.with_gf and h.impl == 'native' and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+                and h.w == h.h == x.shape[-1] == x.shape[-2] and x.is_contiguous() and F_ee.hfs_supported(h.w, h.r)):
             # low-pass, edge filter and blend as one autograd node: three kernels forward, three backward
             p = self.canny.params(self.low, self.high, True)
             return F_ee.EdgeEnhanceFrontFn.apply(x, h.r, p, float(self.w))
         base = h(x) if h is not None else x
-        return edge_enhance(x, base, self.canny, self.w, self.low, self.high, True)
+        return edge_enhance(x, base, self.canny, self.w, self.low, self.high, True, with_gf=self.with_gf)
 
 
 # ---------------------------------------------------------------------------------------------
 # adjacent modules that stay on torch ops (SURVEY.md section 8f "next" rows)
 # ---------------------------------------------------------------------------------------------
 class HighFreqSuppress(torch.nn.Module):
-    """utils/core.py:15-55: square low-pass in the 2-D Fourier domain.  The reference calls
-    torch.rfft / torch.irfft (removed in torch 1.8) and hard-codes .cuda(); `_fft_forward` is the
-    torch.fft restatement (onesided=False forward, C2R inverse that reads the one-sided half).
-    On CUDA tensors of the reference's shapes (64 px / r 8, 28 px / r 4, 224 px / r 16, 128 px / r 12, 288 px / r 18) the same operator runs as ONE
-    kernel per direction (libedge_b200.so: ee_hfs_f32, five small real-DFT products per plane in shared
-    memory; 2.3-5x faster than the three cuFFT / elementwise passes) registered as an autograd.Function whose
-    backward is the same kernel (the operator is symmetric).  Parity for this module is UNPINNED against
-    the reference (its version cannot run on any torch that supports sm_100); the kernel is pinned to
-    the torch.fft restatement and to the closed spatial form (tests)."""
+    """utils/core.py:15-55: square low-pass in the 2-D Fourier domain (rfft(onesided=False) -> mask -> irfft(onesided=False)).
 
-    def __init__(self, w, h, r):
+    The reference calls torch.rfft / torch.irfft, removed in torch 1.8, so its own code cannot run on any torch that
+    knows sm_100 and parity for this module is UNPINNED.  Its mask `temp` keeps the frequency indices [-r, r-1] on both
+    axes, which is not Hermitian-symmetric (-r is kept, +r is not), so the result depends on what the old complex-to-real
+    inverse did with the non-Hermitian part.  Both readings are implemented and selectable:
+
+      c2r='onesided' (default): the old C2R kernel read only the one-sided half spectrum [..., :W//2+1] and implied the rest
+                    by symmetry (what cuFFT / MKL C2R do, and what torch <= 1.7's irfft(onesided=False) did by narrowing
+                    its input).  = torch.fft.irfft2(fft2(x)[..., :W//2+1] * temp[..., :W//2+1]).
+      c2r='full'  : the real part of the full complex inverse, Re(ifft2(fft2(x) * temp)) (the k = -r row / column then
+                    gets weight 1/2 and leaks into k = +r).  tests/test_host_logic.py quantifies the difference.
+
+    impl='native' (default): ONE CUDA kernel per direction (libedge_b200.so: ee_hfs_f32, five small real-DFT products per
+    plane in shared memory; 2.3-5x faster than the three cuFFT / elementwise passes), registered as an autograd.Function
+    whose backward is the same kernel (the operator is symmetric).  Exists for c2r='onesided' and the reference's
+    configurations (28 / 4, 32 / 8, 64 / 8, 128 / 12, 224 / 16, 288 / 18); any other request RAISES -- there is no
+    silent fallback.  impl='torch_fft' is the explicit opt-in to the torch.fft restatement (library code, any shape, any
+    device); it is what the native kernel is pinned to (tests)."""
+
+    def __init__(self, w, h, r, c2r='onesided', impl='native'):
         super(HighFreqSuppress, self).__init__()
+        if c2r not in ('onesided', 'full') or impl not in ('native', 'torch_fft'):
+            raise ValueError("HighFreqSuppress: c2r must be 'onesided' or 'full', impl 'native' or 'torch_fft'")
+        if c2r == 'full' and impl == 'native':
+            raise NotImplementedError("HighFreqSuppress: the native kernel implements c2r='onesided'; "
+                                      "use impl='torch_fft' with c2r='full'")
         self.w = w
         self.h = h
         self.r = r
+        self.c2r = c2r
+        self.impl = impl
         self.templete()
 
     def templete(self):
@@ -293,26 +332,38 @@ class HighFreqSuppress(torch.nn.Module):
         self.temp = temp                     # [1,1,w,h,1] like the reference
         self._mask_cache = {}
 
-    def _mask(self, device):
-        m = self._mask_cache.get(device)
+    def _mask(self, device, full=False):
+        m = self._mask_cache.get((device, full))
         if m is None:
-            half = self.h // 2 + 1
-            m = self.temp[..., 0][..., :half].to(device)
-            self._mask_cache[device] = m
+            m = self.temp[..., 0]
+            if not full:
+                m = m[..., :self.h // 2 + 1]
+            m = m.to(device)
+            self._mask_cache[(device, full)] = m
         return m
 
-    def _fft_forward(self, x):
-        # rfft(x, 2, onesided=False) followed by a C2R inverse that reads only the one-sided half equals a
-        # real-to-complex transform of the half spectrum: rfft2 does half the work of fft2(x)[..., :half]
+    def _fft_forward(self, x, c2r=None):
+        """The torch.fft restatement (any device).  'onesided': rfft(x, 2, onesided=False) followed by a C2R inverse that
+        reads only the one-sided half equals a real-to-complex transform of the half spectrum (rfft2 does half the work
+        of fft2(x)[..., :half]).  'full': real part of the full complex inverse."""
+        if (c2r or self.c2r) == 'full':
+            return torch.fft.ifft2(torch.fft.fft2(x) * self._mask(x.device, True)).real
         x_hat = torch.fft.rfft2(x)
         x_hat = x_hat * self._mask(x.device)
         return torch.fft.irfft2(x_hat, s=x.shape[-2:])
 
     def forward(self, x):
-        if (x.is_cuda and x.dtype == torch.float32 and self.w == self.h and x.shape[-1] == self.w and x.shape[-2] == self.h
-                and self.w % 2 == 0 and F_ee.hfs_supported(self.w, self.r)):
-            return F_ee.HfsFn.apply(x, self.r)
-        return self._fft_forward(x)
+        if self.impl == 'torch_fft':
+            return self._fft_forward(x)
+        if not x.is_cuda:
+            raise RuntimeError("edge_b200: HighFreqSuppress got a tensor on %s; the native kernel is CUDA-only and there is "
+                               "no CPU fallback (impl='torch_fft' selects the torch.fft restatement explicitly)" % x.device)
+        if not (x.dtype == torch.float32 and self.w == self.h and x.shape[-1] == self.w and x.shape[-2] == self.h
+                and F_ee.hfs_supported(self.w, self.r)):
+            raise RuntimeError("edge_b200: no native HighFreqSuppress kernel for %s planes of %s with w=%d h=%d r=%d "
+                               "(have: 28/4, 32/8, 64/8, 128/12, 224/16, 288/18, float32); pass impl='torch_fft' to use "
+                               "the torch.fft restatement" % (tuple(x.shape[-2:]), x.dtype, self.w, self.h, self.r))
+        return F_ee.HfsFn.apply(x, self.r)
 
     def extra_repr(self):
         return 'feature_width={}, feature_height={}, radius={}'.format(self.w, self.h, self.r)

@@ -12,6 +12,8 @@
 #include "ee_edge_step125.cuh"
 #include "ee_square.cuh"
 #include "ee_hfs.cuh"
+#include "ee_gf.cuh"
+#include "ee_pgd_l2.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -66,6 +68,62 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 
 constexpr int kMaxSmem = 227 * 1024;
 constexpr int kThreads = 256;
+constexpr int kMaxDevices = 32;
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a driver round trip (~2 us); a kernel needs it once per
+// device, not once per launch.  The largest value set so far is remembered per (kernel address, device).
+struct SmemOnce { std::atomic<int> have[kMaxDevices]; };
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);             // thread-local lookup in the runtime, no driver call
+    return dev;
+}
+template <typename K>
+int ensure_smem(SmemOnce& once, K kernel, size_t smem) {
+    if (smem <= 48 * 1024) return EE_OK;
+    const int dev = current_device();
+    if (dev >= 0 && dev < kMaxDevices && once.have[dev].load(std::memory_order_relaxed) >= (int)smem) return EE_OK;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+    if (dev >= 0 && dev < kMaxDevices) once.have[dev].store((int)smem, std::memory_order_relaxed);
+    return EE_OK;
+}
+// table of SmemOnce slots keyed by the kernel's address (lock-free, fixed size; a full table just re-sets the attribute)
+inline SmemOnce& smem_slot(const void* fn) {
+    constexpr int kSlots = 512;
+    static std::atomic<const void*> keys[kSlots];
+    static SmemOnce slots[kSlots];
+    static SmemOnce overflow;
+    size_t h = (reinterpret_cast<uintptr_t>(fn) >> 4) * 0x9E3779B97F4A7C15ull >> 40;
+    for (int probe = 0; probe < kSlots; ++probe) {
+        const int i = (int)((h + probe) % kSlots);
+        const void* k = keys[i].load(std::memory_order_acquire);
+        if (k == fn) return slots[i];
+        if (k == nullptr) {
+            const void* expect = nullptr;
+            if (keys[i].compare_exchange_strong(expect, fn, std::memory_order_acq_rel) || expect == fn) return slots[i];
+        }
+    }
+    for (int d = 0; d < kMaxDevices; ++d) overflow.have[d].store(0, std::memory_order_relaxed);
+    return overflow;
+}
+template <typename K>
+int ensure_smem(K kernel, size_t smem) {
+    if (smem <= 48 * 1024) return EE_OK;
+    return ensure_smem(smem_slot(reinterpret_cast<const void*>(kernel)), kernel, smem);
+}
+inline int sm_count() {
+    static std::atomic<int> cached[kMaxDevices];
+    const int dev = current_device();
+    if (dev >= 0 && dev < kMaxDevices) {
+        const int c = cached[dev].load(std::memory_order_relaxed);
+        if (c > 0) return c;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (dev >= 0 && dev < kMaxDevices) cached[dev].store(sms, std::memory_order_relaxed);
+    return sms;
+}
 
 // Validate EEParams and extract the three Gaussian taps.
 int check_params(const EEParams* p, float& c0, float& c1, float& c2) {
@@ -73,7 +131,7 @@ int check_params(const EEParams* p, float& c0, float& c1, float& c2) {
     if (p->variant < EE_VARIANT_STEP125 || p->variant > EE_VARIANT_BPDA)
         return fail(EE_ERR_INVALID_ARG, "unknown variant %d", p->variant);
     if (p->layout != EE_LAYOUT_NCHW && p->layout != EE_LAYOUT_NHWC) return fail(EE_ERR_INVALID_ARG, "unknown layout %d", p->layout);
-    if (p->reserved != 0) return fail(EE_ERR_INVALID_ARG, "EEParams.reserved must be 0");
+    if ((p->flags & ~EE_FLAG_NAN_COMPAT) != 0) return fail(EE_ERR_INVALID_ARG, "EEParams.flags has unknown bits (0x%x)", p->flags);
     const float* g = p->gauss;
     if (!(g[0] == g[2] && g[0] == g[6] && g[0] == g[8] && g[1] == g[3] && g[1] == g[5] && g[1] == g[7]))
         return fail(EE_ERR_UNSUPPORTED, "gauss[9] lacks the corner/edge/centre symmetry of get_gaussian_kernel(3,..)");
@@ -123,7 +181,9 @@ int plan_fast(int H, int W, int R, int rows_per_th, int rows_fixed, int max_halo
     // Full-width strips up to max_full_width columns (measured at 224 px: the forward is faster with
     // full-width strips of ~18 rows, 6.3 vs 5.4 TB/s; the backward with 56+8-column tiles, 3.9-4.3 vs 3.4 TB/s)
     int tw_target = 64;
-    if (const char* e = getenv("EE_TILE_COLS")) { const int v = atoi(e); if (v >= 8) { tw_target = v; max_full_width = 0; } }   // tuning experiments
+#ifdef EE_TUNING_ENV        // tuning experiments only (-DEE_TUNING_ENV): never read the environment in a production build
+    if (const char* e = getenv("EE_TILE_COLS")) { const int v = atoi(e); if (v >= 8) { tw_target = v; max_full_width = 0; } }
+#endif
     if (W <= max_full_width || tw_target >= W) { L.tiles_x = 1; L.TW = W; L.planeW = W; }
     else {
         L.tiles_x = (W + tw_target - 1) / tw_target;
@@ -185,10 +245,7 @@ int plan_fast(int H, int W, int R, int rows_per_th, int rows_fixed, int max_halo
 
 template <typename K>
 int launch_fast(K kernel, const Launch& L, int B, const ee::FastArgs& a, cudaStream_t s, const char* name) {
-    if (L.smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-    }
+    if (int rc = ensure_smem(kernel, L.smem)) return rc;
     const long long grid = (long long)B * L.tiles;
     if (grid > 0x7fffffffLL) return fail(EE_ERR_TOO_LARGE, "too many tiles");
     kernel<<<(unsigned)grid, L.threads, L.smem, s>>>(a);
@@ -222,8 +279,8 @@ int launch_cluster(K kernel, int W, int TH, int CS, int B, const ee::EdgeArgs& e
     L.smem = (size_t)3 * TH * (W + ee::kPadW) * sizeof(float);
     ee::FastArgs f;
     fill_fast(f, e, L);
-    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
-    if (err != cudaSuccess) return cuda_fail(err, "cudaFuncSetAttribute");
+    if (int rc = ensure_smem(kernel, L.smem)) return rc;
+    cudaError_t err;
     if ((long long)B * CS > 0x7fffffffLL) return fail(EE_ERR_TOO_LARGE, "too many tiles");
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(B * CS));
@@ -302,10 +359,7 @@ int make_x_tensor_map(CUtensorMap* map, const float* x, int B, int C, int H, int
 
 template <typename K>
 int launch_tiles(K kernel, const Launch& L, int B, const ee::FastArgs& a, const CUtensorMap& map, cudaStream_t s, const char* name) {
-    if (L.smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-    }
+    if (int rc = ensure_smem(kernel, L.smem)) return rc;
     const long long grid = (long long)B * L.tiles;
     if (grid > 0x7fffffffLL) return fail(EE_ERR_TOO_LARGE, "too many tiles");
     kernel<<<(unsigned)grid, L.threads, L.smem, s>>>(a, map);
@@ -316,6 +370,7 @@ int launch_tiles(K kernel, const Launch& L, int B, const ee::FastArgs& a, const 
 
 bool fast_eligible(const ee::EdgeArgs& a, bool vec_ok) {
     if (g_staging.load() == 1 || !vec_ok || a.W < 8 || a.H < 4) return false;
+    if (a.nan_compat && a.g_in != nullptr) return false;      // reference-NaN backward: shape-generic kernels only
     return std::isfinite(a.high) && std::isfinite(a.alpha) && std::isfinite(a.low) && fabsf(a.high) < 1e18f &&
            fabsf(a.alpha) < 1e18f;
 }
@@ -412,10 +467,7 @@ int plan(int H, int W, bool vec_ok, int rows_per_th, int rows_fixed, int max_hal
 
 template <typename K>
 int launch(K kernel, const Launch& L, int B, const ee::EdgeArgs& a, cudaStream_t s, const char* name) {
-    if (L.smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-    }
+    if (int rc = ensure_smem(kernel, L.smem)) return rc;
     const long long grid = (long long)B * L.tiles;
     if (grid > 0x7fffffffLL) return fail(EE_ERR_TOO_LARGE, "too many tiles");
     kernel<<<(unsigned)grid, L.threads, L.smem, s>>>(a);
@@ -433,7 +485,12 @@ int fill_args(ee::EdgeArgs& a, int B, int C, int H, int W, const EEParams* p, fl
     a.B = B; a.C = C; a.H = H; a.W = W;
     a.c0 = c0; a.c1 = c1; a.c2 = c2; a.fC = (float)C;
     a.alpha = p->alpha; a.low = p->low_thr; a.high = p->high_thr; a.w = w;
-    a.variant = p->variant; a.has_low = p->has_low != 0; a.has_high = p->has_high != 0; a.hyst = p->hysteresis != 0;
+    a.variant = p->variant; a.has_low = p->has_low != 0; a.has_high = p->has_high != 0;
+    // CannyFilter_step125_1 ignores low_threshold / hysteresis (core.py:549-585): normalise them here so that every entry
+    // point and every predicate below sees the same request whatever the caller left in those fields
+    if (p->variant == EE_VARIANT_STEP125) a.has_low = 0;
+    a.hyst = (p->variant != EE_VARIANT_STEP125) && p->hysteresis != 0;
+    a.nan_compat = (p->flags & EE_FLAG_NAN_COMPAT) != 0;
     return EE_OK;
 }
 
@@ -659,10 +716,7 @@ int ee_shared::bwd_canny(ee::EdgeArgs& a, const EEParams* p, int B, bool blend, 
 namespace {
 template <typename K>
 int launch_stream(K kernel, const ee::StreamArgs& sa, unsigned grid, int threads, size_t smem, cudaStream_t s, const char* name) {
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-    }
+    if (int rc = ensure_smem(kernel, smem)) return rc;
     kernel<<<grid, threads, smem, s>>>(sa);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, name);
@@ -779,14 +833,9 @@ static int launch_hfs(const ee::HfsArgs& a, cudaStream_t s) {
     using D_ = ee::HfsDims<N, R>;
     const size_t smem = (size_t)(D_::kTables + P * D_::kPlane) * sizeof(float);
     auto kernel = ee::hfs_kernel<N, R, P>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-    }
+    if (int rc = ensure_smem(kernel, smem)) return rc;
     // persistent CTAs: as many as can be resident (shared-memory limited), each loops over groups of P planes
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count();
     const int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
     const int groups = (a.planes + P - 1) / P;
     int grid = sms * (per_sm < 1 ? 1 : per_sm);
@@ -801,11 +850,9 @@ template <int N, int R>
 static int launch_hfs_rows(const ee::HfsArgs& a, cudaStream_t s) {
     const size_t smem = (size_t)ee::HfsRowsDims<N, R>::kFloats * sizeof(float);
     auto kernel = ee::hfs_rows_kernel<N, R>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (int rc = ensure_smem(kernel, smem)) return rc;
+    const int sms = sm_count();
+    cudaError_t e;
     const int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
     int grid = sms * (per_sm < 1 ? 1 : per_sm);
     if (grid > a.planes) grid = a.planes;
@@ -883,10 +930,76 @@ int ee_pgd_l2_step_f32(const float* x, const float* g, const float* x0, float* o
     if (B == 0 || n_per == 0) return EE_OK;
     if (!x || !g || !x0 || !out) return fail(EE_ERR_INVALID_ARG, "ee_pgd_l2_step_f32: null pointer");
     if (out == x) return fail(EE_ERR_INVALID_ARG, "ee_pgd_l2_step_f32: out must not alias x");
-    ee::pgd_l2_kernel<<<(unsigned)B, 1024, 0, (cudaStream_t)stream>>>(x, g, x0, out, n_per, step, eps);
+    cudaStream_t s = (cudaStream_t)stream;
+    ee::L2Plan pl;
+    // one pass (16 B/element): a cluster of K CTAs keeps the sample on chip between the two norms (ee_pgd_l2.cuh)
+    if (g_staging.load() != 1 && aligned16(x) && aligned16(g) && aligned16(x0) && aligned16(out) && ee::pgd_l2_plan(n_per, pl) &&
+        (long long)B * pl.K <= 0x7fffffffLL) {
+        auto kernel = ee::pgd_l2_cluster_kernel;
+        if (int rc = ensure_smem(kernel, pl.smem)) return rc;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)((long long)B * pl.K));
+        cfg.blockDim = dim3((unsigned)ee::kL2Threads);
+        cfg.dynamicSmemBytes = pl.smem;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)pl.K; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, x, g, x0, out, n_per, pl.slice4, pl.K, step, eps);
+        if (e != cudaSuccess) return cuda_fail(e, "ee_pgd_l2_step_f32");
+        return EE_OK;
+    }
+    // any size / alignment: three passes, one CTA per sample (a different, equally fixed, reduction order)
+    ee::pgd_l2_kernel<<<(unsigned)B, 1024, 0, s>>>(x, g, x0, out, n_per, step, eps);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "ee_pgd_l2_step_f32");
     return EE_OK;
+}
+
+static int gf_blend(bool bwd, const float* g_out, const float* edge, const float* base, float* out, float* g_edge, float* g_base,
+                    int B, int C, int H, int W, const float* gauss, float w, void* stream) {
+    const char* name = bwd ? "ee_gf_blend_bwd_f32" : "ee_gf_blend_fwd_f32";
+    if (B < 0 || C <= 0 || H <= 0 || W <= 0) return fail(EE_ERR_INVALID_ARG, "%s: bad shape", name);
+    if (B == 0) return EE_OK;
+    if (!edge || !base || !gauss || (bwd ? !g_out : !out)) return fail(EE_ERR_INVALID_ARG, "%s: null pointer", name);
+    if (bwd && !g_edge && !g_base) return EE_OK;
+    if (!(gauss[0] == gauss[2] && gauss[0] == gauss[6] && gauss[0] == gauss[8] && gauss[1] == gauss[3] && gauss[1] == gauss[5] &&
+          gauss[1] == gauss[7]))
+        return fail(EE_ERR_UNSUPPORTED, "%s: gauss[9] lacks the corner/edge/centre symmetry of get_gaussian_kernel(3,..)", name);
+    if (B > 65535) return fail(EE_ERR_TOO_LARGE, "%s: more than 65535 images per call", name);
+    ee::GfArgs a;
+    a.edge = edge; a.base = base; a.g_out = g_out; a.out = out; a.g_edge = g_edge; a.g_base = g_base;
+    a.B = B; a.C = C; a.H = H; a.W = W; a.c0 = gauss[0]; a.c1 = gauss[1]; a.c2 = gauss[4]; a.w = w;
+    const dim3 grid((unsigned)((W + ee::kGfTW - 1) / ee::kGfTW), (unsigned)((H + ee::kGfTH - 1) / ee::kGfTH), (unsigned)B);
+    if (bwd) ee::gf_blend_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    else ee::gf_blend_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, name);
+    return EE_OK;
+}
+int ee_gf_blend_fwd_f32(const float* edge, const float* base, float* out, int B, int C, int H, int W, const float gauss[9],
+                        float w, void* stream) {
+    return gf_blend(false, nullptr, edge, base, out, nullptr, nullptr, B, C, H, W, gauss, w, stream);
+}
+int ee_gf_blend_bwd_f32(const float* g_out, const float* edge, const float* base, float* g_edge_or_null, float* g_base_or_null,
+                        int B, int C, int H, int W, const float gauss[9], float w, void* stream) {
+    return gf_blend(true, g_out, edge, base, nullptr, g_edge_or_null, g_base_or_null, B, C, H, W, gauss, w, stream);
+}
+
+int ee_edge_pgd_iteration_f32(const float* x, const float* base, const float* g_out, const float* x0, float* out_or_null,
+                              float* g_x, float* g_base_or_null, float* x_next, int B, int C, int H, int W, const EEParams* p,
+                              float w, float alpha_signed, float eps, void* stream) {
+    if (!g_x || !x_next || !x0) return fail(EE_ERR_INVALID_ARG, "ee_edge_pgd_iteration_f32: null pointer");
+    if (x_next == x) return fail(EE_ERR_INVALID_ARG, "ee_edge_pgd_iteration_f32: x_next must not alias x");
+    int rc = EE_OK;
+    if (out_or_null) rc = edge_forward(x, base, out_or_null, nullptr, B, C, H, W, p, w, true, stream);
+    if (rc) return rc;
+    rc = edge_backward(g_out, x, base, g_x, g_base_or_null, B, C, H, W, p, w, true, stream);
+    if (rc) return rc;
+    return launch_ew<3>(x, g_x, x0, nullptr, nullptr, x_next, (int64_t)B * C * H * W, ee::FPgdLinf{alpha_signed, eps, 0.0f, 1.0f},
+                        stream, "ee_edge_pgd_iteration_f32");
 }
 
 int ee_to_compare_fwd_f32(const float* in, float* out, int64_t n, float thr, void* stream) {

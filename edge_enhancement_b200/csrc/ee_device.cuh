@@ -190,9 +190,11 @@ __device__ __forceinline__ int orient_dir(float gx1, float gy1) {
 
 // dL/d(mag) -> (dL/dSgx, dL/dSgy):  mag = u^.5, u = gx1^2 + gy1^2 ; autograd evaluates
 // g*0.5*u^-.5, then *2*gx1, then /C (three divisions); canonical form: (g / (mag*C)) * gx1, one
-// division, equal up to ~2 ulp.  Sub-gradient at mag == 0 is 0.
+// division, equal up to ~2 ulp.  Sub-gradient at mag == 0 is 0 -- unless nan_compat asks for what autograd does
+// there: g * 0.5 * 0^-0.5 * 2 * 0 = NaN whatever g is (EE_FLAG_NAN_COMPAT, include/edge_b200.h).
 __device__ __forceinline__ void mag_backward(float gm, float mag, float gx1, float gy1, float fC,
-                                             float& a, float& b) {
+                                             float& a, float& b, int nan_compat = 0) {
+    if (nan_compat && mag == 0.0f) { a = __int_as_float(0x7fc00000); b = a; return; }
     if (gm == 0.0f || mag == 0.0f) { a = 0.0f; b = 0.0f; return; }
     const float t = gm / (mag * fC);
     a = t * gx1;

@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(256) edge_bwd_canny_kernel(const EdgeArgs a) {
                 float gm = g_thin_of(a, mode, ge[k], thin[k], wih[k]);
                 if (meta_removed(meta[k])) gm = 0.0f;                     // core.py:290 / :480
                 if (a.variant == 1 && mag < a.alpha) gm = 0.0f;           // torch.where backward
-                mag_backward(gm, mag, gx1[k], gy1[k], a.fC, av[k], bv[k]);
+                mag_backward(gm, mag, gx1[k], gy1[k], a.fC, av[k], bv[k], a.nan_compat);
             }
             st_vec<VEC>(A + (size_t)(row - ab_lo) * W + col, av);
             st_vec<VEC>(Bv + (size_t)(row - ab_lo) * W + col, bv);

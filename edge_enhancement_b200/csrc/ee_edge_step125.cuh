@@ -34,6 +34,7 @@ struct EdgeArgs {
     int GX, RY;           // thread t -> (tx = t % GX, ty = t / GX); rows advance by RY
     float c0, c1, c2, fC, alpha, low, high, w;
     int variant, has_low, has_high, hyst;
+    int nan_compat;       // EE_FLAG_NAN_COMPAT: dL/dSgx = dL/dSgy = NaN where the magnitude is exactly 0 (generic backward kernels)
 };
 
 #define EE_FOR_TILE(row_lo, row_hi)                                     \
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(256) edge_bwd_step125_kernel(const EdgeArgs a)
             for (int k = 0; k < VEC; ++k) {
                 float gm = ste_sel(ge[k], magm[k], a.high);              // To_compare.backward
                 if (mag[k] < a.alpha) gm = 0.0f;                         // torch.where backward
-                mag_backward(gm, mag[k], gx1[k], gy1[k], a.fC, av[k], bv[k]);
+                mag_backward(gm, mag[k], gx1[k], gy1[k], a.fC, av[k], bv[k], a.nan_compat);
             }
             st_vec<VEC>(A + (size_t)(row - ab_lo) * W + col, av);
             st_vec<VEC>(Bv + (size_t)(row - ab_lo) * W + col, bv);

@@ -19,8 +19,9 @@ VARIANTS = {"step125": EE_VARIANT_STEP125, "canny": EE_VARIANT_CANNY, "bpda": EE
 _SOBEL_X = np.array([[-0.5, 0.0, 0.5], [-1.0, 0.0, 1.0], [-0.5, 0.0, 0.5]], dtype=np.float32)
 
 
-def make_params(variant, gauss, alpha=0.0, low=None, high=None, hysteresis=False, sobel=None):
-    """Build an EEParams from module state (3x3 fp32 kernels) + forward() arguments."""
+def make_params(variant, gauss, alpha=0.0, low=None, high=None, hysteresis=False, sobel=None, nan_compat=False):
+    """Build an EEParams from module state (3x3 fp32 kernels) + forward() arguments.  nan_compat=True asks the backward
+    for the reference's NaNs where the gradient magnitude is exactly 0 (EE_FLAG_NAN_COMPAT, include/edge_b200.h)."""
     p = EEParams()
     p.variant = VARIANTS[variant] if isinstance(variant, str) else int(variant)
     p.layout = _lib.EE_LAYOUT_NCHW
@@ -38,7 +39,7 @@ def make_params(variant, gauss, alpha=0.0, low=None, high=None, hysteresis=False
     p.has_low = int(low is not None)
     p.has_high = int(high is not None)
     p.hysteresis = int(bool(hysteresis))
-    p.reserved = 0
+    p.flags = _lib.EE_FLAG_NAN_COMPAT if nan_compat else 0
     return p
 
 
@@ -64,9 +65,12 @@ def _is_channels_last(t):
             and t.is_contiguous(memory_format=torch.channels_last))
 
 
-def _nhwc_ok(x):
-    """The fused kernels read torch.channels_last directly for C == 3 and W % 4 == 0 (include/edge_b200.h)."""
+def _nhwc_ok(x, params=None):
+    """The fused kernels read torch.channels_last directly for C == 3 and W % 4 == 0 (include/edge_b200.h); the
+    NaN-compatible backward is NCHW-only."""
     B, C, H, W = x.shape
+    if params is not None and (params.flags & _lib.EE_FLAG_NAN_COMPAT):
+        return False
     return _is_channels_last(x) and C == 3 and W % 4 == 0 and W >= 8 and H >= 4
 
 
@@ -179,7 +183,7 @@ def edge_blend_backward(g_out, x, base, params, w, need_x=True, need_base=True, 
     """(g_x, g_base) of edge_blend in one pass -- ee_edge_blend_bwd_f32.  g_x / g_base may be
     preallocated buffers (not aliasing any input)."""
     x = _chk_nocopy(x, "img")
-    nhwc = _nhwc_ok(x)
+    nhwc = _nhwc_ok(x, params)
     x = _as_layout(x, "img", None, nhwc)
     B, C, H, W = x.shape
     base = _as_layout(base, "base", x.shape, nhwc)
@@ -193,6 +197,66 @@ def edge_blend_backward(g_out, x, base, params, w, need_x=True, need_base=True, 
                                                    B, C, H, W, ctypes.byref(p), float(w), _stream(x))
         _lib.check(rc, "ee_edge_blend_bwd_f32")
     return g_x, g_base
+
+
+def pgd_iteration(x, base, g_out, x0, params, w, alpha_signed, eps, out=None, g_x=None, g_base=None, x_next=None,
+                  want_out=True, want_base=True):
+    """One iteration of the edge-enhanced PGD hot path in ONE C-ABI call (ee_edge_pgd_iteration_f32): fused forward
+    (skipped with want_out=False), fused backward of `g_out`, sign / project / clamp update from the edge-path gradient.
+    Dense NCHW tensors; returns (out, g_x, g_base, x_next)."""
+    x, base, g_out, x0 = _same(x, base, g_out, x0)
+    if x.dim() != 4:
+        raise ValueError("img must be [B,C,H,W]")
+    B, C, H, W = x.shape
+    out = _out_like(x, out) if want_out else None
+    g_x = _out_like(x, g_x)
+    g_base = _out_like(x, g_base) if want_base else None
+    x_next = _out_like(x, x_next)
+    if x.numel():
+        p = _with_layout(params, False)
+        with _on_device(x):
+            rc = _lib.load().ee_edge_pgd_iteration_f32(_ptr(x), _ptr(base), _ptr(g_out), _ptr(x0), _ptr(out), _ptr(g_x),
+                                                       _ptr(g_base), _ptr(x_next), B, C, H, W, ctypes.byref(p), float(w),
+                                                       float(alpha_signed), float(eps), _stream(x))
+        _lib.check(rc, "ee_edge_pgd_iteration_f32")
+    return out, g_x, g_base, x_next
+
+
+def _gauss9(gauss):
+    g = np.ascontiguousarray(np.asarray(gauss, dtype=np.float32).reshape(-1))
+    if g.size != 9:
+        raise NotImplementedError("edge_b200: the gf option uses the 3x3 Gaussian of the reference (resnet_EE.py:133-136)")
+    return (ctypes.c_float * 9)(*[float(v) for v in g])
+
+
+def gf_blend(edge, base, gauss, w, out=None):
+    """out = clamp(base + w * conv2d(edge, gauss, padding=1), 0, 1): the with_gf=True blend (resnet_EE.py:185-191)."""
+    base = _chk(base, "base")
+    B, C, H, W = base.shape
+    edge = _chk(edge, "edge", (B, 1, H, W))
+    out = _out_like(base, out)
+    if base.numel():
+        with _on_device(base):
+            rc = _lib.load().ee_gf_blend_fwd_f32(_ptr(edge), _ptr(base), _ptr(out), B, C, H, W, _gauss9(gauss), float(w),
+                                                 _stream(base))
+        _lib.check(rc, "ee_gf_blend_fwd_f32")
+    return out
+
+
+def gf_blend_backward(g_out, edge, base, gauss, w, need_edge=True, need_base=True):
+    """(g_edge, g_base) of gf_blend in one pass."""
+    base = _chk(base, "base")
+    B, C, H, W = base.shape
+    edge = _chk(edge, "edge", (B, 1, H, W))
+    g_out = _chk(g_out, "grad_out", base.shape)
+    g_edge = torch.empty_like(edge) if need_edge else None
+    g_base = torch.empty_like(base) if need_base else None
+    if base.numel() and (need_edge or need_base):
+        with _on_device(base):
+            rc = _lib.load().ee_gf_blend_bwd_f32(_ptr(g_out), _ptr(edge), _ptr(base), _ptr(g_edge), _ptr(g_base), B, C, H, W,
+                                                 _gauss9(gauss), float(w), _stream(base))
+        _lib.check(rc, "ee_gf_blend_bwd_f32")
+    return g_edge, g_base
 
 
 def _same(*ts):
@@ -443,6 +507,22 @@ class EdgeEnhanceFn(torch.autograd.Function):
         need_x, need_base = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         g_x, g_base = edge_blend_backward(g_out, img, base, ctx.params, ctx.w, need_x, need_base)
         return g_x, g_base, None, None
+
+
+class GfBlendFn(torch.autograd.Function):
+    """out = clamp(base + w * gauss3x3_zero_pad(edge), 0, 1) -- the `with_gf=True` blend of the *_EE models."""
+
+    @staticmethod
+    def forward(ctx, edge, base, gauss, w):
+        ctx.gauss, ctx.w = gauss, float(w)
+        ctx.save_for_backward(edge, base)
+        return gf_blend(edge, base, gauss, w)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        edge, base = ctx.saved_tensors
+        g_edge, g_base = gf_blend_backward(g_out, edge, base, ctx.gauss, ctx.w, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return g_edge, g_base, None, None
 
 
 class HfsFn(torch.autograd.Function):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define EE_VERSION 100 /* 0.1.0 */
+#define EE_VERSION 200 /* 0.2.0 */
 
 enum {
     EE_OK = 0,
@@ -63,8 +63,17 @@ typedef struct EEParams {
     int32_t has_low;    /* low_threshold is not None                                            */
     int32_t has_high;   /* high_threshold is not None (STEP125 requires it, core.py:578-583)    */
     int32_t hysteresis; /* forward(hysteresis=...); ignored by STEP125                          */
-    int32_t reserved;   /* must be 0                                                            */
+    int32_t flags;      /* EE_FLAG_* bits, 0 by default                                         */
 } EEParams;
+
+/* EEParams.flags.
+ * EE_FLAG_NAN_COMPAT: reproduce the reference backward's NaNs.  autograd differentiates (gx^2 + gy^2) ** 0.5
+ * (core.py:250, :453, :571) at magnitude 0 as 0 * inf, so the reference's input gradient is NaN on the 5 x 5
+ * neighbourhood of every pixel whose gradient magnitude is exactly 0 (flat regions: MNIST backgrounds, saturated
+ * patches) and torch.sign(NaN) = 0 freezes those pixels in PGD / FGSM.  Default (flag clear): the sub-gradient 0.
+ * With the flag the backward entry points write NaN into dL/dSgx, dL/dSgy there and let it spread through the two
+ * adjoint stencils exactly like the reference; they then run the shape-generic kernels (NCHW only). */
+enum { EE_FLAG_NAN_COMPAT = 1 };
 
 /* ---- edge filter: module-level drop-in -------------------------------------------------- */
 
@@ -76,7 +85,7 @@ int ee_edge_fwd_f32(const float* x, float* edge, int B, int C, int H, int W,
 /* g_x[B,C,H,W] = d(edge)/d(x)^T g_edge[B,1,H,W]; replaces autograd through the above incl.
  * To_compare/To_eq/BinaryConnectDeterministic.backward (core.py:138-145, :350-358, :375-382).
  * Forward intermediates are recomputed from x (no saved tensors).  Sub-gradient of
- * sqrt at 0 is 0 (the reference produces NaN there). */
+ * sqrt at 0 is 0 unless EE_FLAG_NAN_COMPAT asks for the reference's NaNs. */
 int ee_edge_bwd_f32(const float* g_edge, const float* x, float* g_x, int B, int C, int H, int W,
                     const EEParams* p, void* stream);
 
@@ -94,6 +103,17 @@ int ee_edge_blend_fwd_f32(const float* x, const float* base, float* out, float* 
 int ee_edge_blend_bwd_f32(const float* g_out, const float* x, const float* base, float* g_x_or_null,
                           float* g_base_or_null, int B, int C, int H, int W, const EEParams* p,
                           float w, void* stream);
+
+/* The `gf` option of the *_EE models (with_gf=True: Tiny_ImageNet/models_tinyimagenet/resnet_EE.py:185-187 and its
+ * copies): the edge map goes through a ZERO-padded 3 x 3 Gaussian (get_gaussian_kernel(3, 0, 1)) before the blend,
+ *     out = clamp(base + w * conv2d(edge, gauss, padding=1), 0, 1).
+ * No reference config enables it, so it is not fused into the filter kernels: the caller runs ee_edge_fwd_f32 first and
+ * ee_edge_bwd_f32 last.  fwd reads edge[B,1,H,W] and base, writes out.  bwd reads g_out, edge, base and writes
+ * g_edge[B,1,H,W] = conv2d^T(w * sum_c g_pre_c) (may be NULL) and g_base = g_pre = g_out * [0 <= pre <= 1] (may be NULL). */
+int ee_gf_blend_fwd_f32(const float* edge, const float* base, float* out, int B, int C, int H, int W,
+                        const float gauss[9], float w, void* stream);
+int ee_gf_blend_bwd_f32(const float* g_out, const float* edge, const float* base, float* g_edge_or_null,
+                        float* g_base_or_null, int B, int C, int H, int W, const float gauss[9], float w, void* stream);
 
 /* Workspace the edge entry points need from the caller: always 0 (recompute formulation). */
 size_t ee_aux_bytes(int B, int C, int H, int W, int variant);
@@ -137,6 +157,18 @@ int ee_avmixup_mix_f32(const float* x_adv, const float* inputs, const double* we
  * l2_norm (:360-366).  One CTA per sample; out must NOT alias x. */
 int ee_pgd_l2_step_f32(const float* x, const float* g, const float* x0, float* out, int B,
                        int64_t n_per_sample, float step, float eps, void* stream);
+
+/* One whole iteration of the edge-enhanced PGD hot path (the loop body of utils/attacks.py:19-27 around a model whose
+ * front end is the fused edge filter + blend) enqueued by ONE call, for callers that hold the upstream gradient g_out
+ * already (benchmarks, CUDA-graph capture, custom training loops):
+ *     out    = clamp(base + w*edge(x), 0, 1)                      (skipped when out_or_null == NULL)
+ *     g_x, g_base = adjoint of the above applied to g_out
+ *     x_next = clamp(min(max(x + alpha_signed*sign(g_x), x0-eps), x0+eps), 0, 1)
+ * Same kernels, same arithmetic as the three separate entry points; x_next must not alias x. */
+int ee_edge_pgd_iteration_f32(const float* x, const float* base, const float* g_out, const float* x0,
+                              float* out_or_null, float* g_x, float* g_base_or_null, float* x_next,
+                              int B, int C, int H, int W, const EEParams* p, float w,
+                              float alpha_signed, float eps, void* stream);
 
 /* ---- straight-through helper Functions (elementwise; out may alias g/in) ----------------- */
 int ee_to_compare_fwd_f32(const float* in, float* out, int64_t n, float thr, void* stream);                 /* core.py:338-347 */

@@ -38,6 +38,7 @@ typedef struct {
     float low_thr, high_thr;  /* thresholds, already rounded to fp32 like torch does       */
     int   has_low, has_high;  /* "is not None" flags of forward() (core.py:295,309)        */
     int   hysteresis;         /* core.py:317                                               */
+    int   nan_compat;         /* backward: NaN where the magnitude is 0, like autograd through (gx^2+gy^2)**0.5 (core.py:250, :453, :571) */
 } ee_oracle_params;
 
 static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -425,6 +426,9 @@ static void edge_backward_image(const float *ge, int C, int H, int W, const ee_o
          * the same value up to ~2 ulp, well inside the 1e-5 gradient tolerance.
          * Sub-gradient at mag == 0 defined as 0 (the reference yields NaN). */
         float m = pl->mag[q];
+        /* nan_compat: what autograd really computes at u = 0: g * 0.5 * u^-0.5 = g * inf (NaN for g == 0), times
+         * 2*gx1 = 0 -> NaN whatever g is; the two adjoint stencils below then spread it over the 5 x 5 neighbourhood */
+        if (pr->nan_compat && m == 0.0f) { a[q] = NAN; b[q] = NAN; continue; }
         if (gm == 0.0f || m == 0.0f) { a[q] = 0.0f; b[q] = 0.0f; continue; }
         float t = gm / (m * fC);
         a[q] = t * pl->gx1[q];
@@ -603,28 +607,136 @@ static float rms_canonical(const float *v, int64_t n, const float *v2_sub, int m
     return sqrtf(wsum[0] / (float)n);
 }
 
-/* TRADES PGD-L2 step, attacks.py:391-399. */
-void ee_oracle_pgd_l2_step(const float *x, const float *g, const float *x0, float *out, int B,
-                           int64_t n_per, float step, float eps)
+/* The one-pass CUDA kernel (edge_enhancement_b200/csrc/ee_pgd_l2.cuh) keeps a sample on chip in a cluster of K CTAs of 512
+ * threads; its reduction order, restated: the sample's float4 words are cut into K slices of slice4 words; inside a slice
+ * thread t accumulates words t, t + 512, ... element by element with fmaf; shuffle tree (strides 16..1) inside each warp;
+ * the 16 warp sums padded with zeros to 32 and the same tree; then the K slice sums left to right. */
+#define EE_L2C_THREADS 512
+#define EE_L2C_TARGET_SLICE4 3072
+#define EE_L2C_MAX_CLUSTER 8
+static int l2_cluster_plan(int64_t n_per, int *K, int64_t *slice4)
 {
+    if (n_per <= 0 || (n_per & 3)) return 0;
+    int64_t n4 = n_per >> 2;
+    int k = 1;
+    while (k < EE_L2C_MAX_CLUSTER && (n4 + k - 1) / k > EE_L2C_TARGET_SLICE4) k <<= 1;
+    int64_t s4 = (n4 + k - 1) / k;
+    if (128 + (size_t)s4 * 32 > (size_t)227 * 1024) return 0;
+    *K = k; *slice4 = s4;
+    return 1;
+}
+static float rms_cluster(const float *v, int64_t n, int K, int64_t slice4)
+{
+    const int64_t n4 = n >> 2;
+    float total = 0.0f;
+    for (int k = 0; k < K; ++k) {
+        int64_t lo4 = (int64_t)k * slice4, hi4 = lo4 + slice4 < n4 ? lo4 + slice4 : n4;
+        float part[EE_L2C_THREADS];
+        for (int t = 0; t < EE_L2C_THREADS; ++t) {
+            float acc = 0.0f;
+            for (int64_t i = lo4 + t; i < hi4; i += EE_L2C_THREADS)
+                for (int c = 0; c < 4; ++c) { float e = v[4 * i + c]; acc = fmaf(e, e, acc); }
+            part[t] = acc;
+        }
+        float wsum[32];
+        for (int w = 0; w < 32; ++w) wsum[w] = 0.0f;
+        for (int w = 0; w < EE_L2C_THREADS / 32; ++w) {
+            float *p = part + 32 * w;
+            for (int s = 16; s >= 1; s >>= 1)
+                for (int l = 0; l < s; ++l) p[l] = p[l] + p[l + s];
+            wsum[w] = p[0];
+        }
+        for (int s = 16; s >= 1; s >>= 1)
+            for (int l = 0; l < s; ++l) wsum[l] = wsum[l] + wsum[l + s];
+        total = (k == 0) ? wsum[0] : total + wsum[0];
+    }
+    return sqrtf(total / (float)n);
+}
+
+/* TRADES PGD-L2 step, attacks.py:391-399.  mode < 0: the order the library picks for 16-byte aligned tensors (cluster
+ * kernel when the sample fits, else the three-pass kernel); mode 0: the three-pass kernel's order. */
+void ee_oracle_pgd_l2_step(const float *x, const float *g, const float *x0, float *out, int B,
+                           int64_t n_per, float step, float eps, int mode)
+{
+    int K = 0; int64_t slice4 = 0;
+    const int cluster = (mode < 0) && l2_cluster_plan(n_per, &K, &slice4);
 #pragma omp parallel for schedule(static)
     for (int b = 0; b < B; ++b) {
         const float *xb = x + (int64_t)b * n_per, *gb = g + (int64_t)b * n_per, *x0b = x0 + (int64_t)b * n_per;
         float *ob = out + (int64_t)b * n_per;
-        float gn = rms_canonical(gb, n_per, NULL, 0) + 1e-8f;      /* :391 */
-        for (int64_t i = 0; i < n_per; ++i) ob[i] = xb[i] + step * (gb[i] / gn);   /* :391-392 */
-        float dn = rms_canonical(ob, n_per, x0b, 1);               /* :394-395 */
+        float gn = (cluster ? rms_cluster(gb, n_per, K, slice4) : rms_canonical(gb, n_per, NULL, 0)) + 1e-8f;      /* :391 */
+        float dn;
+        if (cluster) {
+            for (int64_t i = 0; i < n_per; ++i) ob[i] = (xb[i] + step * (gb[i] / gn)) - x0b[i];    /* d = xa - x0, :391-394 */
+            dn = rms_cluster(ob, n_per, K, slice4);                                                 /* :395 */
+        } else {
+            for (int64_t i = 0; i < n_per; ++i) ob[i] = xb[i] + step * (gb[i] / gn);               /* :391-392 */
+            dn = rms_canonical(ob, n_per, x0b, 1);                                                  /* :394-395 */
+        }
         int cond = dn > eps;                                       /* :396 */
         float scale = eps / dn;                                    /* :397 */
         for (int64_t i = 0; i < n_per; ++i) {
-            float d = ob[i] - x0b[i];
+            float d = cluster ? ob[i] : ob[i] - x0b[i];
             if (cond) d = d * scale;
             ob[i] = minn(maxn(x0b[i] + d, 0.0f), 1.0f);            /* :398-399 */
         }
     }
 }
 
-/* STE helper Functions (core.py:115-145, :329-382), elementwise. */
+/* with_gf=True blend, Tiny_ImageNet/models_tinyimagenet/resnet_EE.py:185-191: the edge map through a ZERO-padded 3x3
+ * Gaussian (F.conv2d(.., padding=1)), then clamp(base + w * that, 0, 1).  Same tap order as blur3_replicate. */
+static float gf_tap(const float *p, int H, int W, int i, int j, float c0, float c1, float c2)
+{
+    float pu = fmaf(c1, at0(p, H, W, i - 1, j), c0 * (at0(p, H, W, i - 1, j - 1) + at0(p, H, W, i - 1, j + 1)));
+    float qm = fmaf(c2, at0(p, H, W, i, j), c1 * (at0(p, H, W, i, j - 1) + at0(p, H, W, i, j + 1)));
+    float pd = fmaf(c1, at0(p, H, W, i + 1, j), c0 * (at0(p, H, W, i + 1, j - 1) + at0(p, H, W, i + 1, j + 1)));
+    return (pu + qm) + pd;
+}
+void ee_oracle_gf_blend_fwd(const float *edge, const float *base, float *out, int B, int C, int H, int W,
+                            float c0, float c1, float c2, float w)
+{
+    const size_t hw = (size_t)H * W;
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b)
+        for (int i = 0; i < H; ++i)
+            for (int j = 0; j < W; ++j) {
+                float we = w * gf_tap(edge + b * hw, H, W, i, j, c0, c1, c2);
+                for (int c = 0; c < C; ++c) {
+                    size_t o = ((size_t)b * C + c) * hw + (size_t)i * W + j;
+                    out[o] = clamp01_nan(base[o] + we);
+                }
+            }
+}
+/* g_base = g_out * [0 <= pre <= 1]; t = sum_c w * g_base_c (fma chain); g_edge = conv^T(t) = the same symmetric taps */
+int ee_oracle_gf_blend_bwd(const float *g_out, const float *edge, const float *base, float *g_edge, float *g_base,
+                           int B, int C, int H, int W, float c0, float c1, float c2, float w)
+{
+    const size_t hw = (size_t)H * W;
+    float *t = (float *)malloc(sizeof(float) * hw * (size_t)B);
+    if (!t) return 1;
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b) {
+        for (int i = 0; i < H; ++i)
+            for (int j = 0; j < W; ++j) {
+                float we = w * gf_tap(edge + b * hw, H, W, i, j, c0, c1, c2);
+                float acc = 0.0f;
+                for (int c = 0; c < C; ++c) {
+                    size_t o = ((size_t)b * C + c) * hw + (size_t)i * W + j;
+                    float pre = base[o] + we;
+                    float gp = (pre >= 0.0f && pre <= 1.0f) ? g_out[o] : 0.0f;
+                    acc = (c == 0) ? gp * w : fmaf(gp, w, acc);
+                    if (g_base) g_base[o] = gp;
+                }
+                t[b * hw + (size_t)i * W + j] = acc;
+            }
+        if (g_edge)
+            for (int i = 0; i < H; ++i)
+                for (int j = 0; j < W; ++j) g_edge[b * hw + (size_t)i * W + j] = gf_tap(t + b * hw, H, W, i, j, c0, c1, c2);
+    }
+    free(t);
+    return 0;
+}
+
 void ee_oracle_to_compare_fwd(const float *in, float *out, int64_t n, float thr)
 { for (int64_t i = 0; i < n; ++i) out[i] = to_compare(in[i], thr); }
 void ee_oracle_to_compare_bwd(const float *g, const float *in, float *out, int64_t n, float thr)

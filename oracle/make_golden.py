@@ -33,7 +33,8 @@ EDGE_CASES = [
     ("step125_tiny_3x32", "CannyFilter_step125_1", "step125", (4, 3, 32, 32), "uniform", 0.0, 1.0, None, 76 / 255, False, 1.0, 101),
     ("step125_tiny_3x64", "CannyFilter_step125_1", "step125", (2, 3, 64, 64), "uniform", 0.0, 1.0, None, 76 / 255, False, 1.0, 102),
     ("step125_mnist_1x28", "CannyFilter_step125_1", "step125", (8, 1, 28, 28), "sparse", 0.3, 1.0, None, 51 / 255, False, 1.0, 103),
-    ("step125_smooth_w05", "CannyFilter_step125_1", "step125", (2, 3, 48, 40), "smooth", 0.0, 1.0, None, 76 / 255, False, 0.5, 104),
+    # (high 40/255: edge fraction 0.43 -- with the Tiny-ImageNet threshold 76/255 this smooth input has no edge at all)
+    ("step125_smooth_w05", "CannyFilter_step125_1", "step125", (2, 3, 48, 40), "smooth", 0.0, 1.0, None, 40 / 255, False, 0.5, 104),
     ("step125_odd_17x23", "CannyFilter_step125_1", "step125", (2, 3, 17, 23), "uniform", 0.05, 1.0, None, 60 / 255, False, 1.0, 105),
     ("canny_tiny_3x32", "CannyFilter", "canny", (4, 3, 32, 32), "uniform", 0.0, 1.0, 38 / 255, 76 / 255, True, 1.0, 201),
     ("canny_tiny_3x64", "CannyFilter", "canny", (2, 3, 64, 64), "uniform", 0.0, 1.0, 38 / 255, 76 / 255, True, 1.0, 202),
@@ -195,16 +196,170 @@ def run_add_square_cases(rc):
         torch.Tensor.cuda = orig_cuda
 
 
+def flat_patch_input(seed, shape):
+    """8-bit quantised image with saturated / flat patches (what real MNIST / ImageNet pixels look like): the gradient
+    magnitude is EXACTLY 0 inside the patches whatever the summation order, so the reference's NaN set is deterministic."""
+    x, base, g_out, _ = T.make_inputs(seed, *shape, kind="uniform")
+    x = np.round(np.clip(x * 3 - 1, 0, 1) * 255).astype(np.float32) / np.float32(255)
+    H, W = shape[2], shape[3]
+    x[:, :, H // 6:H // 2, W // 10:W // 2] = 1.0
+    x[:, :, (2 * H) // 3:H - 2, W // 2 + 2:W - 1] = 0.0
+    x[:, :, 0:4, 0:5] = 0.0                    # flat patches touching a corner and an edge of the image
+    x[:, :, H - 3:, W - 6:] = 1.0
+    return x, base, g_out
+
+
+NAN_CASES = [   # name, class, variant, shape, alpha, low, high, seed
+    ("step125_3x32", "CannyFilter_step125_1", "step125", (2, 3, 32, 32), 0.0, None, 76 / 255, 701),
+    ("canny_3x32", "CannyFilter", "canny", (2, 3, 32, 32), 0.0, 38 / 255, 76 / 255, 702),
+    ("bpda_3x32", "CannyFilter_BPDA", "bpda", (2, 3, 32, 32), 0.0, 38 / 255, 76 / 255, 703),
+    ("canny_mnist_1x28", "CannyFilter", "canny", (4, 1, 28, 28), 0.3, 25 / 255, 51 / 255, 704),
+]
+
+
+def run_nan_cases(rc):
+    """The reference's backward on inputs with flat regions: g_x is NaN on the 5x5 neighbourhood of every pixel whose
+    gradient magnitude is 0 (autograd of (gx^2+gy^2)**0.5 at 0).  Pins EE_FLAG_NAN_COMPAT / nan_compat=True: the NaN set
+    exactly, the finite entries within 1e-5."""
+    for name, cls, variant, shape, alpha, low, high, seed in NAN_CASES:
+        x, base, g_out = flat_patch_input(seed, shape)
+        with ref_loader.quiet():
+            f = getattr(rc, cls)(use_cuda=False, alpha=alpha)
+        xt = torch.from_numpy(x).requires_grad_()
+        bt = torch.from_numpy(base).requires_grad_()
+        edge = f(xt, low_threshold=low, high_threshold=high, hysteresis=True)
+        out = torch.clamp(bt + 1.0 * edge, 0.0, 1.0)
+        out.backward(torch.from_numpy(g_out))
+        g_x = xt.grad.numpy()
+        np.savez_compressed(os.path.join(OUT, "nan_%s.npz" % name), x=x, base=base, g_out=g_out,
+                            edge=edge.detach().numpy().astype(np.float32), g_x=g_x, g_base=bt.grad.numpy(),
+                            meta=np.array([variant, str(alpha), "1.0", repr(low), repr(high), "1", "1.0"]))
+        print("nan_%-18s NaN fraction of g_x %.3f, inf %d" % (name, np.isnan(g_x).mean(), np.isinf(g_x).sum()))
+
+
+def run_ste_cases(rc):
+    """Standalone To_compare / To_eq / BinaryConnectDeterministic (utils/core.py:121-145, :329-382), forward and backward,
+    incl. a negative and a zero threshold and values on both sides of every window (thr, 1.001, 0.5, 0)."""
+    r = T.rng(801)
+    v = (r.random((3, 1, 9, 11), dtype=np.float32) * 1.4 - 0.2).astype(np.float32)
+    flat = v.reshape(-1)
+    flat[:12] = np.array([0.0, -0.0, 0.5, 0.25, 0.3, 1.001, 1.0010000467300415, 1.0009999275207520, -1.001, 1.5, -1.5, 0.29803923],
+                         dtype=np.float32)
+    g = r.standard_normal(v.shape, dtype=np.float32)
+    out = {"v": v, "g": g}
+    for tag, thr in (("pos", 76 / 255), ("neg", -0.1), ("zero", 0.0)):
+        t = torch.from_numpy(v).requires_grad_()
+        y = rc.To_compare.apply(t, torch.tensor(thr))
+        y.backward(torch.from_numpy(g))
+        out["cmp_%s_thr" % tag] = np.array(thr)
+        out["cmp_%s_fwd" % tag] = y.detach().numpy()
+        out["cmp_%s_bwd" % tag] = t.grad.numpy()
+    t = torch.from_numpy(v).requires_grad_()
+    y = rc.To_eq.apply(t)
+    y.backward(torch.from_numpy(g))
+    out["eq_fwd"], out["eq_bwd"] = y.detach().numpy(), t.grad.numpy()
+    t = torch.from_numpy(v).requires_grad_()
+    y = rc.BinaryConnectDeterministic.apply(t)
+    y.backward(torch.from_numpy(g))
+    out["bcd_fwd"], out["bcd_bwd"] = y.detach().numpy(), t.grad.numpy()
+    out["safe_sign"] = rc.safeSign(torch.from_numpy(v)).numpy()
+    np.savez_compressed(os.path.join(OUT, "ste_functions.npz"), **out)
+    print("ste_functions: To_compare x3 thresholds, To_eq, BinaryConnectDeterministic, safeSign")
+
+
+def run_gf_case(rc):
+    """with_gf=True blend exactly as Tiny_ImageNet/models_tinyimagenet/resnet_EE.py:133-136, :185-191 writes it."""
+    import torch.nn.functional as Fn
+    x, base, g_out, _ = T.make_inputs(901, 2, 3, 24, 40, kind="uniform")
+    with ref_loader.quiet():
+        f = rc.CannyFilter_step125_1(use_cuda=False, alpha=0.0)
+    gaussian_2D = rc.get_gaussian_kernel(3, 0., 1.)
+    wg = torch.from_numpy(gaussian_2D).unsqueeze(0).unsqueeze(0).type(torch.float)
+    xt = torch.from_numpy(x).requires_grad_()
+    bt = torch.from_numpy(base).requires_grad_()
+    edge = f(xt, low_threshold=38 / 255, high_threshold=76 / 255, hysteresis=True)
+    edge.retain_grad()
+    x_canny = Fn.conv2d(edge.type(torch.float), wg, padding=1)
+    out = torch.clamp(bt + 0.8 * x_canny, 0.0, 1.0)
+    out.backward(torch.from_numpy(g_out))
+    np.savez_compressed(os.path.join(OUT, "gf_blend.npz"), x=x, base=base, g_out=g_out, edge=edge.detach().numpy(),
+                        out=out.detach().numpy(), g_edge=edge.grad.numpy(), g_base=bt.grad.numpy(), g_x=xt.grad.numpy(),
+                        w=np.array(0.8), high=np.array(76 / 255))
+    print("gf_blend: edge fraction %.3f" % float(edge.mean()))
+
+
+class TracedEENet(TinyEENet):
+    """TinyEENet that records, for every forward the attack makes, the input, the reference's edge mask and (through a
+    tensor hook) the input gradient the reference's torch.autograd.grad returns."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.xs, self.edges, self.grads = [], [], []
+
+    def forward(self, x):
+        self.xs.append(x.detach().clone())
+        if x.requires_grad:
+            x.register_hook(lambda g: self.grads.append(g.detach().clone()))
+        e = self.canny(x, low_threshold=self.low, high_threshold=self.high, hysteresis=True)
+        self.edges.append(e.detach().clone())
+        z = torch.clamp(x + self.w * e, 0.0, 1.0)
+        return z.reshape(z.shape[0], -1) @ self.weight.to(z.device).t()
+
+
+def run_teacher_forced_pgd(rc, ra):
+    """One full reference PGD-10 run (utils/attacks.py:12-29) per filter variant with every iterate traced: x_i, the
+    reference's edge mask at x_i and its gradient g_i.  The tests replay it teacher-forced: x_0 = x, x_{i+1} = fused
+    step(x_i, REFERENCE g_i); at each x_i the mask must be exact and our gradient within 1e-5 of g_i, and the last iterate
+    must equal the reference's x_adv bit for bit -- which removes the sign-ambiguity caveat of comparing two free-running
+    trajectories (the step is exact given the same gradient)."""
+    class Args:
+        random = False
+        epsilon = 16 / 255
+    B, C, H, W, n_class, steps = 4, 3, 32, 32, 10, 10
+    x = T.rng(1001).random((B, C, H, W), dtype=np.float32)
+    y = T.rng(1002).integers(0, n_class, size=(B,))
+    for variant, cls in (("step125", "CannyFilter_step125_1"), ("canny", "CannyFilter"), ("bpda", "CannyFilter_BPDA")):
+        with ref_loader.quiet():
+            canny = getattr(rc, cls)(use_cuda=False, alpha=0.0)
+        model = TracedEENet(canny, 38 / 255, 76 / 255, 1.0, C, H, W, n_class, seed=1003)
+        xadv = ra.PGD(model, Args, torch.from_numpy(x), torch.from_numpy(y), steps, 2 / 255)
+        assert len(model.xs) == steps and len(model.grads) == steps
+        gs = torch.stack(model.grads).numpy()          # x_i is not stored: x_{i+1} = step(x_i, g_i) bit for bit, x_0 = x
+        edges = np.packbits(torch.stack(model.edges).numpy().astype(np.uint8).reshape(-1))
+        np.savez_compressed(os.path.join(OUT, "pgd10_traced_%s.npz" % variant), x=x, y=y, gs=gs, edges=edges,
+                            x_adv=xadv.numpy(), head_seed=np.array(1003), n_class=np.array(n_class))
+        print("pgd10_traced_%s: finite g %.4f, min |g| %.3g, zeros %d" % (variant, np.isfinite(gs).mean(),
+              np.abs(gs[np.isfinite(gs)]).min(), int((gs == 0).sum())))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(1)        # fixed reduction order for the fixtures
     rc, ra = ref_loader.load()
-    for case in EDGE_CASES:
-        run_edge_case(rc, case)
-    run_attack_cases(rc, ra)
-    run_add_square_cases(rc)
-    run_attack_extras()
+    only = set(sys.argv[1:])        # e.g. `python -m oracle.make_golden nan ste` regenerates just those groups
+    want = lambda group: not only or group in only
+    if want("edge"):
+        for case in EDGE_CASES:
+            if not only or not (only - {"edge"}) or case[0] in only:
+                run_edge_case(rc, case)
+    for case in EDGE_CASES:          # single edge cases by name
+        if case[0] in only and "edge" not in only:
+            run_edge_case(rc, case)
+    if want("attack"):
+        run_attack_cases(rc, ra)
+    if want("square"):
+        run_add_square_cases(rc)
+    if want("extras"):
+        run_attack_extras()
+    if want("nan"):
+        run_nan_cases(rc)
+    if want("ste"):
+        run_ste_cases(rc)
+    if want("gf"):
+        run_gf_case(rc)
+    if want("traced"):
+        run_teacher_forced_pgd(rc, ra)
     print("fixtures written to", OUT)
 
 

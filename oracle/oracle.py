@@ -20,7 +20,7 @@ class OracleParams(ctypes.Structure):
                 ("alpha", ctypes.c_float),
                 ("low_thr", ctypes.c_float), ("high_thr", ctypes.c_float),
                 ("has_low", ctypes.c_int), ("has_high", ctypes.c_int),
-                ("hysteresis", ctypes.c_int)]
+                ("hysteresis", ctypes.c_int), ("nan_compat", ctypes.c_int)]
 
 
 def gaussian3(mu=0.0, sigma=1.0):
@@ -33,13 +33,13 @@ def gaussian3(mu=0.0, sigma=1.0):
     return g.astype(np.float32)
 
 
-def make_params(variant="step125", mu=0.0, sigma=1.0, alpha=0.0, low=None, high=None, hysteresis=False):
+def make_params(variant="step125", mu=0.0, sigma=1.0, alpha=0.0, low=None, high=None, hysteresis=False, nan_compat=False):
     g = gaussian3(mu, sigma)
     v = VARIANTS[variant] if isinstance(variant, str) else int(variant)
     return OracleParams(v, float(g[0, 0]), float(g[0, 1]), float(g[1, 1]), float(np.float32(alpha)),
                         float(np.float32(0.0 if low is None else low)),
                         float(np.float32(0.0 if high is None else high)),
-                        int(low is not None), int(high is not None), int(bool(hysteresis)))
+                        int(low is not None), int(high is not None), int(bool(hysteresis)), int(bool(nan_compat)))
 
 
 _LIB = None
@@ -85,8 +85,12 @@ def lib():
     L.ee_oracle_free_at_step.restype = None
     L.ee_oracle_cw_linf_step.argtypes = [fp, fp, fp, fp, fp, fp, i64, f, f]
     L.ee_oracle_cw_linf_step.restype = None
-    L.ee_oracle_pgd_l2_step.argtypes = [fp, fp, fp, fp, i, i64, f, f]
+    L.ee_oracle_pgd_l2_step.argtypes = [fp, fp, fp, fp, i, i64, f, f, i]
     L.ee_oracle_pgd_l2_step.restype = None
+    L.ee_oracle_gf_blend_fwd.argtypes = [fp, fp, fp, i, i, i, i, f, f, f, f]
+    L.ee_oracle_gf_blend_fwd.restype = None
+    L.ee_oracle_gf_blend_bwd.argtypes = [fp, fp, fp, fp, fp, i, i, i, i, f, f, f, f]
+    L.ee_oracle_gf_blend_bwd.restype = i
     L.ee_oracle_add_clamp.argtypes = [fp, fp, fp, i64, f, f]
     L.ee_oracle_add_clamp.restype = None
     L.ee_oracle_avmixup_mix.argtypes = [fp, fp, ctypes.POINTER(ctypes.c_double), fp, i, i64, f]
@@ -191,12 +195,33 @@ def cw_linf_step(adv, g, x, min_x, max_x, step, magnitude):
     return out
 
 
-def pgd_l2_step(x, g, x0, step, eps):
+def pgd_l2_step(x, g, x0, step, eps, three_pass=False):
+    """three_pass=True: the reduction order of the any-shape three-pass kernel instead of the cluster kernel's."""
     x, g, x0 = _f32(x), _f32(g), _f32(x0)
     out = np.empty_like(x)
     B = x.shape[0]
-    lib().ee_oracle_pgd_l2_step(_p(x), _p(g), _p(x0), _p(out), B, x.size // B, step, eps)
+    lib().ee_oracle_pgd_l2_step(_p(x), _p(g), _p(x0), _p(out), B, x.size // B, step, eps, 0 if three_pass else -1)
     return out
+
+
+def gf_blend_fwd(edge, base, w, gauss=None):
+    """clamp(base + w * conv2d(edge, gauss, padding=1), 0, 1) -- the with_gf=True blend (resnet_EE.py:185-191)."""
+    edge, base = _f32(edge), _f32(base)
+    g = gaussian3() if gauss is None else np.asarray(gauss, np.float32)
+    B, C, H, W = base.shape
+    out = np.empty_like(base)
+    lib().ee_oracle_gf_blend_fwd(_p(edge), _p(base), _p(out), B, C, H, W, float(g[0, 0]), float(g[0, 1]), float(g[1, 1]), w)
+    return out
+
+
+def gf_blend_bwd(g_out, edge, base, w, gauss=None):
+    g_out, edge, base = _f32(g_out), _f32(edge), _f32(base)
+    g = gaussian3() if gauss is None else np.asarray(gauss, np.float32)
+    B, C, H, W = base.shape
+    g_edge, g_base = np.empty_like(edge), np.empty_like(base)
+    _chk(lib().ee_oracle_gf_blend_bwd(_p(g_out), _p(edge), _p(base), _p(g_edge), _p(g_base), B, C, H, W,
+                                      float(g[0, 0]), float(g[0, 1]), float(g[1, 1]), w))
+    return g_edge, g_base
 
 
 def add_clamp(x, noise, lo=0.0, hi=1.0):

@@ -49,11 +49,13 @@ def test_module_matches_torch_fft_and_autograd(N, r):
     assert float(m(cb - 0.5).abs().max()) < 1e-5
 
 
-def test_unsupported_shapes_take_the_fft_path_and_non_contiguous_inputs_work():
+def test_unsupported_shapes_raise_and_non_contiguous_inputs_work():
     assert not F_ee.hfs_supported(96, 12)
     m = core.HighFreqSuppress(96, 96, 12)
     x = torch.rand((2, 3, 96, 96), device=DEV)
-    assert torch.equal(m(x), m._fft_forward(x))
+    with pytest.raises(RuntimeError):
+        m(x)                                     # no silent torch.fft fallback
+    assert torch.equal(core.HighFreqSuppress(96, 96, 12, impl='torch_fft')(x), m._fft_forward(x))
     with pytest.raises(RuntimeError):
         F_ee.hfs(x, 12)
     m64 = core.HighFreqSuppress(64, 64, 8)

@@ -31,7 +31,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), "libedge_b200.so does not export %s" % name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert L.ee_version() == 100
+    assert L.ee_version() == 200
     assert L.ee_aux_bytes(256, 3, 64, 64, 0) == 0
     assert L.ee_last_error() is not None
 
@@ -162,7 +162,7 @@ def test_install_aliases_utils_modules():
 def test_high_freq_suppress_restatement():
     """torch.fft restatement of utils/core.py:15-55: mask structure and basic behaviour (UNPINNED vs
     the reference, whose torch.rfft call cannot run on torch >= 1.8)."""
-    h = core.HighFreqSuppress(28, 28, 4)
+    h = core.HighFreqSuppress(28, 28, 4, impl='torch_fft')
     assert h.temp.shape == (1, 1, 28, 28, 1) and int(h.temp.sum()) == 64
     x = torch.rand(2, 3, 28, 28)
     y = h(x)
@@ -171,7 +171,7 @@ def test_high_freq_suppress_restatement():
     half = x.shape[-1] // 2 + 1                                              # the literal restatement: full FFT, one-sided C2R
     lit = torch.fft.irfft2(torch.fft.fft2(x)[..., :half] * h.temp[..., 0][..., :half], s=x.shape[-2:])
     assert torch.allclose(y, lit, atol=1e-6)
-    full = core.HighFreqSuppress(8, 8, 4)                                   # radius covers everything
+    full = core.HighFreqSuppress(8, 8, 4, impl='torch_fft')                 # radius covers everything
     z = torch.rand(1, 1, 8, 8)
     assert torch.allclose(full(z), z, atol=1e-5)
     if ref_loader.available():
@@ -248,9 +248,50 @@ def test_high_freq_suppress_equals_its_spatial_form():
         Qs = 2 * sin_sum / N
         x = np.random.default_rng(N).random((2, 3, N, N))
         want = A @ x @ Qc.T - Bm @ x @ Qs.T                    # Qc symmetric, Qs antisymmetric: x[h', w'] q(w - w')
-        got = core.HighFreqSuppress(N, N, r)(torch.from_numpy(x).float()).double().numpy()
+        got = core.HighFreqSuppress(N, N, r, impl='torch_fft')(torch.from_numpy(x).float()).double().numpy()
         assert np.abs(got - want).max() < 2e-5, (N, r, np.abs(got - want).max())
         # the operator is symmetric: <H a, b> == <a, H b>
         a, b = torch.rand(1, 1, N, N), torch.rand(1, 1, N, N)
-        h = core.HighFreqSuppress(N, N, r)
+        h = core.HighFreqSuppress(N, N, r, impl='torch_fft')
         assert abs(float((h(a) * b).sum() - (a * h(b)).sum())) < 1e-3
+
+
+def test_high_freq_suppress_two_c2r_semantics_are_bounded(capsys):
+    """The reference mask keeps frequency -r but not +r (not Hermitian), so `irfft(onesided=False)` of torch <= 1.7 could
+    mean (a) a C2R transform that reads the one-sided half (the default here, and what the native kernel implements) or
+    (b) the real part of the full complex inverse.  Both are implemented (c2r='onesided' / 'full'); this test quantifies how
+    far apart they are on images (they differ only in how the k = +-r rows / columns are weighted) and checks the closed
+    form of the difference: (b) - (a) lives entirely on the frequencies with |k1| = r or |k2| = r."""
+    rows = []
+    for N, r in ((28, 4), (64, 8), (224, 16)):
+        x = torch.from_numpy(np.random.default_rng(N).random((2, 3, N, N))).float()
+        a = core.HighFreqSuppress(N, N, r, c2r='onesided', impl='torch_fft')(x)
+        b = core.HighFreqSuppress(N, N, r, c2r='full', impl='torch_fft')(x)
+        diff = (a - b)
+        rel = float(diff.abs().max() / a.abs().max())
+        rows.append((N, r, float(diff.abs().max()), rel))
+        spec = torch.fft.fft2(diff.double())
+        k = np.fft.fftfreq(N, 1.0 / N).round().astype(int)
+        on_ring = (np.abs(k)[:, None] == r) | (np.abs(k)[None, :] == r)
+        off = spec.abs().numpy()[..., ~on_ring]
+        assert off.max() < 1e-3 * max(spec.abs().max().item(), 1e-30), (N, r)
+        assert 0 < rel < 0.5, (N, r, rel)          # different: on white-noise images (the worst case) 5-17 % of max |y|
+        # with the mask made Hermitian (drop k = -r) the two readings coincide
+        h = core.HighFreqSuppress(N, N, r, impl='torch_fft')
+        m = h.temp[..., 0].clone()
+        m[..., N - r, :] = 0; m[..., :, N - r] = 0
+        one = torch.fft.irfft2(torch.fft.fft2(x)[..., :N // 2 + 1] * m[..., :N // 2 + 1], s=(N, N))
+        two = torch.fft.ifft2(torch.fft.fft2(x) * m).real
+        assert float((one - two).abs().max()) < 1e-5
+    with capsys.disabled():
+        for N, r, mx, rel in rows:
+            print("\n[HFS c2r] %3d px / r %2d: max |onesided - full| = %.4f (%.2f %% of max |y|)" % (N, r, mx, 100 * rel), end="")
+
+
+def test_high_freq_suppress_raises_instead_of_falling_back():
+    with pytest.raises(RuntimeError):
+        core.HighFreqSuppress(64, 64, 8)(torch.rand(1, 3, 64, 64))         # CPU tensor, native impl: no fallback
+    with pytest.raises(NotImplementedError):
+        core.HighFreqSuppress(64, 64, 8, c2r='full')                       # native kernel = one-sided reading only
+    with pytest.raises(ValueError):
+        core.HighFreqSuppress(64, 64, 8, c2r='half')

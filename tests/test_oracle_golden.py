@@ -145,3 +145,105 @@ def test_attack_extras_bit_exact():
     z = np.load(os.path.join(GOLD, "attack_extras.npz"))
     assert np.array_equal(O.add_clamp(z["x0"], z["noise"]), z["start"])
     assert np.array_equal(O.avmixup_mix(z["x"], z["x0"], z["weight"], float(z["gamma"])), z["mixed"])
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: NaN-compatible backward, standalone STE Functions, with_gf blend, teacher-forced PGD-10
+# ---------------------------------------------------------------------------------------------
+NAN_FILES = sorted(glob.glob(os.path.join(GOLD, "nan_*.npz")))
+
+
+def check_nan_case(z, g_x, g_base, edge):
+    """The reference's NaN set exactly; finite entries within 1e-5 of max |g|; mask and g_base exact."""
+    ref = z["g_x"]
+    assert np.array_equal(edge, z["edge"])
+    assert np.array_equal(g_base, z["g_base"])
+    assert np.isnan(ref).mean() > 0.05, "fixture has no flat region"
+    assert np.array_equal(np.isnan(g_x), np.isnan(ref)), "%d entries differ in NaN-ness" % (np.isnan(g_x) != np.isnan(ref)).sum()
+    fin = np.isfinite(ref)
+    assert np.abs(g_x - ref)[fin].max() <= 1e-5 * np.abs(ref[fin]).max()
+
+
+@pytest.mark.parametrize("path", NAN_FILES, ids=lambda p: os.path.basename(p)[4:-4])
+def test_oracle_nan_compat_matches_reference_backward(path):
+    """Flat / saturated regions: the reference's autograd returns NaN on the 5x5 neighbourhood of every mag == 0 pixel
+    (ADVICE.md round 1).  nan_compat=True reproduces that set exactly; the default keeps the sub-gradient 0."""
+    assert len(NAN_FILES) >= 4
+    z, kw, w = load_edge_case(path)
+    p = O.make_params(nan_compat=True, **kw)
+    out, edge = O.edge_blend_fwd(z["x"], z["base"], p, w, want_edge=True)
+    g_x, g_base = O.edge_blend_bwd(z["g_out"], z["x"], z["base"], p, w)
+    check_nan_case(z, g_x, g_base, edge)
+    # default mode: finite everywhere, equal to the NaN-compatible result wherever that is finite
+    g0, _ = O.edge_blend_bwd(z["g_out"], z["x"], z["base"], O.make_params(**kw), w)
+    assert np.isfinite(g0).all()
+    fin = np.isfinite(g_x)
+    assert np.array_equal(g0[fin], g_x[fin])
+
+
+def test_ste_functions_oracle_matches_reference_fixture():
+    """To_compare / To_eq / BinaryConnectDeterministic / safeSign stand-alone (utils/core.py:115-145, :329-382), incl. the
+    negative-threshold quirk of To_compare.forward (two sequential masked writes: everything becomes 1)."""
+    z = np.load(os.path.join(GOLD, "ste_functions.npz"))
+    v, g = z["v"], z["g"]
+    for tag in ("pos", "neg", "zero"):
+        thr = float(z["cmp_%s_thr" % tag])
+        assert np.array_equal(O.to_compare_fwd(v, thr), z["cmp_%s_fwd" % tag]), tag
+        assert np.array_equal(O.to_compare_bwd(g, v, thr), z["cmp_%s_bwd" % tag]), tag
+    assert z["cmp_neg_fwd"].min() == 1.0                   # the quirk is really in the fixture
+    assert np.array_equal(O.to_eq_fwd(v), z["eq_fwd"]) and np.array_equal(O.to_eq_bwd(g, v), z["eq_bwd"])
+    assert z["eq_fwd"].sum() >= 1
+    assert np.array_equal(O.safe_sign_fwd(v), z["bcd_fwd"]) and np.array_equal(O.safe_sign_bwd(g, v), z["bcd_bwd"])
+    assert np.array_equal(O.safe_sign_fwd(v), z["safe_sign"])
+
+
+def test_gf_blend_oracle_matches_reference_fixture():
+    """with_gf=True (resnet_EE.py:185-191): Gaussian on the edge map, blend, and the autograd through both."""
+    z = np.load(os.path.join(GOLD, "gf_blend.npz"))
+    w = float(z["w"])
+    out = O.gf_blend_fwd(z["edge"], z["base"], w)
+    np.testing.assert_allclose(out, z["out"], rtol=1e-5, atol=1e-7)
+    g_edge, g_base = O.gf_blend_bwd(z["g_out"], z["edge"], z["base"], w)
+    assert np.array_equal(g_base, z["g_base"])
+    assert np.abs(g_edge - z["g_edge"]).max() <= 1e-5 * np.abs(z["g_edge"]).max()
+    # and the whole chain: filter backward of that g_edge == the reference's input gradient
+    p = O.make_params("step125", high=float(z["high"]))
+    assert np.array_equal(O.edge_fwd(z["x"], p), z["edge"])
+    g_x = O.edge_bwd(g_edge, z["x"], p)
+    fin = np.isfinite(z["g_x"])
+    assert np.abs(g_x - z["g_x"])[fin].max() <= 1e-5 * np.abs(z["g_x"][fin]).max()
+
+
+def head_gradient(zt, y, weight):
+    """dL/dz of the fixture model's head (oracle/make_golden.py TinyEENet): logits = z.flatten(1) @ W^T, CE(sum)."""
+    import torch
+    z = torch.from_numpy(zt).requires_grad_()
+    logits = z.reshape(z.shape[0], -1) @ torch.from_numpy(weight).t()
+    loss = torch.nn.functional.cross_entropy(logits, torch.from_numpy(y), reduction='sum')
+    return torch.autograd.grad(loss, [z])[0].numpy()
+
+
+@pytest.mark.parametrize("variant", ["step125", "canny", "bpda"])
+def test_oracle_teacher_forced_pgd10(variant):
+    """The reference's own PGD-10 run (utils/attacks.py:12-29), replayed teacher-forced: at every reference iterate x_i
+    the edge mask is exact and the input gradient within 1e-5 of max |g|; the step applied to the REFERENCE's (x_i, g_i)
+    reproduces the reference's next iterate, so the last one equals its x_adv bit for bit."""
+    import torch
+    torch.set_num_threads(1)
+    z = np.load(os.path.join(GOLD, "pgd10_traced_%s.npz" % variant))
+    x0, y, gs = z["x"], z["y"], z["gs"]
+    B, C, H, W = x0.shape
+    steps = gs.shape[0]
+    edges = np.unpackbits(z["edges"])[:steps * B * H * W].reshape(steps, B, 1, H, W).astype(np.float32)
+    weight = (np.random.default_rng(int(z["head_seed"])).standard_normal((int(z["n_class"]), C * H * W)).astype(np.float32) * 0.05)
+    p = O.make_params(variant, low=38 / 255, high=76 / 255, hysteresis=True)
+    x = x0.copy()
+    for i in range(steps):
+        out, edge = O.edge_blend_fwd(x, x, p, 1.0, want_edge=True)
+        assert np.array_equal(edge, edges[i]), "iteration %d: %d mask pixels differ" % (i, (edge != edges[i]).sum())
+        g_z = head_gradient(out, y, weight)
+        g_x, g_base = O.edge_blend_bwd(g_z, x, x, p, 1.0)
+        g = g_x + g_base
+        assert np.abs(g - gs[i]).max() <= 1e-5 * np.abs(gs[i]).max(), (i, np.abs(g - gs[i]).max(), np.abs(gs[i]).max())
+        x = O.pgd_linf_step(x, gs[i], x0, 2 / 255, 16 / 255)              # teacher-forced: the reference's gradient
+    assert np.array_equal(x, z["x_adv"])
