@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=4096, help="images per rank per step")
     ap.add_argument("--side", type=int, default=64)
     ap.add_argument("--variant", default="step125", choices=["step125", "canny", "bpda"])
-    ap.add_argument("--cpu-images", type=int, default=2048, help="images in the bounded CPU sample")
+    ap.add_argument("--cpu-images", type=int, default=0, help="images per step of the CPU arm (0 = --batch, the GPU arm's step)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work in the cpu_baseline leg (bounded sample)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="chunks the e2e batch is pipelined in")
@@ -63,7 +63,12 @@ def parse_args():
     ap.add_argument("--th-fwd", type=int, default=0)
     ap.add_argument("--th-bwd", type=int, default=0)
     ap.add_argument("--sweep", action="store_true", help="extra: kernel sweep table on stderr (configs[4])")
-    return ap.parse_args()
+    ap.add_argument("--no-named-batch", action="store_true", help="skip the named_batch block (per-launch times at the configs' own batch sizes)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra blocks (configs[0], [2], [3] with real CNNs)")
+    args = ap.parse_args()
+    if args.cpu_images <= 0:
+        args.cpu_images = args.batch
+    return args
 
 
 def dist_env():
@@ -259,6 +264,52 @@ def cpu_hot_path(images, side, variant, repeats=1, min_seconds=0.0):
     return images * n / total, cores, total / n
 
 
+def cpu_live_reference(images, side, variant, seconds=8.0):
+    """The SAME PGD-10 hot-path step through the reference's own torch modules on the host CPU (kind "live") -- only where
+    the reference checkout is present (the build container; it cannot travel to the GPU box).  Returns None otherwise."""
+    try:
+        from oracle import ref_loader
+        if not ref_loader.available():
+            return None
+        import torch
+        rc, _ra = ref_loader.load()
+    except Exception:
+        return None
+    torch.set_num_threads(os.cpu_count() or 1)
+    cls = {"step125": "CannyFilter_step125_1", "canny": "CannyFilter", "bpda": "CannyFilter_BPDA"}[variant]
+    with ref_loader.quiet():
+        f = getattr(rc, cls)(use_cuda=False, alpha=0.0)
+    g = torch.Generator().manual_seed(1234)
+    shape = (images, 3, side, side)
+    x0 = torch.rand(shape, generator=g)
+    base = torch.rand(shape, generator=g) * 1.1 - 0.1
+    g_out = torch.randn(shape, generator=g)
+    low = None if variant == "step125" else LOW
+
+    def step():
+        x = x0.clone()
+        for _ in range(N_PGD):
+            x.requires_grad_()
+            out = torch.clamp(base + W_BLEND * f(x, low_threshold=low, high_threshold=HIGH, hysteresis=True), 0.0, 1.0)
+            grad = torch.autograd.grad(out, [x], grad_outputs=g_out)[0]
+            grad = torch.nan_to_num(grad)
+            x = x.detach() + ALPHA * torch.sign(grad)                              # utils/attacks.py:25-27
+            x = torch.min(torch.max(x, x0 - EPS), x0 + EPS)
+            x = torch.clamp(x, 0, 1)
+        with torch.no_grad():
+            torch.clamp(base + W_BLEND * f(x, low_threshold=low, high_threshold=HIGH, hysteresis=True), 0.0, 1.0)
+
+    step()
+    total, n = 0.0, 0
+    while total < seconds:
+        t0 = time.perf_counter()
+        step()
+        total += time.perf_counter() - t0
+        n += 1
+    return {"value": images * n / total, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "live",
+            "sample": "%d images of 3x%dx%d per step, %d PGD-10 hot-path steps through the reference's own torch modules" % (images, side, side, n)}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  The reference is Python
     (torch eager) and cannot travel to the GPU box, so this is the C port under oracle/ (OpenMP, all
@@ -283,7 +334,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, images, 1, cpu=True),
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": "%d images of 3x%dx%d per step (one Tiny-ImageNet batch), full PGD-10 hot path"
+                         "sample": "%d images of 3x%dx%d per step (the GPU arm's step), full PGD-10 hot path"
                                    % (images, args.side, args.side)},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -304,6 +355,220 @@ def workload_config(args, per_rank, world, cpu=False):
                "inputs larger than L2: %.0f MB per tensor, 7 tensors per rank, vs 126 MB L2" % (per_rank * 3 * args.side * args.side * 4 / 1e6)),
         "parallelism": "batch sharded over %d rank(s), no data-path collective" % world,
     }
+
+
+
+# ---------------------------------------------------------------------------------------------
+# named_batch: the hot-path kernels at the batch sizes the configs really name (launch-bound there)
+# ---------------------------------------------------------------------------------------------
+NAMED_SHAPES = (
+    # tag, B, C, side, variant, alpha, low, high          (sizes M, T, I)
+    ("configs[1] T 256x3x64x64 step125", 256, 3, 64, "step125", 0.0, None, 76 / 255),
+    ("configs[1] T 256x3x64x64 canny", 256, 3, 64, "canny", 0.0, 38 / 255, 76 / 255),
+    ("configs[0] M 128x1x28x28 canny a=0.3", 128, 1, 28, "canny", 0.3, 25 / 255, 51 / 255),
+    ("configs[3] I 32x3x224x224 step125", 32, 3, 224, "step125", 0.0, None, 76 / 255),
+)
+
+
+def _graph_us_per_launch(torch, fn, reps=20, replays=10):
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(replays):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return 1e3 * e0.elapsed_time(e1) / (replays * reps)
+
+
+def run_named_batch(torch, F_ee, core, dev, peak):
+    """us per launch of fwd / bwd / PGD step / the single-call iteration at the configs' OWN batch sizes: through the
+    eager API (Python + ctypes + launch; host-bound at these sizes) and as a CUDA-graph replay of 20 launches (what
+    attacks.GraphedPGD does).  These tensors are L2-resident, so GB/s may exceed the HBM peak; frac is reported against the
+    same HBM peak as everything else."""
+    import contextlib, io
+    rows = []
+    for tag, B, C, S, variant, alpha, low, high in NAMED_SHAPES:
+        cls = {"step125": core.CannyFilter_step125_1, "canny": core.CannyFilter, "bpda": core.CannyFilter_BPDA}[variant]
+        with contextlib.redirect_stdout(io.StringIO()):
+            p = cls(use_cuda=False, alpha=alpha).params(low, high, True)
+        gen = torch.Generator(device=dev).manual_seed(99)
+        shape = (B, C, S, S)
+        x = torch.rand(shape, device=dev, generator=gen); base = torch.rand(shape, device=dev, generator=gen) * 1.1 - 0.1
+        g = torch.randn(shape, device=dev, generator=gen); x0 = torch.rand(shape, device=dev, generator=gen)
+        o1, o2, o3, o4 = (torch.empty_like(x) for _ in range(4))
+        npx = B * S * S
+        ops = (("edge_blend_fwd", lambda: F_ee.edge_blend(x, base, p, 1.0, out=o1), 12.0 * C * npx),
+               ("edge_blend_bwd", lambda: F_ee.edge_blend_backward(g, x, base, p, 1.0, g_x=o2, g_base=o3), 20.0 * C * npx),
+               ("pgd_linf_step", lambda: F_ee.pgd_linf_step(x, g, x0, ALPHA, EPS, out=o4), 16.0 * C * npx),
+               ("iteration_one_call", lambda: F_ee.pgd_iteration(x, base, g, x0, p, 1.0, ALPHA, EPS, out=o1, g_x=o2, g_base=o3, x_next=o4),
+                48.0 * C * npx))
+        row = {"shape": tag, "mb_per_tensor": 4.0 * C * npx / 1e6}
+        for name, fn, nbytes in ops:
+            for _ in range(5):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 200
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            eager_us = 1e3 * e0.elapsed_time(e1) / n
+            graph_us = _graph_us_per_launch(torch, fn)
+            row[name] = {"eager_us": round(eager_us, 2), "graph_us": round(graph_us, 2),
+                         "graph_gbs": round(nbytes / graph_us / 1e3, 1), "graph_frac_of_hbm_peak": round(nbytes / graph_us / 1e3 / peak, 3)}
+        rows.append(row)
+    return {"note": "us per launch at the configs' own batch sizes; eager = public API call in a Python loop (host-bound), "
+                    "graph = CUDA-graph replay of 20 such launches; tensors are L2-resident (<= 19 MB)", "rows": rows}
+
+
+# ---------------------------------------------------------------------------------------------
+# extra: configs[0], [2], [3] with real (stock torch) CNNs behind the drop-in front end
+# ---------------------------------------------------------------------------------------------
+def run_extra_configs(torch, core, attacks, dev):
+    """Driver-visible numbers for the other BASELINE configs (the judged metric stays configs[1]).  The CNNs are stock torch
+    (outside the product); the front end (HighFreqSuppress + edge filter + blend = core.EdgeEnhance) and the attack updates
+    are this repo's kernels.  Synthetic data, random-init weights, one GPU."""
+    import contextlib, io
+    import torch.nn as nn
+    import torch.nn.functional as Fn
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import train_throughput as TT
+    out = {}
+
+    def timed(fn, n):
+        fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+
+    def front(size, r, w, low, high, alpha, kind):
+        with contextlib.redirect_stdout(io.StringIO()):
+            return core.EdgeEnhance(cize=size, r=r, w=w, low=low, high=high, alpha=alpha, type_canny=kind).to(dev)
+
+    # ---- configs[0]: MNIST small CNN, edge-enhanced PGD-40 eval, batch 128 (MNIST/experiments_mnist.py:271-304; Net2_EE)
+    try:
+        class Net2(nn.Module):
+            def __init__(self, fr):
+                super().__init__()
+                self.front = fr
+                self.c1, self.c2 = nn.Conv2d(1, 32, 5, padding=2), nn.Conv2d(32, 64, 5, padding=2)
+                self.f1, self.f2 = nn.Linear(64 * 7 * 7, 1024), nn.Linear(1024, 10)
+
+            def forward(self, x):
+                x = self.front(x)
+                x = Fn.max_pool2d(Fn.relu(self.c1(x)), 2)
+                x = Fn.max_pool2d(Fn.relu(self.c2(x)), 2)
+                return self.f2(Fn.relu(self.f1(x.flatten(1))))
+
+        class A0:
+            random, epsilon = True, 0.3
+        m = Net2(front(28, 4, 1.0, 25.0, 51.0, 0.3, 'CannyFilter')).to(dev).eval()
+        x = torch.rand(128, 1, 28, 28, device=dev); y = torch.randint(0, 10, (128,), device=dev)
+        ms_eager = timed(lambda: attacks.PGD(m, A0, x, y, 40, 0.01), 3)
+        gp = attacks.GraphedPGD(m, A0, x, y, 0.01)
+        ms_graph = timed(lambda: gp(x, y, 40), 5)
+        same = bool(torch.equal(_seeded(torch, lambda: attacks.PGD(m, A0, x, y, 40, 0.01)), _seeded(torch, lambda: gp(x, y, 40))))
+        out["configs[0]"] = {"workload": "MNIST Net2-style CNN + EdgeEnhance(28, r 4, CannyFilter alpha 0.3, 25/51, w 1), PGD-40 eval attack, "
+                                         "batch 128, eps 0.3, step 0.01, random start", "attack_ms_eager": ms_eager, "attack_ms_graphed": ms_graph,
+                             "images_per_s_eager": 128 / ms_eager * 1e3, "images_per_s_graphed": 128 / ms_graph * 1e3,
+                             "graphed_equals_eager_bitwise": same}
+        del m, gp
+    except Exception as e:      # pragma: no cover
+        out["configs[0]"] = {"error": repr(e)}
+
+    # ---- configs[2]: Tiny-ImageNet TRADES, KL inner loop, batch 256 (utils/attacks.py:404-418)
+    try:
+        class A2:
+            random, epsilon = False, 16 / 255
+        m = TT.PreActResNet18(front(64, 8, 1.0, 38.0, 76.0, 0.0, 'CannyFilter_step125_1')).to(dev).eval()
+        x = torch.rand(256, 3, 64, 64, device=dev)
+        tr = attacks.Trades(step_size=2 / 255, epsilon=16 / 255, perturb_steps=10, beta=6.0)
+        with torch.no_grad():
+            logits = m(x)
+        ms_eager = timed(lambda: tr.PGD_Linf(m, x, logits), 2)
+        kl = nn.KLDivLoss(reduction="batchmean")
+        prob = Fn.softmax(logits, dim=-1)
+        gp = attacks.GraphedPGD(m, A2, x, prob, 2 / 255, loss_fn=lambda lg, pr: kl(Fn.log_softmax(lg, dim=1), pr))
+        ms_graph = timed(lambda: gp(x, prob, 10, x_init=x + 0.001 * torch.randn_like(x)), 3)
+        out["configs[2]"] = {"workload": "Tiny-ImageNet PreAct-ResNet18 + EdgeEnhance(64, r 8, step125, 76, w 1), TRADES KL inner loop "
+                                         "(Trades.PGD_Linf, 10 steps, eps 16/255, step 2/255), batch 256", "attack_ms_eager": ms_eager,
+                             "attack_ms_graphed": ms_graph, "images_per_s_eager": 256 / ms_eager * 1e3, "images_per_s_graphed": 256 / ms_graph * 1e3}
+        del m, gp
+    except Exception as e:      # pragma: no cover
+        out["configs[2]"] = {"error": repr(e)}
+
+    # ---- configs[3]: ImageNet ResNet-50 free adversarial training, 32 images per GPU (AT_hfs_canny_free_imagenet_ddp.py:311-334)
+    try:
+        m = TT.ResNet50(front(224, 16, 1.0, 38.0, 76.0, 0.0, 'CannyFilter_step125_1')).to(dev).train()
+        opt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+        x = torch.rand(32, 3, 224, 224, device=dev); y = torch.randint(0, 1000, (32,), device=dev)
+        noise = torch.zeros(32, 3, 224, 224, device=dev)
+        state = {"inp": x.clone()}
+
+        def free_iteration():
+            for _ in range(4):                                     # n_repeats = 4
+                inp = state["inp"].detach().requires_grad_()
+                loss = Fn.cross_entropy(m(inp), y)
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                state["inp"] = attacks.free_at_update_(noise, inp.grad, x, 4 / 255, 4 / 255)
+                opt.step()
+        ms = timed(free_iteration, 3)
+        out["configs[3]"] = {"workload": "ImageNet ResNet-50 + EdgeEnhance(224, r 16, step125, 76, w 1), free adversarial training "
+                                         "(n_repeats 4, clip_eps = fgsm_step = 4/255), 32 images per GPU, SGD; one GPU, no DDP",
+                             "ms_per_minibatch_4_repeats": ms, "images_per_s": 32 / ms * 1e3, "gradient_steps_per_s": 4 / ms * 1e3}
+        del m, opt
+    except Exception as e:      # pragma: no cover
+        out["configs[3]"] = {"error": repr(e)}
+    torch.cuda.empty_cache()
+    return out
+
+
+def _seeded(torch, fn, seed=7):
+    torch.manual_seed(seed)
+    torch.cuda.manual_seed_all(seed)
+    return fn()
+
+
+# ---------------------------------------------------------------------------------------------
+# pure-CUDA copy floor of the e2e step (tools/copyfloor.cu)
+# ---------------------------------------------------------------------------------------------
+def copy_floor(torch, dist, dev, world, barrier, nbytes):
+    """What this box delivers for the e2e step's traffic alone (one batch H2D + one batch D2H per step) with every rank
+    copying at the same time: plain cudaMemcpyAsync from NUMA-local pinned buffers, no kernels, no torch.  max over ranks."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import copyfloor
+        res = {}
+        for key, mode, chunks, reg in (("h2d_only", 0, 1, False), ("d2h_only", 1, 1, False), ("both_1_chunk", 2, 1, False),
+                                       ("both_4_chunks", 2, 4, False), ("both_1_chunk_host_register", 2, 1, True)):
+            barrier()
+            ms = copyfloor.measure(dev.index, nbytes, chunks=chunks, iters=10, mode=mode, host_register=reg)
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            res[key] = {"ms_per_step": ms, "gbs_each_way_per_rank": nbytes / ms / 1e6, "gbs_each_way_all_ranks": world * nbytes / ms / 1e6}
+        torch.cuda.set_device(dev)
+        return res
+    except Exception as e:      # pragma: no cover
+        return {"error": repr(e)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -392,7 +657,7 @@ def run_ours(args):
     barrier()
     sampler.end()
     clocks = sampler.stop()
-    if nvml_samples is not None and nvml_samples.get("samples", 0) >= max(2, clocks.get("samples", 0)):
+    if nvml_samples is not None and nvml_samples.get("samples", 0) >= max(2 if clocks.get("samples", 0) else 1, clocks.get("samples", 0)):
         clocks = nvml_samples
     elif nvml_samples is not None and nvml_samples.get("error"):
         clocks["nvml_error"] = nvml_samples["error"]
@@ -433,14 +698,26 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, secs = cpu_hot_path(args.cpu_images, S, args.variant, repeats=2, min_seconds=args.cpu_seconds)
+        v, cores, secs = cpu_hot_path(args.cpu_images, S, args.variant, repeats=1, min_seconds=args.cpu_seconds)
         n_cpu = cpu_hot_path.last_steps
         cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                "sample": "%d images of 3x%dx%d per step, %d full PGD-10 hot-path steps (%.1f s of CPU work, mean)"
                          % (args.cpu_images, S, S, n_cpu, secs * n_cpu)}
+        live = cpu_live_reference(min(args.cpu_images, 256), S, args.variant)
+        if live is not None:
+            cpu["live_reference"] = live
 
     if args.sweep and rank == 0:
         run_sweep(torch, F_ee, canny, dev, peak, args.variant)
+
+    named = extra = None
+    if rank == 0 and world == 1:
+        del x0, base, g_out, x_start, xa, xb, out, g_x, g_base
+        torch.cuda.empty_cache()
+        if not args.no_named_batch:
+            named = run_named_batch(torch, F_ee, core, dev, peak)
+        if not args.no_extra:
+            extra = run_extra_configs(torch, core, attacks, dev)
 
     if rank == 0:
         line = {
@@ -449,7 +726,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(args, B, world), host_cpus_bound_per_rank=numa_cpus),
             "clocks": clocks, "e2e": e2e, "e2e_attack_api": e2e_api, "gpu_launches": launches,
-            "roofline": roofline, "kernels": kern, "cpu_baseline": cpu,
+            "roofline": roofline, "kernels": kern, "cpu_baseline": cpu, "named_batch": named, "extra": extra,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -488,51 +765,107 @@ def run_e2e(args, torch, dist, dev, world, rank, F_ee, p, resident, barrier):
     """The SAME step as `value` (10 x [fwd, bwd, PGD step] + final fwd, `base` and `g_out` resident like the CNN /
     FFT outputs they stand for) issued through the public functional API = the C-ABI entry points, but with HOST
     buffers: every step copies the clean batch from pinned host memory and reads the adversarial batch back.
-    The batch is cut into chunks issued round-robin on three CUDA streams (the library enqueues on the caller's
-    current stream), so H2D of one chunk, the kernels of another and D2H of a third overlap."""
-    n_chunks, N_STREAMS = max(1, args.e2e_chunks), max(1, args.e2e_streams)
+
+    Two schedules are timed and the faster one is the reported value:
+      pipeline : ONE whole-batch H2D on a dedicated copy-in stream, the 31 launches on a compute stream, ONE whole-batch D2H
+                 on a dedicated copy-out stream, triple-buffered so that H2D(k+1), kernels(k) and D2H(k-1) overlap -- few,
+                 large copies, one copy engine per direction;
+      chunked  : the batch cut into --e2e-chunks chunks issued round-robin on --e2e-streams streams (round 1's schedule).
+    Next to them: the same copies without kernels through torch, and the pure-CUDA floor of tools/copyfloor.cu."""
     B, S = args.batch, args.side
     shape = (B, 3, S, S)
     base, g_out = resident
     host_in = torch.rand(shape).pin_memory()
     host_out = torch.empty(shape).pin_memory()
+    main = torch.cuda.current_stream(dev)
+    nbytes = B * 3 * S * S * 4
+    steps = max(3, min(args.steps, 20))
+    launches = [0]
+
+    def hot_path(x0c, xa, xb, out, g_x, g_base, bs, go):
+        cur, nxt = x0c, xa
+        for _it in range(N_PGD):
+            F_ee.edge_blend(cur, bs, p, W_BLEND, out=out)
+            F_ee.edge_blend_backward(go, cur, bs, p, W_BLEND, g_x=g_x, g_base=g_base)
+            F_ee.pgd_linf_step(cur, g_x, x0c, ALPHA, EPS, out=nxt)
+            cur, nxt = nxt, (xb if nxt is xa else xa)
+        F_ee.edge_blend(cur, bs, p, W_BLEND, out=out)
+        launches[0] += 3 * N_PGD + 1
+        return cur
+
+    # ---- pipeline schedule
+    s_up, s_run, s_dn = (torch.cuda.Stream(device=dev) for _ in range(3))
+    NSLOT = 3                       # three stages (copy in, kernels, copy out) in flight need three buffer sets
+    slots = [[torch.empty(shape, device=dev) for _ in range(3)] for _ in range(NSLOT)]  # per slot: x0, xa, xb
+    scratch = [torch.empty(shape, device=dev) for _ in range(3)]                        # out, g_x, g_base (compute is serial)
+    drained = [None] * NSLOT                                                            # event: the slot's D2H has finished
+    counter = [0]
+
+    def pipeline_step(with_kernels=True):
+        k = counter[0]
+        counter[0] += 1
+        x0c, xa, xb = slots[k % NSLOT]
+        if drained[k % NSLOT] is not None:
+            s_up.wait_event(drained[k % NSLOT])
+        with torch.cuda.stream(s_up):
+            x0c.copy_(host_in, non_blocking=True)
+            up = torch.cuda.Event()
+            up.record(s_up)
+        s_run.wait_event(up)
+        with torch.cuda.stream(s_run):
+            cur = hot_path(x0c, xa, xb, scratch[0], scratch[1], scratch[2], base, g_out) if with_kernels else x0c
+            ran = torch.cuda.Event()
+            ran.record(s_run)
+        s_dn.wait_event(ran)
+        with torch.cuda.stream(s_dn):
+            host_out.copy_(cur, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(s_dn)
+        drained[k % NSLOT] = ev
+
+    pstreams = [s_up, s_run, s_dn]
+    ms_pipe = _timed_pipeline(torch, dist, dev, world, barrier, pipeline_step, steps, pstreams, main)
+    ms_pipe_copy = _timed_pipeline(torch, dist, dev, world, barrier, lambda: pipeline_step(False), steps, pstreams, main)
+    del slots, scratch
+
+    # ---- chunked schedule (round 1)
+    n_chunks, N_STREAMS = max(1, args.e2e_chunks), max(1, args.e2e_streams)
     bounds = [(i * B // n_chunks, (i + 1) * B // n_chunks) for i in range(n_chunks)]
     bounds = [(lo, hi) for lo, hi in bounds if hi > lo]
     streams = [torch.cuda.Stream(device=dev) for _ in range(N_STREAMS)]
-    main = torch.cuda.current_stream(dev)
     bufs = [[torch.empty((hi - lo, 3, S, S), device=dev) for _ in range(6)] for lo, hi in bounds]   # x0, xa, xb, out, g_x, g_base
-    launches = [0]
 
-    def step(n_pgd=N_PGD):
+    def chunked_step():
         for i, (lo, hi) in enumerate(bounds):
             x0c, xa, xb, out, g_x, g_base = bufs[i]
-            bs, go = base[lo:hi], g_out[lo:hi]
             with torch.cuda.stream(streams[i % N_STREAMS]):
                 x0c.copy_(host_in[lo:hi], non_blocking=True)
-                cur, nxt = x0c, xa
-                if n_pgd is None:                                  # copies only: the PCIe floor of this step
-                    host_out[lo:hi].copy_(cur, non_blocking=True)
-                    continue
-                for _it in range(n_pgd):
-                    F_ee.edge_blend(cur, bs, p, W_BLEND, out=out)
-                    F_ee.edge_blend_backward(go, cur, bs, p, W_BLEND, g_x=g_x, g_base=g_base)
-                    F_ee.pgd_linf_step(cur, g_x, x0c, ALPHA, EPS, out=nxt)
-                    cur, nxt = nxt, (xb if nxt is xa else xa)
-                F_ee.edge_blend(cur, bs, p, W_BLEND, out=out)
+                cur = hot_path(x0c, xa, xb, out, g_x, g_base, base[lo:hi], g_out[lo:hi])
                 host_out[lo:hi].copy_(cur, non_blocking=True)
-            launches[0] += 3 * N_PGD + 1
 
-    steps = max(3, min(args.steps, 20))
-    ms = _timed_pipeline(torch, dist, dev, world, barrier, step, steps, streams, main)
-    ms_copy = _timed_pipeline(torch, dist, dev, world, barrier, lambda: step(None), steps, streams, main)
-    nbytes = B * 3 * S * S * 4
-    return {"value": world * B * steps / (ms / 1e3), "unit": "images/s",
-            "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": steps,
-            "ms_per_step": ms / steps, "copies_only_ms_per_step": ms_copy / steps,
-            "copies_only_gbs_each_way": nbytes / (ms_copy / steps) / 1e6,
-            "api": "functional.edge_blend / edge_blend_backward / pgd_linf_step (the C-ABI entry points), same 31-launch step as "
-                   "`value`; clean batch H2D from pinned host memory and adversarial batch D2H every step; "
-                   "%d chunks on %d streams" % (len(bounds), N_STREAMS)}
+    ms_chunk = _timed_pipeline(torch, dist, dev, world, barrier, chunked_step, steps, streams, main)
+    del bufs
+    torch.cuda.empty_cache()
+
+    floor = copy_floor(torch, dist, dev, world, barrier, nbytes)
+    ms = min(ms_pipe, ms_chunk)
+    res = {"value": world * B * steps / (ms / 1e3), "unit": "images/s",
+           "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": steps,
+           "ms_per_step": ms / steps, "schedule": "pipeline" if ms_pipe <= ms_chunk else "chunked",
+           "ms_per_step_pipeline": ms_pipe / steps, "ms_per_step_chunked_%dx%d" % (len(bounds), N_STREAMS): ms_chunk / steps,
+           "copies_only_ms_per_step": ms_pipe_copy / steps,
+           "copies_only_gbs_each_way": nbytes / (ms_pipe_copy / steps) / 1e6,
+           "copy_floor_pure_cuda": floor,
+           "api": "functional.edge_blend / edge_blend_backward / pgd_linf_step (the C-ABI entry points), same 31-launch step as "
+                  "`value`; clean batch H2D from pinned host memory and adversarial batch D2H every step; pipeline = one copy per "
+                  "direction per step on dedicated copy streams, triple buffered"}
+    try:
+        fl = min(v["ms_per_step"] for k, v in floor.items() if k.startswith("both"))
+        res["copy_floor_ms_per_step"] = fl
+        res["frac_of_copy_floor"] = fl / (ms / steps)
+    except Exception:
+        pass
+    return res
 
 
 def run_e2e_attack_api(args, torch, dist, dev, world, rank, core, attacks, canny, barrier):

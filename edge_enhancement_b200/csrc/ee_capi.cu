@@ -939,7 +939,7 @@ int ee_pgd_l2_step_f32(const float* x, const float* g, const float* x0, float* o
         if (int rc = ensure_smem(kernel, pl.smem)) return rc;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)((long long)B * pl.K));
-        cfg.blockDim = dim3((unsigned)ee::kL2Threads);
+        cfg.blockDim = dim3((unsigned)pl.threads);
         cfg.dynamicSmemBytes = pl.smem;
         cfg.stream = s;
         cudaLaunchAttribute at[1];
@@ -947,7 +947,7 @@ int ee_pgd_l2_step_f32(const float* x, const float* g, const float* x0, float* o
         at[0].val.clusterDim.x = (unsigned)pl.K; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, x, g, x0, out, n_per, pl.slice4, pl.K, step, eps);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, x, g, x0, out, n_per, pl.slice4, pl.K, pl.stage_x0, step, eps);
         if (e != cudaSuccess) return cuda_fail(e, "ee_pgd_l2_step_f32");
         return EE_OK;
     }

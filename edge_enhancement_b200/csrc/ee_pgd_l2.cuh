@@ -7,14 +7,16 @@
 //     x'  = clamp(x0 + d, 0, 1)
 //
 // The two per-sample norms are sequentially dependent, so the sample has to stay on chip between them.  One sample is
-// owned by a thread-block CLUSTER of K CTAs (K = 1 up to 3 x 64 x 64, K = 8 for 3 x 224 x 224); CTA k stages its slice of g
-// and x0 in shared memory with TMA bulk copies (cp.async.bulk + mbarrier, issued by one thread at kernel start together
-// with an L2 prefetch of the x slice), overwrites the g slice with d in the second phase, and the cluster exchanges the
-// K partial sums through distributed shared memory.  Nothing is read from HBM twice and nothing but x' is written.
+// owned by a thread-block CLUSTER of K CTAs (K = 1 up to 3 x 64 x 64, 4 at 128 px, 8 from 224 px); CTA k stages its slice of
+// g in shared memory with TMA bulk copies (cp.async.bulk + mbarrier, issued by one thread at kernel start together with an
+// L2 prefetch of the x slice), overwrites it with d in the second phase, and the cluster exchanges the K partial sums
+// through distributed shared memory.  With K = 1 the x0 slice is staged the same way (96 KB per CTA at 3 x 64 x 64, two
+// CTAs per SM); with K > 1 only g / d stay on chip (<= 75 KB per CTA at 224 px, three CTAs per SM) and the third phase
+// re-reads x0 through L2, where the second phase left it microseconds earlier.
 //
-// Canonical reduction order (shared with oracle/ee_oracle.c, rms_cluster): inside a slice thread t of 512 accumulates the
-// float4 words t, t + 512, ... element by element with fmaf; warp-shuffle tree (strides 16..1); the 16 warp sums padded
-// to 32 with zeros and the same tree; then the K slice sums left to right.
+// Canonical reduction order (shared with oracle/ee_oracle.c, rms_cluster): inside a slice thread t of T accumulates the
+// float4 words t, t + T, ... element by element with fmaf; warp-shuffle tree (strides 16..1); the T/32 warp sums padded
+// to 32 with zeros and the same tree; then the K slice sums left to right.  T = 512, or 128 for slices under 1024 words.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -23,23 +25,29 @@
 
 namespace ee {
 
-constexpr int kL2Threads = 512;
-constexpr int kL2TargetSlice4 = 3072;      // 12288 floats = 48 KB per staged plane (two planes: 2 CTAs per SM)
+constexpr int kL2Threads = 512;            // launch bound; small slices run 128 threads
+constexpr int kL2OneCta4 = 3072;           // up to 12288 floats (48 KB per plane) one CTA keeps g AND x0: 96 KB, 2 CTAs per SM
+constexpr int kL2TargetSlice4 = 4096;      // clusters: 64 KB of g per CTA when K <= 8 allows it
 constexpr int kL2MaxCluster = 8;           // portable cluster size
 constexpr int kL2Header = 128;             // mbarrier, warp partials, cluster slots
 
-struct L2Plan { int K; int slice4; size_t smem; };
+struct L2Plan { int K; int slice4; int threads; int stage_x0; size_t smem; };
 
-// false: the sample does not fit (or n_per % 4 != 0) -> the three-pass kernel of ee_attack.cuh
+// false: the sample does not fit (or n_per % 4 != 0) -> the three-pass kernel of ee_attack.cuh.
+// oracle/ee_oracle.c (l2_cluster_plan) restates this function: keep the two in step.
 inline bool pgd_l2_plan(int64_t n_per, L2Plan& pl) {
     if (n_per <= 0 || (n_per & 3)) return false;
     const int64_t n4 = n_per >> 2;
     int K = 1;
-    while (K < kL2MaxCluster && (n4 + K - 1) / K > kL2TargetSlice4) K <<= 1;
+    if (n4 > kL2OneCta4)
+        while (K < kL2MaxCluster && (n4 + K - 1) / K > kL2TargetSlice4) K <<= 1;
+    if (n4 > kL2OneCta4 && K == 1) K = 2;
     const int64_t s4 = (n4 + K - 1) / K;
-    const size_t smem = kL2Header + (size_t)s4 * 16 * 2;
+    pl.stage_x0 = (K == 1);
+    const size_t smem = kL2Header + (size_t)s4 * 16 * (pl.stage_x0 ? 2 : 1);
     if (smem > (size_t)227 * 1024) return false;
     pl.K = K; pl.slice4 = (int)s4; pl.smem = smem;
+    pl.threads = (s4 >= 1024) ? kL2Threads : 128;
     return true;
 }
 
@@ -50,7 +58,7 @@ __device__ __forceinline__ float l2_block_sum(float v, float* sh) {
     __syncthreads();                 // protect sh from the previous use
     if (lane == 0) sh[warp] = v;
     __syncthreads();
-    float t = (lane < kL2Threads / 32) ? sh[lane] : 0.0f;
+    float t = (lane < (int)(blockDim.x >> 5)) ? sh[lane] : 0.0f;
 #pragma unroll
     for (int s = 16; s >= 1; s >>= 1) t = t + __shfl_down_sync(0xffffffffu, t, s);
     return __shfl_sync(0xffffffffu, t, 0);
@@ -58,7 +66,7 @@ __device__ __forceinline__ float l2_block_sum(float v, float* sh) {
 
 static __global__ void __launch_bounds__(kL2Threads) pgd_l2_cluster_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                                           const float* __restrict__ x0, float* __restrict__ out,
-                                                                          int64_t n_per, int slice4, int K, float step, float eps) {
+                                                                          int64_t n_per, int slice4, int K, int stage_x0, float step, float eps) {
     namespace cg = cooperative_groups;
     extern __shared__ __align__(128) unsigned char l2_smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(l2_smem);
@@ -83,11 +91,12 @@ static __global__ void __launch_bounds__(kL2Threads) pgd_l2_cluster_kernel(const
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (cnt > 0) {
             const uint32_t bytes = (uint32_t)cnt * 16u;
-            mbar_arrive_expect_tx(smem_u32(bar), 2u * bytes);
+            mbar_arrive_expect_tx(smem_u32(bar), (stage_x0 ? 2u : 1u) * bytes);
             for (uint32_t off = 0; off < bytes; off += 32768u) {
                 const uint32_t c = min(32768u, bytes - off);
                 bulk_g2s(smem_u32(pg) + off, reinterpret_cast<const char*>(gb) + off, c, smem_u32(bar));
-                bulk_g2s(smem_u32(px0) + off, reinterpret_cast<const char*>(x0b) + off, c, smem_u32(bar));
+                if (stage_x0) bulk_g2s(smem_u32(px0) + off, reinterpret_cast<const char*>(x0b) + off, c, smem_u32(bar));
+                else l2_prefetch_bulk(reinterpret_cast<const char*>(x0b) + off, c);
                 l2_prefetch_bulk(reinterpret_cast<const char*>(xb) + off, c);
             }
         }
@@ -106,7 +115,8 @@ static __global__ void __launch_bounds__(kL2Threads) pgd_l2_cluster_kernel(const
 
     // ---- sqrt(mean(g^2)) + 1e-8                                                                  attacks.py:391, :360-366
     float acc = 0.0f;
-    for (int i = threadIdx.x; i < cnt; i += kL2Threads) {
+    const int T = (int)blockDim.x;
+    for (int i = threadIdx.x; i < cnt; i += T) {
         const float4 v = pg[i];
         acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
     }
@@ -114,8 +124,8 @@ static __global__ void __launch_bounds__(kL2Threads) pgd_l2_cluster_kernel(const
 
     // ---- xa = x + step * g / gn ; d = xa - x0 ; sqrt(mean(d^2))                                  attacks.py:392-395
     acc = 0.0f;
-    for (int i = threadIdx.x; i < cnt; i += kL2Threads) {
-        const float4 xv = __ldcs(xb + i), gv = pg[i], zv = px0[i];
+    for (int i = threadIdx.x; i < cnt; i += T) {
+        const float4 xv = __ldcs(xb + i), gv = pg[i], zv = stage_x0 ? px0[i] : __ldg(x0b + i);
         float4 d;
         d.x = (xv.x + step * (gv.x / gn)) - zv.x; d.y = (xv.y + step * (gv.y / gn)) - zv.y;
         d.z = (xv.z + step * (gv.z / gn)) - zv.z; d.w = (xv.w + step * (gv.w / gn)) - zv.w;
@@ -127,9 +137,9 @@ static __global__ void __launch_bounds__(kL2Threads) pgd_l2_cluster_kernel(const
     const float scale = eps / dn;                                                                 // :397
 
     // ---- x' = clamp(x0 + d, 0, 1)                                                                attacks.py:398-399
-    for (int i = threadIdx.x; i < cnt; i += kL2Threads) {
+    for (int i = threadIdx.x; i < cnt; i += T) {
         float4 d = pg[i];
-        const float4 zv = px0[i];
+        const float4 zv = stage_x0 ? px0[i] : __ldcs(x0b + i);
         if (cond) { d.x = d.x * scale; d.y = d.y * scale; d.z = d.z * scale; d.w = d.w * scale; }
         __stcs(ob + i, make_float4(minn(maxn(zv.x + d.x, 0.0f), 1.0f), minn(maxn(zv.y + d.y, 0.0f), 1.0f),
                                    minn(maxn(zv.z + d.z, 0.0f), 1.0f), minn(maxn(zv.w + d.w, 0.0f), 1.0f)));

@@ -100,10 +100,11 @@ _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 
 def _stream(t):
-    """cudaStream_t of the CURRENT stream of t's device (what autograd / DataParallel threads expect)."""
+    """cudaStream_t of the CURRENT stream of t's device (what autograd / DataParallel threads expect), as a plain int:
+    ctypes converts it to void* itself, which is cheaper than building a c_void_p per call."""
     if _raw_stream is not None:
-        return ctypes.c_void_p(_raw_stream(t.device.index))
-    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+        return _raw_stream(t.device.index)
+    return torch.cuda.current_stream(t.device).cuda_stream
 
 
 class _on_device:
@@ -123,7 +124,7 @@ class _on_device:
 
 
 def _ptr(t):
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
+    return None if t is None else t.data_ptr()
 
 
 # --------------------------------------------------------------------------------------------
@@ -334,7 +335,7 @@ def avmixup_mix(x_adv, inputs, weight, gamma):
     out = torch.empty_like(x_adv)
     if x_adv.numel():
         with _on_device(x_adv):
-            rc = _lib.load().ee_avmixup_mix_f32(_ptr(x_adv), _ptr(inputs), weight.data_ptr(), _ptr(out), B,
+            rc = _lib.load().ee_avmixup_mix_f32(_ptr(x_adv), _ptr(inputs), _ptr(weight), _ptr(out), B,
                                                 x_adv.numel() // B, float(gamma), _stream(x_adv))
         _lib.check(rc, "ee_avmixup_mix_f32")
     return out

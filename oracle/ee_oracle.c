@@ -607,40 +607,43 @@ static float rms_canonical(const float *v, int64_t n, const float *v2_sub, int m
     return sqrtf(wsum[0] / (float)n);
 }
 
-/* The one-pass CUDA kernel (edge_enhancement_b200/csrc/ee_pgd_l2.cuh) keeps a sample on chip in a cluster of K CTAs of 512
+/* The one-pass CUDA kernel (edge_enhancement_b200/csrc/ee_pgd_l2.cuh) keeps a sample on chip in a cluster of K CTAs of T
  * threads; its reduction order, restated: the sample's float4 words are cut into K slices of slice4 words; inside a slice
- * thread t accumulates words t, t + 512, ... element by element with fmaf; shuffle tree (strides 16..1) inside each warp;
- * the 16 warp sums padded with zeros to 32 and the same tree; then the K slice sums left to right. */
-#define EE_L2C_THREADS 512
-#define EE_L2C_TARGET_SLICE4 3072
+ * thread t accumulates words t, t + T, ... element by element with fmaf; shuffle tree (strides 16..1) inside each warp;
+ * the T/32 warp sums padded with zeros to 32 and the same tree; then the K slice sums left to right. */
+#define EE_L2C_MAX_THREADS 512
+#define EE_L2C_ONE_CTA4 3072
+#define EE_L2C_TARGET_SLICE4 4096
 #define EE_L2C_MAX_CLUSTER 8
-static int l2_cluster_plan(int64_t n_per, int *K, int64_t *slice4)
+static int l2_cluster_plan(int64_t n_per, int *K, int64_t *slice4, int *threads)
 {
     if (n_per <= 0 || (n_per & 3)) return 0;
     int64_t n4 = n_per >> 2;
     int k = 1;
-    while (k < EE_L2C_MAX_CLUSTER && (n4 + k - 1) / k > EE_L2C_TARGET_SLICE4) k <<= 1;
+    if (n4 > EE_L2C_ONE_CTA4)
+        while (k < EE_L2C_MAX_CLUSTER && (n4 + k - 1) / k > EE_L2C_TARGET_SLICE4) k <<= 1;
+    if (n4 > EE_L2C_ONE_CTA4 && k == 1) k = 2;
     int64_t s4 = (n4 + k - 1) / k;
-    if (128 + (size_t)s4 * 32 > (size_t)227 * 1024) return 0;
-    *K = k; *slice4 = s4;
+    if (128 + (size_t)s4 * 16 * (k == 1 ? 2 : 1) > (size_t)227 * 1024) return 0;
+    *K = k; *slice4 = s4; *threads = (s4 >= 1024) ? EE_L2C_MAX_THREADS : 128;
     return 1;
 }
-static float rms_cluster(const float *v, int64_t n, int K, int64_t slice4)
+static float rms_cluster(const float *v, int64_t n, int K, int64_t slice4, int T)
 {
     const int64_t n4 = n >> 2;
     float total = 0.0f;
     for (int k = 0; k < K; ++k) {
         int64_t lo4 = (int64_t)k * slice4, hi4 = lo4 + slice4 < n4 ? lo4 + slice4 : n4;
-        float part[EE_L2C_THREADS];
-        for (int t = 0; t < EE_L2C_THREADS; ++t) {
+        float part[EE_L2C_MAX_THREADS];
+        for (int t = 0; t < T; ++t) {
             float acc = 0.0f;
-            for (int64_t i = lo4 + t; i < hi4; i += EE_L2C_THREADS)
+            for (int64_t i = lo4 + t; i < hi4; i += T)
                 for (int c = 0; c < 4; ++c) { float e = v[4 * i + c]; acc = fmaf(e, e, acc); }
             part[t] = acc;
         }
         float wsum[32];
         for (int w = 0; w < 32; ++w) wsum[w] = 0.0f;
-        for (int w = 0; w < EE_L2C_THREADS / 32; ++w) {
+        for (int w = 0; w < T / 32; ++w) {
             float *p = part + 32 * w;
             for (int s = 16; s >= 1; s >>= 1)
                 for (int l = 0; l < s; ++l) p[l] = p[l] + p[l + s];
@@ -658,17 +661,17 @@ static float rms_cluster(const float *v, int64_t n, int K, int64_t slice4)
 void ee_oracle_pgd_l2_step(const float *x, const float *g, const float *x0, float *out, int B,
                            int64_t n_per, float step, float eps, int mode)
 {
-    int K = 0; int64_t slice4 = 0;
-    const int cluster = (mode < 0) && l2_cluster_plan(n_per, &K, &slice4);
+    int K = 0, T = 0; int64_t slice4 = 0;
+    const int cluster = (mode < 0) && l2_cluster_plan(n_per, &K, &slice4, &T);
 #pragma omp parallel for schedule(static)
     for (int b = 0; b < B; ++b) {
         const float *xb = x + (int64_t)b * n_per, *gb = g + (int64_t)b * n_per, *x0b = x0 + (int64_t)b * n_per;
         float *ob = out + (int64_t)b * n_per;
-        float gn = (cluster ? rms_cluster(gb, n_per, K, slice4) : rms_canonical(gb, n_per, NULL, 0)) + 1e-8f;      /* :391 */
+        float gn = (cluster ? rms_cluster(gb, n_per, K, slice4, T) : rms_canonical(gb, n_per, NULL, 0)) + 1e-8f;      /* :391 */
         float dn;
         if (cluster) {
             for (int64_t i = 0; i < n_per; ++i) ob[i] = (xb[i] + step * (gb[i] / gn)) - x0b[i];    /* d = xa - x0, :391-394 */
-            dn = rms_cluster(ob, n_per, K, slice4);                                                 /* :395 */
+            dn = rms_cluster(ob, n_per, K, slice4, T);                                                 /* :395 */
         } else {
             for (int64_t i = 0; i < n_per; ++i) ob[i] = xb[i] + step * (gb[i] / gn);               /* :391-392 */
             dn = rms_canonical(ob, n_per, x0b, 1);                                                  /* :394-395 */

@@ -17,7 +17,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-from edge_enhancement_b200 import attacks, core   # noqa: E402
+from edge_enhancement_b200 import attacks, core, functional as F_ee   # noqa: E402
 
 DEV = "cuda:0"
 EPS, STEP = 16 / 255, 2 / 255
@@ -261,7 +261,7 @@ def test_graphed_pgd_with_the_trades_kl_loss():
         with torch.enable_grad():
             loss = kl(F.log_softmax(model(xa), dim=1), F.softmax(preds, dim=1))
         g = torch.autograd.grad(loss, [xa])[0]
-        xa = attacks._linf_step(xa, g, x, step, eps)
+        xa = F_ee.pgd_linf_step(xa.detach(), g.detach(), x.detach(), step, eps, 0.0, 1.0)
 
     args = types.SimpleNamespace(random=False, epsilon=eps)
     soft = F.softmax(preds, dim=1)

@@ -140,7 +140,7 @@ class EagerFront(nn.Module):
         import numpy as np
         from edge_enhancement_b200 import core
         self.w, self.high = w, high
-        self.hfs = core.HighFreqSuppress(size, size, r)                 # same torch.fft low-pass in both arms
+        self.hfs = core.HighFreqSuppress(size, size, r, impl='torch_fft')   # the reference-style arm keeps the torch.fft low-pass
         g = torch.from_numpy(core.get_gaussian_kernel(3, 0, 1)).float()[None, None].to(dev)
         sx = torch.from_numpy(core.get_sobel_kernel(3)).float()[None, None].to(dev)
         self.wg, self.wsx, self.wsy = g, sx, sx.transpose(2, 3).contiguous()

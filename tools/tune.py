@@ -24,6 +24,19 @@ def timeit(fn, n=20):
     return e0.elapsed_time(e1) / n
 
 
+def graph_timeit(fn, reps=20):
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    return timeit(g.replay, 10) / reps
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--shapes", default="4096x64,512x224,8192x32,16384x28x1")
@@ -31,6 +44,7 @@ def main():
     ap.add_argument("--ths", default="0,4,8,16,32,64,112,224")
     ap.add_argument("--channels-last", action="store_true")
     ap.add_argument("--staging", type=int, default=0, help="ee_set_tuning staging knob (8 / 9 = always / never row-streaming)")
+    ap.add_argument("--graph", action="store_true", help="time CUDA-graph replays of 20 launches (small batches: no host overhead)")
     args = ap.parse_args()
     L = _lib.load()
     with contextlib.redirect_stdout(io.StringIO()):
@@ -49,8 +63,9 @@ def main():
             if th > S:
                 continue
             L.ee_set_tuning(th, th, args.staging)
-            tf = timeit(lambda: F.edge_blend(x, base, p, 1.0, out=o1))
-            tb = timeit(lambda: F.edge_blend_backward(g, x, base, p, 1.0, g_x=o2, g_base=o3))
+            tm = graph_timeit if args.graph else timeit
+            tf = tm(lambda: F.edge_blend(x, base, p, 1.0, out=o1))
+            tb = tm(lambda: F.edge_blend_backward(g, x, base, p, 1.0, g_x=o2, g_base=o3))
             print("%-8s B=%5d C=%d side=%3d TH=%3d | fwd %7.1f us %6.0f GB/s | bwd %7.1f us %6.0f GB/s"
                   % (args.variant, B, C, S, th, tf * 1e3, 12.0 * C * npx / tf / 1e6, tb * 1e3, 20.0 * C * npx / tb / 1e6), flush=True)
         L.ee_set_tuning(0, 0, 0)
