@@ -23,8 +23,14 @@ class EEParams(ctypes.Structure):
                 ("hysteresis", ctypes.c_int32), ("flags", ctypes.c_int32)]
 
 
+class EEStrides(ctypes.Structure):
+    """Mirror of `struct EEStrides`: element strides (n, c, h, w) = torch.Tensor.stride() of a [B,C,H,W] tensor."""
+    _fields_ = [("n", ctypes.c_int64), ("c", ctypes.c_int64), ("h", ctypes.c_int64), ("w", ctypes.c_int64)]
+
+
 _vp, _i, _i64, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
 _pp = ctypes.POINTER(EEParams)
+_sp = ctypes.POINTER(EEStrides)
 
 # name -> argtypes ; every function returns int unless listed in _RESTYPE
 SIGNATURES = {
@@ -32,6 +38,10 @@ SIGNATURES = {
     "ee_edge_bwd_f32": [_vp, _vp, _vp, _i, _i, _i, _i, _pp, _vp],
     "ee_edge_blend_fwd_f32": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _pp, _f, _vp],
     "ee_edge_blend_bwd_f32": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _pp, _f, _vp],
+    "ee_edge_fwd_strided_f32": [_vp, _sp, _vp, _sp, _i, _i, _i, _i, _pp, _vp],
+    "ee_edge_bwd_strided_f32": [_vp, _sp, _vp, _sp, _vp, _sp, _i, _i, _i, _i, _pp, _vp],
+    "ee_edge_blend_fwd_strided_f32": [_vp, _sp, _vp, _sp, _vp, _sp, _vp, _sp, _i, _i, _i, _i, _pp, _f, _vp],
+    "ee_edge_blend_bwd_strided_f32": [_vp, _sp, _vp, _sp, _vp, _sp, _vp, _sp, _vp, _sp, _i, _i, _i, _i, _pp, _f, _vp],
     "ee_aux_bytes": [_i, _i, _i, _i, _i],
     "ee_pgd_linf_step_f32": [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _vp],
     "ee_fgsm_step_f32": [_vp, _vp, _vp, _i64, _f, _f, _f, _vp],

@@ -197,11 +197,14 @@ class _PlainTensorFilter(_EdgeFilterBase):
         super(_PlainTensorFilter, self).__init__()
         g, sx, sy, d, h = self._setup(k_gaussian, mu, sigma, k_sobel, use_cuda, alpha)
         self.alpha = torch.tensor(alpha)
-        self.weight_gaussian = g.to(self.device)
-        self.weight_sobel_x = sx.to(self.device)
-        self.weight_sobel_y = sy.to(self.device)
-        self.weight_directional = d.to(self.device)
-        self.weight_hysteresis = h.to(self.device)
+        # (API-compatibility attributes: the kernels read the taps from host copies.  On a box without a CUDA device the
+        # constructor still succeeds; the first forward then raises the package's "no CPU fallback" error.)
+        dev = self.device if (self.device == 'cpu' or torch.cuda.is_available()) else 'cpu'
+        self.weight_gaussian = g.to(dev)
+        self.weight_sobel_x = sx.to(dev)
+        self.weight_sobel_y = sy.to(dev)
+        self.weight_directional = d.to(dev)
+        self.weight_hysteresis = h.to(dev)
 
 
 class CannyFilter_BPDA(_PlainTensorFilter):

@@ -371,6 +371,7 @@ int launch_tiles(K kernel, const Launch& L, int B, const ee::FastArgs& a, const 
 bool fast_eligible(const ee::EdgeArgs& a, bool vec_ok) {
     if (g_staging.load() == 1 || !vec_ok || a.W < 8 || a.H < 4) return false;
     if (a.nan_compat && a.g_in != nullptr) return false;      // reference-NaN backward: shape-generic kernels only
+    if (a.strided) return false;                              // non-dense strides: shape-generic kernels only
     return std::isfinite(a.high) && std::isfinite(a.alpha) && std::isfinite(a.low) && fabsf(a.high) < 1e18f &&
            fabsf(a.alpha) < 1e18f;
 }
@@ -491,6 +492,11 @@ int fill_args(ee::EdgeArgs& a, int B, int C, int H, int W, const EEParams* p, fl
     if (p->variant == EE_VARIANT_STEP125) a.has_low = 0;
     a.hyst = (p->variant != EE_VARIANT_STEP125) && p->hysteresis != 0;
     a.nan_compat = (p->flags & EE_FLAG_NAN_COMPAT) != 0;
+    const int64_t hw = (int64_t)H * W;
+    const ee::EEStride3 dense = {(int64_t)C * hw, hw, (int64_t)W}, dense1 = {hw, hw, (int64_t)W};
+    a.sx = a.sbase = a.sg = a.sout = a.sgx = a.sgbase = dense;
+    a.sedge = dense1;
+    a.strided = 0;
     return EE_OK;
 }
 
@@ -773,8 +779,48 @@ int ee_shared::canny_stream(ee::EdgeArgs& a, const EEParams* p, int B, bool blen
 #if EE_HAS(1)
 namespace {
 
+// How a caller-described tensor can be read: dense in a layout the tuned kernels know, rows contiguous (generic kernels
+// on the strides), or not at all.
+enum StrideKind { SK_DENSE_NCHW, SK_DENSE_NHWC, SK_ROWS, SK_BAD };
+StrideKind classify(const EEStrides* s, int B, int C, int H, int W, int layout, ee::EEStride3& out) {
+    const int64_t hw = (int64_t)H * W;
+    if (!s) {
+        out = {(int64_t)C * hw, hw, (int64_t)W};
+        return (layout == EE_LAYOUT_NHWC && C > 1) ? SK_DENSE_NHWC : SK_DENSE_NCHW;
+    }
+    // strides of size-1 dimensions carry no information (torch leaves them arbitrary)
+    const int64_t sn = (B == 1) ? (int64_t)C * hw : s->n, sc = (C == 1) ? hw : s->c, sh = (H == 1) ? W : s->h, sw = (W == 1) ? 1 : s->w;
+    out = {sn, sc, sh};
+    if (sw == 1 && sh == W && sc == hw && sn == (int64_t)C * hw) return SK_DENSE_NCHW;
+    if (C > 1 && sc == 1 && sw == C && sh == (int64_t)W * C && (B == 1 || s->n == hw * C)) return SK_DENSE_NHWC;
+    if (sw == 1) return SK_ROWS;
+    return SK_BAD;
+}
+bool stride_vec_ok(const ee::EEStride3& s) { return ((s.b | s.c | s.h) & 3) == 0; }
+
+struct TensorDesc { const void* ptr; const EEStrides* s; int C; ee::EEStride3* dst; const char* name; };
+
+// Fills the strides of every described tensor; returns the common kind (dense NCHW / dense NHWC / rows), or fails.
+int resolve_strides(TensorDesc* t, int n, int B, int H, int W, int layout, StrideKind& kind, bool& vec_ok) {
+    kind = SK_DENSE_NCHW;
+    bool any_rows = false, any_nhwc = false, any_nchw = false;
+    for (int i = 0; i < n; ++i) {
+        if (!t[i].ptr) continue;
+        const StrideKind k = classify(t[i].s, B, t[i].C, H, W, layout, *t[i].dst);
+        if (k == SK_BAD) return fail(EE_ERR_UNSUPPORTED, "%s: column stride must be 1 (or the tensor dense channels_last); make a contiguous copy", t[i].name);
+        if (k == SK_ROWS) any_rows = true;
+        else if (k == SK_DENSE_NHWC) any_nhwc = true;
+        else if (t[i].C > 1) any_nchw = true;
+        vec_ok = vec_ok && stride_vec_ok(*t[i].dst);
+    }
+    if (any_nhwc && (any_rows || any_nchw)) return fail(EE_ERR_UNSUPPORTED, "mixed memory layouts: every image tensor must be channels_last, or none");
+    kind = any_rows ? SK_ROWS : (any_nhwc ? SK_DENSE_NHWC : SK_DENSE_NCHW);
+    return EE_OK;
+}
+
 int edge_forward(const float* x, const float* base, float* out, float* edge, int B, int C, int H, int W,
-                 const EEParams* p, float w, bool blend, void* stream) {
+                 const EEParams* p, float w, bool blend, void* stream, const EEStrides* xs = nullptr,
+                 const EEStrides* bs = nullptr, const EEStrides* os = nullptr, const EEStrides* es = nullptr, bool strided_api = false) {
     ee::EdgeArgs a;
     int rc = fill_args(a, B, C, H, W, p, w);
     if (rc) return rc;
@@ -782,14 +828,26 @@ int edge_forward(const float* x, const float* base, float* out, float* edge, int
     if (blend && (!base || !out)) return fail(EE_ERR_INVALID_ARG, "base/out is null");
     if (!blend && !edge) return fail(EE_ERR_INVALID_ARG, "edge is null");
     a.x = x; a.base = base; a.out = out; a.edge = edge;
-    const bool vec_ok = (W % 4 == 0) && aligned16(x) && aligned16(base) && aligned16(out) && aligned16(edge);
-    const bool nhwc = (p->layout == EE_LAYOUT_NHWC) && C > 1;       // with one channel the layouts coincide
+    bool vec_ok = (W % 4 == 0) && aligned16(x) && aligned16(base) && aligned16(out) && aligned16(edge);
+    bool nhwc = (p->layout == EE_LAYOUT_NHWC) && C > 1;       // with one channel the layouts coincide
+    if (strided_api) {
+        TensorDesc t[4] = {{x, xs, C, &a.sx, "x"}, {base, bs, C, &a.sbase, "base"}, {out, os, C, &a.sout, "out"}, {edge, es, 1, &a.sedge, "edge"}};
+        StrideKind kind;
+        rc = resolve_strides(t, 4, B, H, W, p->layout, kind, vec_ok);
+        if (rc) return rc;
+        nhwc = (kind == SK_DENSE_NHWC);
+        a.strided = (kind == SK_ROWS);
+        if (nhwc && a.edge && classify(es, B, 1, H, W, EE_LAYOUT_NCHW, a.sedge) != SK_DENSE_NCHW)
+            return fail(EE_ERR_UNSUPPORTED, "edge must be dense next to channels_last images");
+    }
     if (p->variant == EE_VARIANT_STEP125) return ee_shared::fwd_step125(a, p, B, blend, vec_ok, nhwc, (cudaStream_t)stream);
     return ee_shared::fwd_canny(a, p, B, blend, vec_ok, nhwc, (cudaStream_t)stream);
 }
 
 int edge_backward(const float* g_in, const float* x, const float* base, float* g_x, float* g_base, int B, int C,
-                  int H, int W, const EEParams* p, float w, bool blend, void* stream) {
+                  int H, int W, const EEParams* p, float w, bool blend, void* stream, const EEStrides* gs = nullptr,
+                  const EEStrides* xs = nullptr, const EEStrides* bs = nullptr, const EEStrides* gxs = nullptr,
+                  const EEStrides* gbs = nullptr, bool strided_api = false) {
     ee::EdgeArgs a;
     int rc = fill_args(a, B, C, H, W, p, w);
     if (rc) return rc;
@@ -798,8 +856,17 @@ int edge_backward(const float* g_in, const float* x, const float* base, float* g
     if (!blend && !g_x) return fail(EE_ERR_INVALID_ARG, "g_x is null");
     if (blend && !g_x && !g_base) return EE_OK;   // nothing requested
     a.x = x; a.base = base; a.g_in = g_in; a.g_x = g_x; a.g_base = g_base;
-    const bool vec_ok = (W % 4 == 0) && aligned16(x) && aligned16(base) && aligned16(g_in) && aligned16(g_x) && aligned16(g_base);
-    const bool nhwc = (p->layout == EE_LAYOUT_NHWC) && C > 1;
+    bool vec_ok = (W % 4 == 0) && aligned16(x) && aligned16(base) && aligned16(g_in) && aligned16(g_x) && aligned16(g_base);
+    bool nhwc = (p->layout == EE_LAYOUT_NHWC) && C > 1;
+    if (strided_api) {
+        TensorDesc t[5] = {{g_in, gs, blend ? C : 1, &a.sg, "grad"}, {x, xs, C, &a.sx, "x"}, {base, bs, C, &a.sbase, "base"},
+                           {g_x, gxs, C, &a.sgx, "g_x"}, {g_base, gbs, C, &a.sgbase, "g_base"}};
+        StrideKind kind;
+        rc = resolve_strides(t, 5, B, H, W, p->layout, kind, vec_ok);
+        if (rc) return rc;
+        nhwc = (kind == SK_DENSE_NHWC);
+        a.strided = (kind == SK_ROWS);
+    }
     if (p->variant == EE_VARIANT_STEP125) return ee_shared::bwd_step125(a, p, B, blend, vec_ok, nhwc, (cudaStream_t)stream);
     return ee_shared::bwd_canny(a, p, B, blend, vec_ok, nhwc, (cudaStream_t)stream);
 }
@@ -878,6 +945,24 @@ int ee_edge_bwd_f32(const float* g_edge, const float* x, float* g_x, int B, int 
 int ee_edge_blend_bwd_f32(const float* g_out, const float* x, const float* base, float* g_x_or_null,
                           float* g_base_or_null, int B, int C, int H, int W, const EEParams* p, float w, void* stream) {
     return edge_backward(g_out, x, base, g_x_or_null, g_base_or_null, B, C, H, W, p, w, true, stream);
+}
+int ee_edge_fwd_strided_f32(const float* x, const EEStrides* xs, float* edge, const EEStrides* es, int B, int C, int H, int W,
+                            const EEParams* p, void* stream) {
+    return edge_forward(x, nullptr, nullptr, edge, B, C, H, W, p, 0.0f, false, stream, xs, nullptr, nullptr, es, true);
+}
+int ee_edge_bwd_strided_f32(const float* g_edge, const EEStrides* ges, const float* x, const EEStrides* xs, float* g_x,
+                            const EEStrides* gxs, int B, int C, int H, int W, const EEParams* p, void* stream) {
+    return edge_backward(g_edge, x, nullptr, g_x, nullptr, B, C, H, W, p, 0.0f, false, stream, ges, xs, nullptr, gxs, nullptr, true);
+}
+int ee_edge_blend_fwd_strided_f32(const float* x, const EEStrides* xs, const float* base, const EEStrides* bs, float* out,
+                                  const EEStrides* os, float* edge_or_null, const EEStrides* es, int B, int C, int H, int W,
+                                  const EEParams* p, float w, void* stream) {
+    return edge_forward(x, base, out, edge_or_null, B, C, H, W, p, w, true, stream, xs, bs, os, es, true);
+}
+int ee_edge_blend_bwd_strided_f32(const float* g_out, const EEStrides* gs, const float* x, const EEStrides* xs, const float* base,
+                                  const EEStrides* bs, float* g_x_or_null, const EEStrides* gxs, float* g_base_or_null,
+                                  const EEStrides* gbs, int B, int C, int H, int W, const EEParams* p, float w, void* stream) {
+    return edge_backward(g_out, x, base, g_x_or_null, g_base_or_null, B, C, H, W, p, w, true, stream, gs, xs, bs, gxs, gbs, true);
 }
 size_t ee_aux_bytes(int, int, int, int, int) { return 0; }
 

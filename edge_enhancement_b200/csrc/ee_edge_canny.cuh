@@ -128,19 +128,18 @@ template <int VEC, int NC, bool BLEND>
 __device__ __forceinline__ void emit(const EdgeArgs& a, int b, int row, int col, const float (&e)[VEC]) {
     const int W = a.W;
     const int C = NC ? NC : a.C;
-    const size_t hw = (size_t)a.H * W;
-    const size_t pix = (size_t)row * W + col;
-    if (a.edge) stg_vec<VEC>(a.edge + (size_t)b * hw + pix, e);
+    (void)W;
+    if (a.edge) stg_vec<VEC>(a.edge + at(a.sedge, b, 0, row, col), e);
     if (BLEND) {
         float we[VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) we[k] = a.w * e[k];
         for (int c = 0; c < C; ++c) {
             float t[VEC], o[VEC];
-            ldg_vec<VEC>(a.base + ((size_t)b * C + c) * hw + pix, t);
+            ldg_vec<VEC>(a.base + at(a.sbase, b, c, row, col), t);
 #pragma unroll
             for (int k = 0; k < VEC; ++k) o[k] = clamp01_nan(t[k] + we[k]);
-            stg_vec<VEC>(a.out + ((size_t)b * C + c) * hw + pix, o);
+            stg_vec<VEC>(a.out + at(a.sout, b, c, row, col), o);
         }
     }
 }
@@ -171,7 +170,7 @@ __global__ void __launch_bounds__(256) edge_fwd_canny_kernel(const EdgeArgs a) {
     const int m_lo = max(r0 - 1 - hc, 0), m_hi = min(r1 + 1 + hc, H);
 
     float* S = R1; float* Bl = R2;
-    stage_channel_sum<VEC, NC>(a, a.x + (size_t)b * C * hw, S, s_lo, s_hi, G, tx, ty);
+    stage_channel_sum<VEC, NC>(a, a.x + (size_t)((int64_t)b * a.sx.b), S, s_lo, s_hi, G, tx, ty);
     __syncthreads();
     stage_blur<VEC>(a, S, s_lo, Bl, b_lo, b_hi, G, tx, ty);
     __syncthreads();
@@ -275,7 +274,7 @@ __global__ void __launch_bounds__(256) edge_bwd_canny_kernel(const EdgeArgs a) {
     const int gb_lo = max(r0 - 1, 0), gb_hi = min(r1 + 1, H);
 
     float* S = R1; float* Bl = R2;
-    stage_channel_sum<VEC, NC>(a, a.x + (size_t)b * C * hw, S, s_lo, s_hi, G, tx, ty);
+    stage_channel_sum<VEC, NC>(a, a.x + (size_t)((int64_t)b * a.sx.b), S, s_lo, s_hi, G, tx, ty);
     __syncthreads();
     stage_blur<VEC>(a, S, s_lo, Bl, b_lo, b_hi, G, tx, ty);
     __syncthreads();
@@ -321,20 +320,19 @@ __global__ void __launch_bounds__(256) edge_bwd_canny_kernel(const EdgeArgs a) {
             }
             const bool interior = (row >= r0 && row < r1);
             for (int c = 0; c < C; ++c) {
-                const size_t o = ((size_t)b * C + c) * hw + pix;
                 float bs[VEC], go[VEC], gp[VEC];
-                ldg_vec<VEC>(a.base + o, bs);
-                ldg_vec<VEC>(a.g_in + o, go);
+                ldg_vec<VEC>(a.base + at(a.sbase, b, c, row, col), bs);
+                ldg_vec<VEC>(a.g_in + at(a.sg, b, c, row, col), go);
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) {
                     const float pre = bs[k] + we[k];
                     gp[k] = (pre >= 0.0f && pre <= 1.0f) ? go[k] : 0.0f;
                     ge[k] = (c == 0) ? gp[k] * a.w : fmaf(gp[k], a.w, ge[k]);
                 }
-                if (a.g_base && interior) stg_vec<VEC>(a.g_base + o, gp);
+                if (a.g_base && interior) stg_vec<VEC>(a.g_base + at(a.sgbase, b, c, row, col), gp);
             }
         } else {
-            ldg_vec<VEC>(a.g_in + (size_t)b * hw + pix, ge);
+            ldg_vec<VEC>(a.g_in + at(a.sg, b, 0, row, col), ge);
         }
         if (want_gx) {
             float av[VEC], bv[VEC];

@@ -21,6 +21,8 @@
 
 namespace ee {
 
+struct EEStride3 { int64_t b, c, h; };
+
 struct EdgeArgs {
     const float* x;       // [B,C,H,W]
     const float* base;    // [B,C,H,W]   (blend only)
@@ -35,7 +37,17 @@ struct EdgeArgs {
     float c0, c1, c2, fC, alpha, low, high, w;
     int variant, has_low, has_high, hyst;
     int nan_compat;       // EE_FLAG_NAN_COMPAT: dL/dSgx = dL/dSgy = NaN where the magnitude is exactly 0 (generic backward kernels)
+    // element strides (batch, channel, row) of the image tensors; the column stride is always 1.  Dense NCHW is
+    // {C*H*W, H*W, W}; the shape-generic kernels honour them (sliced batches, channel slices, crops: ee_*_strided_f32),
+    // the tuned kernels require dense tensors.
+    EEStride3 sx, sbase, sg, sout, sgx, sgbase, sedge;
+    int strided;          // some tensor is not dense: shape-generic kernels only
 };
+
+// element offset of (image b, channel c, row r, column col)
+__device__ __forceinline__ size_t at(const EEStride3& s, int b, int c, int r, int col) {
+    return (size_t)((int64_t)b * s.b + (int64_t)c * s.c + (int64_t)r * s.h) + col;
+}
 
 #define EE_FOR_TILE(row_lo, row_hi)                                     \
     if (ty < a.RY)                                                      \
@@ -48,10 +60,10 @@ __device__ __forceinline__ void stage_channel_sum(const EdgeArgs& a, const float
                                                   int lo, int hi, int G, int tx, int ty) {
     const int C = NC ? NC : a.C;
     const int W = a.W;
-    const size_t hw = (size_t)a.H * W;
+    const size_t hw = (size_t)a.sx.c;                  // channel stride of x
     EE_FOR_TILE(lo, hi) {
         const int col = g * VEC;
-        const float* px = xb + (size_t)row * W + col;
+        const float* px = xb + (size_t)row * (size_t)a.sx.h + col;
         float acc[VEC];
         ldg_vec<VEC>(px, acc);
         if (NC == 3) {
@@ -122,7 +134,7 @@ __global__ void __launch_bounds__(256) edge_fwd_step125_kernel(const EdgeArgs a)
     float* S = smem;
     float* Bl = smem + (size_t)(a.TH + 4) * W;
 
-    stage_channel_sum<VEC, NC>(a, a.x + (size_t)b * C * hw, S, s_lo, s_hi, G, tx, ty);
+    stage_channel_sum<VEC, NC>(a, a.x + (size_t)((int64_t)b * a.sx.b), S, s_lo, s_hi, G, tx, ty);
     __syncthreads();
     stage_blur<VEC>(a, S, s_lo, Bl, b_lo, b_hi, G, tx, ty);
     __syncthreads();
@@ -133,7 +145,7 @@ __global__ void __launch_bounds__(256) edge_fwd_step125_kernel(const EdgeArgs a)
         float bs[NC ? NC : 1][VEC];
         if (BLEND && NC) {
 #pragma unroll
-            for (int c = 0; c < NC; ++c) ldg_vec<VEC>(a.base + ((size_t)b * C + c) * hw + pix, bs[c]);
+            for (int c = 0; c < NC; ++c) ldg_vec<VEC>(a.base + at(a.sbase, b, c, row, col), bs[c]);
         }
         float gx1[VEC], gy1[VEC], e[VEC];
         sobel_at<VEC>(a, Bl, b_lo, row, col, gx1, gy1);
@@ -143,7 +155,7 @@ __global__ void __launch_bounds__(256) edge_fwd_step125_kernel(const EdgeArgs a)
             const float magm = (mag < a.alpha) ? 0.0f : mag;       // core.py:574-575
             e[k] = to_compare(magm, a.high);                      // core.py:578-583
         }
-        if (a.edge) stg_vec<VEC>(a.edge + (size_t)b * hw + pix, e);
+        if (a.edge) stg_vec<VEC>(a.edge + at(a.sedge, b, 0, row, col), e);
         if (BLEND) {
             float we[VEC];
 #pragma unroll
@@ -154,15 +166,15 @@ __global__ void __launch_bounds__(256) edge_fwd_step125_kernel(const EdgeArgs a)
                     float o[VEC];
 #pragma unroll
                     for (int k = 0; k < VEC; ++k) o[k] = clamp01_nan(bs[c][k] + we[k]);
-                    stg_vec<VEC>(a.out + ((size_t)b * C + c) * hw + pix, o);
+                    stg_vec<VEC>(a.out + at(a.sout, b, c, row, col), o);
                 }
             } else {
                 for (int c = 0; c < C; ++c) {
                     float t[VEC], o[VEC];
-                    ldg_vec<VEC>(a.base + ((size_t)b * C + c) * hw + pix, t);
+                    ldg_vec<VEC>(a.base + at(a.sbase, b, c, row, col), t);
 #pragma unroll
                     for (int k = 0; k < VEC; ++k) o[k] = clamp01_nan(t[k] + we[k]);
-                    stg_vec<VEC>(a.out + ((size_t)b * C + c) * hw + pix, o);
+                    stg_vec<VEC>(a.out + at(a.sout, b, c, row, col), o);
                 }
             }
         }
@@ -270,8 +282,7 @@ __device__ __forceinline__ void stage_gauss_adjoint_store(const EdgeArgs& a, con
 #pragma unroll
             for (int k = 0; k < VEC; ++k) o[k] = o[k] + t[k];
         }
-        float* pg = a.g_x + (size_t)b * C * hw + (size_t)row * W + col;
-        for (int c = 0; c < C; ++c) stg_vec<VEC>(pg + (size_t)c * hw, o);
+        for (int c = 0; c < C; ++c) stg_vec<VEC>(a.g_x + at(a.sgx, b, c, row, col), o);
     }
 }
 
@@ -302,7 +313,7 @@ __global__ void __launch_bounds__(256) edge_bwd_step125_kernel(const EdgeArgs a)
     const int gb_lo = max(r0 - 1, 0), gb_hi = min(r1 + 1, H);
 
     float* S = R1; float* Bl = R2;
-    stage_channel_sum<VEC, NC>(a, a.x + (size_t)b * C * hw, S, s_lo, s_hi, G, tx, ty);
+    stage_channel_sum<VEC, NC>(a, a.x + (size_t)((int64_t)b * a.sx.b), S, s_lo, s_hi, G, tx, ty);
     __syncthreads();
     stage_blur<VEC>(a, S, s_lo, Bl, b_lo, b_hi, G, tx, ty);
     __syncthreads();
@@ -325,20 +336,19 @@ __global__ void __launch_bounds__(256) edge_bwd_step125_kernel(const EdgeArgs a)
             for (int k = 0; k < VEC; ++k) we[k] = a.w * to_compare(magm[k], a.high);
             const bool interior = (row >= r0 && row < r1);
             for (int c = 0; c < C; ++c) {
-                const size_t o = ((size_t)b * C + c) * hw + pix;
                 float bs[VEC], go[VEC], gp[VEC];
-                ldg_vec<VEC>(a.base + o, bs);
-                ldg_vec<VEC>(a.g_in + o, go);
+                ldg_vec<VEC>(a.base + at(a.sbase, b, c, row, col), bs);
+                ldg_vec<VEC>(a.g_in + at(a.sg, b, c, row, col), go);
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) {
                     const float pre = bs[k] + we[k];
                     gp[k] = (pre >= 0.0f && pre <= 1.0f) ? go[k] : 0.0f;     // clamp backward, inclusive
                     ge[k] = (c == 0) ? gp[k] * a.w : fmaf(gp[k], a.w, ge[k]);
                 }
-                if (a.g_base && interior) stg_vec<VEC>(a.g_base + o, gp);
+                if (a.g_base && interior) stg_vec<VEC>(a.g_base + at(a.sgbase, b, c, row, col), gp);
             }
         } else {
-            ldg_vec<VEC>(a.g_in + (size_t)b * hw + pix, ge);
+            ldg_vec<VEC>(a.g_in + at(a.sg, b, 0, row, col), ge);
         }
         if (want_gx) {
             float av[VEC], bv[VEC];

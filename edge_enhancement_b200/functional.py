@@ -79,6 +79,22 @@ def _as_layout(t, name, shape, nhwc):
     return t.contiguous(memory_format=torch.channels_last) if nhwc else t.contiguous()
 
 
+def _rows_ok(t):
+    """A non-dense 4-D view the library reads in place through ee_*_strided_f32: unit column stride (sliced batches,
+    channel slices, expanded batches, spatial crops) and no negative strides."""
+    return t.dim() == 4 and (t.shape[3] == 1 or t.stride(3) == 1) and min(t.stride()) >= 0
+
+
+def _strides(t):
+    return None if t is None or t.is_contiguous() else ctypes.byref(_lib.EEStrides(*t.stride()))
+
+
+def _in_place_or_copy(t, name, shape=None):
+    """The tensor itself when the library can read its strides, else a dense copy (never silently wrong)."""
+    t = _chk_nocopy(t, name, shape)
+    return t if (t.is_contiguous() or _rows_ok(t)) else t.contiguous()
+
+
 def _with_layout(params, nhwc):
     want = EE_LAYOUT_NHWC if nhwc else EE_LAYOUT_NCHW
     if params.layout == want:
@@ -132,7 +148,7 @@ def _ptr(t):
 # --------------------------------------------------------------------------------------------
 def edge_map(x, params):
     """edge[B,1,H,W] = filter(x[B,C,H,W]) -- ee_edge_fwd_f32."""
-    x = _chk(x, "img")
+    x = _in_place_or_copy(x, "img")
     if x.dim() != 4:
         raise ValueError("img must be [B,C,H,W]")
     B, C, H, W = x.shape
@@ -140,20 +156,27 @@ def edge_map(x, params):
     if x.numel() == 0:
         return edge
     with _on_device(x):
-        rc = _lib.load().ee_edge_fwd_f32(_ptr(x), _ptr(edge), B, C, H, W, ctypes.byref(params), _stream(x))
+        if x.is_contiguous():
+            rc = _lib.load().ee_edge_fwd_f32(_ptr(x), _ptr(edge), B, C, H, W, ctypes.byref(params), _stream(x))
+        else:                       # a view with unit column stride: read in place
+            rc = _lib.load().ee_edge_fwd_strided_f32(_ptr(x), _strides(x), _ptr(edge), None, B, C, H, W, ctypes.byref(params), _stream(x))
     _lib.check(rc, "ee_edge_fwd_f32")
     return edge
 
 
 def edge_map_backward(g_edge, x, params):
-    x = _chk(x, "img")
+    x = _in_place_or_copy(x, "img")
     B, C, H, W = x.shape
-    g_edge = _chk(g_edge, "grad_edge", (B, 1, H, W))
-    g_x = torch.empty_like(x)
+    g_edge = _in_place_or_copy(g_edge, "grad_edge", (B, 1, H, W))
+    g_x = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
     if x.numel() == 0:
         return g_x
     with _on_device(x):
-        rc = _lib.load().ee_edge_bwd_f32(_ptr(g_edge), _ptr(x), _ptr(g_x), B, C, H, W, ctypes.byref(params), _stream(x))
+        if x.is_contiguous() and g_edge.is_contiguous():
+            rc = _lib.load().ee_edge_bwd_f32(_ptr(g_edge), _ptr(x), _ptr(g_x), B, C, H, W, ctypes.byref(params), _stream(x))
+        else:
+            rc = _lib.load().ee_edge_bwd_strided_f32(_ptr(g_edge), _strides(g_edge), _ptr(x), _strides(x), _ptr(g_x), None,
+                                                     B, C, H, W, ctypes.byref(params), _stream(x))
     _lib.check(rc, "ee_edge_bwd_f32")
     return g_x
 
@@ -166,6 +189,8 @@ def edge_blend(x, base, params, w, want_edge=False, out=None):
     if x.dim() != 4:
         raise ValueError("img must be [B,C,H,W]")
     nhwc = _nhwc_ok(x)
+    if not nhwc and not (x.is_contiguous() and base.is_contiguous()):
+        return _edge_blend_strided(x, base, params, w, want_edge, out)
     x = _as_layout(x, "img", None, nhwc)
     B, C, H, W = x.shape
     base = _as_layout(base, "base", x.shape, nhwc)
@@ -180,11 +205,32 @@ def edge_blend(x, base, params, w, want_edge=False, out=None):
     return (out, edge) if want_edge else out
 
 
+def _edge_blend_strided(x, base, params, w, want_edge, out):
+    """edge_blend on views the library reads in place (unit column stride): no .contiguous() pass over HBM."""
+    x = _in_place_or_copy(x, "img")
+    B, C, H, W = x.shape
+    base = _in_place_or_copy(base, "base", x.shape)
+    if out is None:
+        out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+    elif not (out.is_cuda and out.dtype == torch.float32 and out.shape == x.shape and (out.is_contiguous() or _rows_ok(out))):
+        raise ValueError("edge_b200: `out` must be a float32 CUDA tensor of the input's shape with unit column stride")
+    edge = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device) if want_edge else None
+    if x.numel():
+        p = _with_layout(params, False)
+        with _on_device(x):
+            rc = _lib.load().ee_edge_blend_fwd_strided_f32(_ptr(x), _strides(x), _ptr(base), _strides(base), _ptr(out), _strides(out),
+                                                           _ptr(edge), None, B, C, H, W, ctypes.byref(p), float(w), _stream(x))
+        _lib.check(rc, "ee_edge_blend_fwd_strided_f32")
+    return (out, edge) if want_edge else out
+
+
 def edge_blend_backward(g_out, x, base, params, w, need_x=True, need_base=True, g_x=None, g_base=None):
     """(g_x, g_base) of edge_blend in one pass -- ee_edge_blend_bwd_f32.  g_x / g_base may be
     preallocated buffers (not aliasing any input)."""
     x = _chk_nocopy(x, "img")
     nhwc = _nhwc_ok(x, params)
+    if not nhwc and not _is_channels_last(x) and not (x.is_contiguous() and base.is_contiguous() and g_out.is_contiguous()):
+        return _edge_blend_backward_strided(g_out, x, base, params, w, need_x, need_base, g_x, g_base)
     x = _as_layout(x, "img", None, nhwc)
     B, C, H, W = x.shape
     base = _as_layout(base, "base", x.shape, nhwc)
@@ -258,6 +304,30 @@ def gf_blend_backward(g_out, edge, base, gauss, w, need_edge=True, need_base=Tru
                                                  _gauss9(gauss), float(w), _stream(base))
         _lib.check(rc, "ee_gf_blend_bwd_f32")
     return g_edge, g_base
+
+
+def _edge_blend_backward_strided(g_out, x, base, params, w, need_x, need_base, g_x, g_base):
+    x = _in_place_or_copy(x, "img")
+    B, C, H, W = x.shape
+    base = _in_place_or_copy(base, "base", x.shape)
+    g_out = _in_place_or_copy(g_out, "grad_out", x.shape)
+
+    def result(buf):
+        if buf is None:
+            return torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+        if not (buf.is_cuda and buf.dtype == torch.float32 and buf.shape == x.shape and (buf.is_contiguous() or _rows_ok(buf))):
+            raise ValueError("edge_b200: gradient buffers must be float32 CUDA tensors of the input's shape with unit column stride")
+        return buf
+    g_x = result(g_x) if need_x else None
+    g_base = result(g_base) if need_base else None
+    if x.numel() and (need_x or need_base):
+        p = _with_layout(params, False)
+        with _on_device(x):
+            rc = _lib.load().ee_edge_blend_bwd_strided_f32(_ptr(g_out), _strides(g_out), _ptr(x), _strides(x), _ptr(base), _strides(base),
+                                                           _ptr(g_x), _strides(g_x), _ptr(g_base), _strides(g_base), B, C, H, W,
+                                                           ctypes.byref(p), float(w), _stream(x))
+        _lib.check(rc, "ee_edge_blend_bwd_strided_f32")
+    return g_x, g_base
 
 
 def _same(*ts):

@@ -115,6 +115,27 @@ int ee_gf_blend_fwd_f32(const float* edge, const float* base, float* out, int B,
 int ee_gf_blend_bwd_f32(const float* g_out, const float* edge, const float* base, float* g_edge_or_null,
                         float* g_base_or_null, int B, int C, int H, int W, const float gauss[9], float w, void* stream);
 
+/* ---- strided variants (`const int64_t xs[4]`) ------------------------------------------
+ * Element strides of a [B,C,H,W] tensor in torch.Tensor.stride() order; a NULL EEStrides pointer means "dense in
+ * EEParams.layout".  Accepted without a copy: dense NCHW, dense NHWC (= torch.channels_last, subject to the NHWC rules
+ * above), and ANY tensor whose column stride is 1 -- sliced batches (x[::2], x[lo:hi]), channel slices (x[:, 1:4]),
+ * expanded batches (stride 0) and spatial crops (x[:, :, 16:240, 16:240]).  Dense tensors run the tuned kernels; other
+ * strides run the shape-generic kernels on the tensor in place (128-bit path when every stride and base address is a
+ * multiple of 4 floats), which costs less than the contiguous copy it replaces.  A column stride other than 1 (outside
+ * channels_last) returns EE_ERR_UNSUPPORTED.  Outputs may be strided too; tensors must not overlap. */
+typedef struct EEStrides { int64_t n, c, h, w; } EEStrides;
+
+int ee_edge_fwd_strided_f32(const float* x, const EEStrides* xs, float* edge, const EEStrides* es, int B, int C, int H, int W,
+                            const EEParams* p, void* stream);
+int ee_edge_bwd_strided_f32(const float* g_edge, const EEStrides* ges, const float* x, const EEStrides* xs, float* g_x,
+                            const EEStrides* gxs, int B, int C, int H, int W, const EEParams* p, void* stream);
+int ee_edge_blend_fwd_strided_f32(const float* x, const EEStrides* xs, const float* base, const EEStrides* bs, float* out,
+                                  const EEStrides* os, float* edge_or_null, const EEStrides* es, int B, int C, int H, int W,
+                                  const EEParams* p, float w, void* stream);
+int ee_edge_blend_bwd_strided_f32(const float* g_out, const EEStrides* gs, const float* x, const EEStrides* xs, const float* base,
+                                  const EEStrides* bs, float* g_x_or_null, const EEStrides* gxs, float* g_base_or_null,
+                                  const EEStrides* gbs, int B, int C, int H, int W, const EEParams* p, float w, void* stream);
+
 /* Workspace the edge entry points need from the caller: always 0 (recompute formulation). */
 size_t ee_aux_bytes(int B, int C, int H, int W, int variant);
 

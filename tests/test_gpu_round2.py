@@ -314,3 +314,74 @@ def test_hfs_module_has_no_silent_fallback():
     assert y.shape == x.shape
     with pytest.raises(NotImplementedError):
         core.HighFreqSuppress(64, 64, 8, c2r='full')
+
+
+# ---------------------------------------------------------------------------------------------
+# strided tensors at the C ABI (ee_*_strided_f32): views are read in place, results identical to the dense call
+# ---------------------------------------------------------------------------------------------
+def _views(B, C, H, W, seed):
+    """name -> (x, base, g_out) views of larger tensors, all with unit column stride but not contiguous."""
+    gen = torch.Generator(device=DEV).manual_seed(seed)
+    def big(*shape):
+        return torch.rand(shape, device=DEV, generator=gen)
+    out = {}
+    t = [big(2 * B, C, H, W) for _ in range(3)]
+    out["batch_step2"] = tuple(v[::2] for v in t)
+    t = [big(B, C + 2, H, W) for _ in range(3)]
+    out["channel_slice"] = tuple(v[:, 1:1 + C] for v in t)
+    t = [big(B, C, H + 8, W + 8) for _ in range(3)]
+    out["crop_aligned"] = tuple(v[:, :, 4:4 + H, 4:4 + W] for v in t)          # 16-byte aligned rows: 128-bit path
+    out["crop_unaligned"] = tuple(v[:, :, 3:3 + H, 5:5 + W] for v in t)        # scalar path
+    t = [big(1, C, H, W) for _ in range(3)]
+    out["expanded_batch"] = tuple(v.expand(B, C, H, W) for v in t)
+    return out
+
+
+@pytest.mark.parametrize("variant", ["step125", "canny", "bpda"])
+@pytest.mark.parametrize("shape", [(4, 3, 64, 64), (3, 1, 28, 28), (2, 3, 24, 40)], ids=str)
+def test_strided_views_are_read_in_place(variant, shape):
+    B, C, H, W = shape
+    low = None if variant == "step125" else T.LOW
+    p = F_ee.make_params(variant, GAUSS, 0.0, low, T.HIGH, True)
+    for name, (x, base, g_out) in _views(B, C, H, W, 3).items():
+        assert not x.is_contiguous(), name
+        base = base * 1.1 - 0.1
+        g_out = g_out - 0.5
+        xc, bc, gc = x.contiguous(), base.contiguous(), g_out.contiguous()
+        want_out, want_edge = F_ee.edge_blend(xc, bc, p, 1.0, want_edge=True)
+        got_out, got_edge = F_ee.edge_blend(x, base, p, 1.0, want_edge=True)
+        assert torch.equal(got_out, want_out) and torch.equal(got_edge, want_edge), name
+        want_gx, want_gb = F_ee.edge_blend_backward(gc, xc, bc, p, 1.0)
+        got_gx, got_gb = F_ee.edge_blend_backward(g_out, x, base, p, 1.0)
+        assert torch.equal(got_gx, want_gx) and torch.equal(got_gb, want_gb), name
+        assert torch.equal(F_ee.edge_map(x, p), F_ee.edge_map(xc, p)), name
+        ge = g_out[:, :1]
+        assert torch.equal(F_ee.edge_map_backward(ge, x, p), F_ee.edge_map_backward(ge.contiguous(), xc, p)), name
+    # strided OUTPUT buffers
+    x, base, g_out = (v.contiguous() for v in _views(B, C, H, W, 4)["batch_step2"])
+    big_out = torch.zeros((B, C, H + 4, W + 4), device=DEV)
+    view = big_out[:, :, 2:2 + H, 0:W]
+    F_ee.edge_blend(x, base[::1], p, 1.0, out=None)
+    got = F_ee._edge_blend_strided(x, base, p, 1.0, False, view)
+    assert got is view and torch.equal(view, F_ee.edge_blend(x, base, p, 1.0)) and float(big_out[:, :, :2].abs().sum()) == 0.0
+
+
+def test_strided_autograd_and_unsupported_strides():
+    f = quiet(core.CannyFilter_step125_1, use_cuda=False, alpha=0.0)
+    big = torch.rand((8, 3, 64, 64), device=DEV)
+    xv = big[1::2].detach().requires_grad_()            # a non-contiguous leaf view
+    xc = big[1::2].contiguous().requires_grad_()
+    g = torch.randn((4, 3, 64, 64), device=DEV)
+    core.edge_enhance(xv, xv, f, 1.0, None, T.HIGH, True).backward(g)
+    core.edge_enhance(xc, xc, f, 1.0, None, T.HIGH, True).backward(g)
+    assert torch.equal(xv.grad, xc.grad)
+    # a transposed view (column stride != 1) is copied by the wrapper, and rejected at the ABI
+    xt = torch.rand((2, 3, 64, 64), device=DEV).transpose(2, 3)
+    p = f.params(None, T.HIGH, False)
+    assert torch.equal(F_ee.edge_map(xt, p), F_ee.edge_map(xt.contiguous(), p))
+    L = _lib.load()
+    import ctypes
+    s = _lib.EEStrides(*xt.stride())
+    edge = torch.empty((2, 1, 64, 64), device=DEV)
+    rc = L.ee_edge_fwd_strided_f32(xt.data_ptr(), ctypes.byref(s), edge.data_ptr(), None, 2, 3, 64, 64, ctypes.byref(p), None)
+    assert rc == -2 and b"column stride" in L.ee_last_error()

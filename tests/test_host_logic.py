@@ -295,3 +295,21 @@ def test_high_freq_suppress_raises_instead_of_falling_back():
         core.HighFreqSuppress(64, 64, 8, c2r='full')                       # native kernel = one-sided reading only
     with pytest.raises(ValueError):
         core.HighFreqSuppress(64, 64, 8, c2r='half')
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference checkout not present (build container only)")
+@pytest.mark.parametrize("script", ["mnist", "tiny", "imagenet"])
+def test_reference_scripts_run_their_main_up_to_the_first_kernel(script, tmp_path):
+    """tools/run_reference_step.py runs the reference's UNMODIFIED main() -- config parsing, model
+    construction from the reference's own model files (whose `from utils.core import ...` resolve to the drop-ins), optimiser,
+    synthetic loaders, train() -- and on this CPU-only container must stop exactly at the drop-in's first kernel call."""
+    import subprocess
+    import sys
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "run_reference_step.py")
+    r = subprocess.run([sys.executable, tool, script, "--dry-run"], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "DRY RUN OK" in r.stdout and "no CPU fallback" in r.stdout
+    if script == "imagenet":
+        assert "validate(): 6-argument calls" in r.stdout
+    if script == "tiny":
+        assert "duplicate keys" in r.stdout and "step_size_1" in r.stdout
