@@ -856,6 +856,7 @@ int edge_backward(const float* g_in, const float* x, const float* base, float* g
     if (!blend && !g_x) return fail(EE_ERR_INVALID_ARG, "g_x is null");
     if (blend && !g_x && !g_base) return EE_OK;   // nothing requested
     a.x = x; a.base = base; a.g_in = g_in; a.g_x = g_x; a.g_base = g_base;
+    if (!blend) a.sg = a.sedge;                      // module-level backward: the upstream gradient is the [B,1,H,W] edge gradient
     bool vec_ok = (W % 4 == 0) && aligned16(x) && aligned16(base) && aligned16(g_in) && aligned16(g_x) && aligned16(g_base);
     bool nhwc = (p->layout == EE_LAYOUT_NHWC) && C > 1;
     if (strided_api) {

@@ -25,6 +25,8 @@
 #pragma once
 #include <cuda_pipeline.h>
 
+#include <type_traits>
+
 #include "ee_device.cuh"
 
 namespace ee {
@@ -56,8 +58,15 @@ template <int N, int R, int P>
 __global__ void __launch_bounds__(256) hfs_kernel(const HfsArgs a) {
     using D_ = HfsDims<N, R>;
     constexpr int NJp = D_::NJp, NIp = D_::NIp, NI = D_::NI, NJ = D_::NJ, XS = D_::XS, JS = D_::JS, IS = D_::IS;
-    constexpr int TP = 256 / P, N4 = N / 4;
+    constexpr int TP = 256 / P, N4 = N / 4, HALFN = N / 2;
     static_assert(N % 4 == 0 && 256 % P == 0, "whole float4 rows, whole thread groups");
+    // even-odd folding of the two large products (stages 0, 1, 5): measured 172 -> 164 us at 64 px, 308 -> 254 us at 128 px,
+    // but 53 -> 57 us at 28 px (planes of 16 threads: the fold pass costs more than the shorter chains save)
+    constexpr bool FOLD = (N >= 64);
+    static_assert(!FOLD || R % 4 == 0, "cosine / sine column blocks of the bases must be whole float4 groups (even-odd folding)");
+    // (stage 2 has only (NIp/4)*(NJp/4) register tiles per plane -- 20 at 64 px for 64 threads; splitting its K range over
+    //  two adjacent lanes halves the longest serial chain but was measured SLOWER on the same box, 153.8 -> 168.7 us at
+    //  4096x3x64x64: the kernel is bound by issued instructions, not by that chain, and the split adds 16 shuffles per lane)
     extern __shared__ __align__(16) float smem_hfs[];
     float* CB = smem_hfs;                       // [N][JS]
     float* RB = CB + N * JS;                    // [N][IS]
@@ -69,6 +78,14 @@ __global__ void __launch_bounds__(256) hfs_kernel(const HfsArgs a) {
     float* Dm = T + N * JS;                     // [NIp][NJp]
     float* G = Dm + NIp * NJp;                  // [NIp][NJp]
     const int groups = (a.planes + P - 1) / P;
+    // The stages of one plane only exchange data among that plane's TP threads, so they synchronise on a NAMED barrier of
+    // their own (bar.sync id, TP) instead of stalling the other planes of the CTA at every stage boundary (16 % of the
+    // stall samples with CTA-wide barriers, profiles/r2j_*); one warp per plane needs __syncwarp only.
+    auto plane_sync = [&]() {
+        if constexpr (TP == 32) __syncwarp();
+        else if constexpr (TP % 32 == 0 && P <= 15) asm volatile("bar.sync %0, %1;" ::"r"(p + 1), "n"(TP) : "memory");
+        else __syncthreads();
+    };
     auto load_planes_async = [&](int g) {        // this thread group's plane of group g -> X (16-byte cp.async)
         const int pl = g * P + p;
         if (g < groups && pl < a.planes) {
@@ -98,8 +115,90 @@ __global__ void __launch_bounds__(256) hfs_kernel(const HfsArgs a) {
     const int plane = grp * P + p;
     const bool live = plane < a.planes;
     __pipeline_wait_prior(0);
-    __syncthreads();                             // this group's planes (and, the first time, the tables) are in shared memory
+    if (grp == (int)blockIdx.x) __syncthreads();  // first group: the tables (loaded by all threads) are in shared memory
+    else plane_sync();                            // later: only this plane's threads wrote / will read its buffers
 
+    if constexpr (FOLD) {
+    // ---- stage 0: fold every row of X into its even and odd part about w = 0 (in place; the pairs are disjoint):
+    //          X[h][w] <- x[w] + x[N-w] (w = 1..N/2-1; w = 0 and N/2 are their own mirror),  X[h][N-w] <- x[N-w] - x[w].
+    //      cos(k th_w) is even and sin(k th_w) odd in w, so the cosine columns of T only need the even part over
+    //      w = 0..N/2 and the sine columns the odd part over w = N/2+1..N-1: half the multiply-adds of stage 1.
+    if (live) {
+        // items are (h, w) with w in [0, HP): HP = N/2 rounded up to a power of two keeps the index arithmetic to a shift
+        // and a mask (a division by N/2 - 1 cost as much as the fold saves); consecutive lanes take consecutive w
+        constexpr int HP = (HALFN <= 16) ? 16 : (HALFN <= 32 ? 32 : 64), HPS = (HP == 16) ? 4 : (HP == 32 ? 5 : 6);
+        for (int e = lt; e < N * HP; e += TP) {
+            const int h = e >> HPS, w = e & (HP - 1);
+            if (w >= 1 && w < HALFN) {
+                float* row = X + h * XS;
+                const float u = row[w], v = row[N - w];
+                row[w] = u + v;
+                row[N - w] = v - u;
+            }
+        }
+    }
+    plane_sync();
+
+    // ---- stage 1: T = X CB   (N x NJp): tile = rows {hg + N4*i} x columns 4jg..4jg+3; the K range is w = 0..N/2 for a
+    //      tile of cosine columns and w = N/2..N-1 for sine columns (the table entry sin(k th_{N/2}) is exactly 0).  The two
+    //      kinds are separate instantiations so that every loop bound and shared-memory offset is a compile-time constant
+    //      (with run-time bounds the address arithmetic cost as much as the folding saved) ---------------------------------
+    if (live) {
+        auto tile1 = [&](auto cos_tag, const int hg, const int jg) {
+            constexpr bool COS = decltype(cos_tag)::value;
+            constexpr int W_LO = COS ? 0 : HALFN, W_HI = COS ? HALFN + 1 : N;
+            constexpr int V_LO = (W_LO + 3) & ~3, V_HI = W_HI & ~3;          // float4-aligned body [V_LO, V_HI)
+            const float* xr = X + hg * XS;
+            const float* cr = CB + 4 * jg;
+            float acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
+            auto one = [&](const int w) {
+                const float4 cv = *reinterpret_cast<const float4*>(cr + w * JS);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float xs = xr[N4 * i * XS + w];
+                    acc[i][0] = fmaf(xs, cv.x, acc[i][0]);
+                    acc[i][1] = fmaf(xs, cv.y, acc[i][1]);
+                    acc[i][2] = fmaf(xs, cv.z, acc[i][2]);
+                    acc[i][3] = fmaf(xs, cv.w, acc[i][3]);
+                }
+            };
+#pragma unroll
+            for (int w = W_LO; w < V_LO; ++w) one(w);
+#pragma unroll 4
+            for (int w = V_LO; w < V_HI; w += 4) {
+                float4 xv[4], cv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(xr + N4 * i * XS + w);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) cv[q] = *reinterpret_cast<const float4*>(cr + (w + q) * JS);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float xs[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        acc[i][0] = fmaf(xs[q], cv[q].x, acc[i][0]);
+                        acc[i][1] = fmaf(xs[q], cv[q].y, acc[i][1]);
+                        acc[i][2] = fmaf(xs[q], cv[q].z, acc[i][2]);
+                        acc[i][3] = fmaf(xs[q], cv[q].w, acc[i][3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int w = V_HI; w < W_HI; ++w) one(w);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(T + (hg + N4 * i) * JS + 4 * jg) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        };
+        for (int t = lt; t < N4 * (NJp / 4); t += TP) {          // cosine tiles first: at 64 px warp 0 of the plane takes them, warp 1 the sines
+            const int hg = t % N4, jg = t / N4;
+            if (4 * jg < R) tile1(std::true_type{}, hg, jg); else tile1(std::false_type{}, hg, jg);
+        }
+    }
+    } else {
     // ---- stage 1: T = X CB   (N x NJp, K = N): tile = rows {hg + N4*i} x columns 4jg..4jg+3 -------------------
     if (live) {
         for (int t = lt; t < N4 * (NJp / 4); t += TP) {
@@ -133,7 +232,8 @@ __global__ void __launch_bounds__(256) hfs_kernel(const HfsArgs a) {
                 *reinterpret_cast<float4*>(T + (hg + N4 * i) * JS + 4 * jg) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
         }
     }
-    __syncthreads();
+    }
+    plane_sync();
     load_planes_async(grp + gridDim.x);          // X is dead: fetch the next group's planes behind stages 2-5
 
     // ---- stage 2: D = RB^T T   (NIp x NJp, K = N): tile = 4 basis rows x 4 columns ------------------------------
@@ -163,7 +263,7 @@ __global__ void __launch_bounds__(256) hfs_kernel(const HfsArgs a) {
                 *reinterpret_cast<float4*>(Dm + (4 * ig + i) * NJp + 4 * jg) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
         }
     }
-    __syncthreads();
+    plane_sync();
 
     // ---- stage 3: G = W o D, plus the four cross terms that the unpaired frequency row -r contributes -----------
     //      basis order: rows  i = 0..R : cos(k), i = R+k : sin(k) (k = 1..R);  columns j = 0..R-1 : cos(k), j = R-1+k : sin(k)
@@ -181,7 +281,7 @@ __global__ void __launch_bounds__(256) hfs_kernel(const HfsArgs a) {
             G[e] = (i < NI && j < NJ) ? g : 0.0f;
         }
     }
-    __syncthreads();
+    plane_sync();
 
     // ---- stage 4: V = RB G   (N x NJp, K = NI): tile = rows {hg + N4*i} x columns 4jg..4jg+3 --------------------
     if (live) {
@@ -209,8 +309,74 @@ __global__ void __launch_bounds__(256) hfs_kernel(const HfsArgs a) {
                 *reinterpret_cast<float4*>(V + (hg + N4 * i) * JS + 4 * jg) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
         }
     }
-    __syncthreads();
+    plane_sync();
 
+    if constexpr (FOLD) {
+    // ---- stage 5: y = V CB^T   (N x N): with Ye = (cosine columns of V) . cos(k th_w) and Yo = (sine columns) . sin(k th_w),
+    //      y[h][w] = Ye + Yo and y[h][N-w] = Ye - Yo: one tile = rows {hg + N4*i} x columns {wg + WS*c} of the HALF plane
+    //      w < N/2 with an even and an odd accumulator each (half the multiply-adds); the column w = N/2 (Yo == 0) is a
+    //      short pass of its own --------------------------------------------------------------------------------------
+    if (live) {
+        float* py = a.y + (size_t)plane * N * N;
+        const float* pa = a.add ? a.add + (size_t)plane * N * N : nullptr;
+        constexpr int WS = (HALFN + 3) / 4;
+        constexpr bool EXACT = (HALFN % 4 == 0);                  // every column slot of a tile is a real column
+        for (int t = lt; t < N4 * WS; t += TP) {
+            const int wg = t % WS, hg = t / WS;
+            float ae[4][4], ao[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { ae[i][c] = 0.0f; ao[i][c] = 0.0f; }
+#pragma unroll
+            for (int q = 0; q < NJp / 4; ++q) {
+                float4 vv[4], cv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) vv[i] = *reinterpret_cast<const float4*>(V + (hg + N4 * i) * JS + 4 * q);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) cv[c] = *reinterpret_cast<const float4*>(CB + (EXACT ? wg + WS * c : min(wg + WS * c, HALFN)) * JS + 4 * q);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float s = (4 * q < R) ? ae[i][c] : ao[i][c];
+                        s = fmaf(vv[i].x, cv[c].x, s);
+                        s = fmaf(vv[i].y, cv[c].y, s);
+                        s = fmaf(vv[i].z, cv[c].z, s);
+                        s = fmaf(vv[i].w, cv[c].w, s);
+                        if (4 * q < R) ae[i][c] = s; else ao[i][c] = s;
+                    }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int w = wg + WS * c;
+                    if (EXACT || w < HALFN) {
+                        const int o1 = (hg + N4 * i) * N + w;
+                        const float y1 = ae[i][c] + ao[i][c];
+                        __stcs(py + o1, pa ? y1 + __ldcs(pa + o1) : y1);
+                        if (w != 0) {
+                            const int o2 = (hg + N4 * i) * N + N - w;
+                            const float y2 = ae[i][c] - ao[i][c];
+                            __stcs(py + o2, pa ? y2 + __ldcs(pa + o2) : y2);
+                        }
+                    }
+                }
+        }
+        for (int h = lt; h < N; h += TP) {                      // the self-mirrored column w = N/2
+            float se = 0.0f, so = 0.0f;
+#pragma unroll
+            for (int j = 0; j < NJp; ++j) {
+                const float p_ = V[h * JS + j], c_ = CB[HALFN * JS + j];
+                if (j < R) se = fmaf(p_, c_, se); else so = fmaf(p_, c_, so);
+            }
+            const int o = h * N + HALFN;
+            const float y1 = se + so;
+            __stcs(py + o, pa ? y1 + __ldcs(pa + o) : y1);
+        }
+    }
+    } else {
     // ---- stage 5: y = V CB^T   (N x N, K = NJp): tile = rows {hg + N4*i} x columns {wg + N4*c} -------------------
     if (live) {
         float* py = a.y + (size_t)plane * N * N;
@@ -249,6 +415,7 @@ __global__ void __launch_bounds__(256) hfs_kernel(const HfsArgs a) {
                         __stcs(py + o, pa ? acc[i][c] + __ldcs(pa + o) : acc[i][c]);
                     }
         }
+    }
     }
   }   // persistent loop over plane groups (the barrier at its top also protects V against the next stage 1)
 }

@@ -453,6 +453,8 @@ def hfs_tables(N, r, device):
             cb[:, k] = np.cos(k * th); cb[:, r - 1 + k] = np.sin(k * th)
         for k in range(1, r + 1):
             rb[:, k] = np.cos(k * th); rb[:, r + k] = np.sin(k * th)
+        if N % 2 == 0:
+            cb[N // 2, r:] = 0.0       # sin(k pi) is exactly 0: the folded kernel's sine chains start at w = N/2
         alpha = np.zeros(NIp); beta = np.zeros(NJp)
         alpha[0] = 1.0 / N; alpha[1:r] = 2.0 / N; alpha[r] = 1.0 / N; alpha[r + 1:2 * r] = 2.0 / N; alpha[2 * r] = 1.0 / N
         beta[0] = 1.0 / N; beta[1:NJ] = 2.0 / N

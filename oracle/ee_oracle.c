@@ -834,9 +834,14 @@ static float tree_sum(float *p, int ks)
 }
 
 /* ks1 / ks2: the large-plane kernel (hfs_rows_kernel) splits the K range of T = x CB over ks1 lanes and that of
- * D = RB^T T over ks2 lanes and reduces the partial chains with a butterfly; 1 / 1 for the whole-plane kernel. */
+ * D = RB^T T over ks2 lanes and reduces the partial chains with a butterfly; 1 / 1 for the whole-plane kernel.
+ * fold: the whole-plane kernel (hfs_kernel) uses the parity of the bases along w -- cos(k th_w) even, sin(k th_w) odd about
+ * w = 0 -- to halve the two large products: every row of x is folded into xe[w] = x[w] + x[N-w] (w = 1..N/2-1; w = 0 and
+ * N/2 unchanged) and xo[w'] = x[w'] - x[N-w'] (w' = N/2+1..N-1); the cosine columns of T sum xe over w = 0..N/2, the sine
+ * columns xo over w = N/2..N-1 (table entry exactly 0 at N/2); y[h][w] = Ye + Yo and y[h][N-w] = Ye - Yo with the cosine
+ * / sine halves of the last product as two separate ascending chains. */
 int ee_oracle_hfs(const float *x, float *y, const float *add, int planes, int N, int r, const float *cb,
-                  const float *rb, const float *w, float gamma, int ks1, int ks2)
+                  const float *rb, const float *w, float gamma, int ks1, int ks2, int fold)
 {
     const int NJ = 2 * r - 1, NI = 2 * r + 1;
     const int NJp = (NJ + 3) / 4 * 4, NIp = (NI + 3) / 4 * 4;
@@ -848,7 +853,19 @@ int ee_oracle_hfs(const float *x, float *y, const float *add, int planes, int N,
         float *V = T + (size_t)N * NJp, *D = V + (size_t)N * NJp, *G = D + NIp * NJp;
         const float *X = x + (size_t)p * N * N;
         float *Y = y + (size_t)p * N * N;
-        for (int h = 0; h < N; ++h)
+        const int half = N / 2;
+        for (int h = 0; h < N && fold; ++h) {
+            float xf[1024];
+            for (int q = 0; q < N; ++q) xf[q] = X[h * N + q];
+            for (int q = 1; q < half; ++q) { float u = X[h * N + q], v = X[h * N + N - q]; xf[q] = u + v; xf[N - q] = v - u; }
+            for (int j = 0; j < NJp; ++j) {
+                float acc = 0.0f;
+                if (j < r) { for (int q = 0; q <= half; ++q) acc = fmaf(xf[q], cb[q * NJp + j], acc); }
+                else { for (int q = half; q < N; ++q) acc = fmaf(xf[q], cb[q * NJp + j], acc); }
+                T[h * NJp + j] = acc;
+            }
+        }
+        for (int h = 0; h < N && !fold; ++h)
             for (int j = 0; j < NJp; ++j) {
                 float part[8] = {0.0f};
                 for (int s = 0; s < ks1; ++s) {
@@ -886,7 +903,17 @@ int ee_oracle_hfs(const float *x, float *y, const float *add, int planes, int N,
                 for (int i = 0; i < NI; ++i) acc = fmaf(rb[h * NIp + i], G[i * NJp + j], acc);
                 V[h * NJp + j] = acc;
             }
-        for (int h = 0; h < N; ++h)
+        for (int h = 0; h < N && fold; ++h)
+            for (int q = 0; q <= half; ++q) {
+                float ye = 0.0f, yo = 0.0f;
+                for (int j = 0; j < r; ++j) ye = fmaf(V[h * NJp + j], cb[q * NJp + j], ye);
+                for (int j = r; j < NJp; ++j) yo = fmaf(V[h * NJp + j], cb[q * NJp + j], yo);
+                const size_t o1 = (size_t)h * N + q, o2 = (size_t)h * N + N - q, pb = (size_t)p * N * N;
+                const float y1 = ye + yo, y2 = ye - yo;
+                Y[o1] = add ? y1 + add[pb + o1] : y1;                                   /* y = H x + add */
+                if (q != 0 && q != half) Y[o2] = add ? y2 + add[pb + o2] : y2;
+            }
+        for (int h = 0; h < N && !fold; ++h)
             for (int q = 0; q < N; ++q) {
                 float acc = 0.0f;
                 for (int j = 0; j < NJp; ++j) acc = fmaf(V[h * NJp + j], cb[q * NJp + j], acc);

@@ -95,7 +95,7 @@ def lib():
     L.ee_oracle_add_clamp.restype = None
     L.ee_oracle_avmixup_mix.argtypes = [fp, fp, ctypes.POINTER(ctypes.c_double), fp, i, i64, f]
     L.ee_oracle_avmixup_mix.restype = None
-    L.ee_oracle_hfs.argtypes = [fp, fp, fp, i, i, i, fp, fp, fp, f, i, i]
+    L.ee_oracle_hfs.argtypes = [fp, fp, fp, i, i, i, fp, fp, fp, f, i, i, i]
     L.ee_oracle_hfs.restype = i
     L.ee_oracle_add_square.argtypes = [fp, fp, fp, fp, fp, i, i, i, i, i, f]
     L.ee_oracle_add_square.restype = None
@@ -255,6 +255,8 @@ def hfs_tables(N, r):
         cb[:, k] = np.cos(k * th); cb[:, r - 1 + k] = np.sin(k * th)
     for k in range(1, r + 1):
         rb[:, k] = np.cos(k * th); rb[:, r + k] = np.sin(k * th)
+    if N % 2 == 0:
+        cb[N // 2, r:] = 0.0           # sin(k pi) is exactly 0 (the folded kernel's sine chains start at w = N/2)
     alpha = np.zeros(NIp); beta = np.zeros(NJp)
     alpha[0] = 1.0 / N; alpha[1:r] = 2.0 / N; alpha[r] = 1.0 / N; alpha[r + 1:2 * r] = 2.0 / N; alpha[2 * r] = 1.0 / N
     beta[0] = 1.0 / N; beta[1:NJ] = 2.0 / N
@@ -276,7 +278,10 @@ def hfs(x, r, add=None):
     # 224 px: half-plane blocks, no lane split in stage 1; 288 px: 8-row blocks with the lane split
     rbk = 8 if N >= 256 else 16
     ks1, ks2 = (1, 1) if N <= 128 else ((1 if N == 224 else (8 if (rbk // 4) * (cb.shape[1] // 4) * 8 <= 256 else 4)), 2)
-    _chk(lib().ee_oracle_hfs(_p(x), _p(y), _p(add), x.size // (N * N), N, r, _p(cb), _p(rb), _p(w), gamma, ks1, ks2))
+    # whole-plane kernel (N <= 128): from 64 px it folds the rows of x into even / odd parts (half the multiply-adds of the two
+    # large products)
+    fold = 1 if 64 <= N <= 128 else 0
+    _chk(lib().ee_oracle_hfs(_p(x), _p(y), _p(add), x.size // (N * N), N, r, _p(cb), _p(rb), _p(w), gamma, ks1, ks2, fold))
     return y
 
 
