@@ -429,6 +429,8 @@ class Add_Square(nn.Module):
             raise RuntimeError("edge_b200: Add_Square(channels=%d, size=%d) got input of shape %s"
                                % (self.c, self.h, tuple(x.shape)))
         stripe, table = self.draw(x.shape[0])
-        stripe = stripe.to(x.device, non_blocking=True)
-        table = table.to(x.device, non_blocking=True)
+        # the draws are host tensors (CPU generator, like the reference): stage them in pinned memory so that the two H2D copies
+        # are really asynchronous (a `non_blocking` copy from pageable memory makes the host wait for the copy engine)
+        stripe = stripe.pin_memory().to(x.device, non_blocking=True)
+        table = table.pin_memory().to(x.device, non_blocking=True)
         return F_ee.AddSquareFn.apply(x, stripe, table, float(self.eps))
