@@ -330,6 +330,16 @@ bool canny_stream_ok(const ee::EdgeArgs& a, bool vec_ok, bool nhwc, bool bwd) {
     return bwd && a.W > 128 && 8 * gx >= 7 * lanes && (long long)a.B * a.H >= 64LL * 224;
 }
 
+// CannyFilter_step125_1 backward through the row-streaming kernel (VAR = 0): OPT-IN (staging 8; parity-tested).  Measured
+// on B200 (profiles/r2m_step125_stream.txt, us streaming / chunk-aligned tiles): 512x3x224x224 381 / 325, 128: 125 / 89,
+// 64: 70 / 52 -- without the suppression and hysteresis work the pipeline still costs 381 us, i.e. the per-row cost of the
+// streaming skeleton itself (one CTA barrier, ring rotations and range guards per row), not the Canny stages, is what bounds
+// that kernel family; the halo tiles stay the default for step125.
+bool step125_stream_ok(const ee::EdgeArgs& a, bool vec_ok, bool nhwc) {
+    if (g_staging.load() != 8 || nhwc) return false;
+    return fast_eligible(a, vec_ok) && a.C == 3 && a.has_high && a.W >= 8 && a.W <= 1024 && a.H >= 2 && a.g_x != nullptr;
+}
+
 // Tensor map of x as [B*C, H, W] fp32 with a (64 + 8) x (TH + 8) x 1 box for the TMA-staged tile kernel.  The driver
 // entry point is looked up at run time (no link-time dependency on libcuda).
 int make_x_tensor_map(CUtensorMap* map, const float* x, int B, int C, int H, int W, int box_rows, int plane_w = 64) {
@@ -621,6 +631,7 @@ int ee_shared::bwd_step125(ee::EdgeArgs& a, const EEParams* p, int B, bool blend
         if (blend) return launch_cluster(ee::edge_bwd_step125_cluster<3, true, 4, 224, 28, 8>, 224, 28, 8, B, a, s, "edge_bwd_step125_cluster");
         return launch_cluster(ee::edge_bwd_step125_cluster<3, false, 4, 224, 28, 8>, 224, 28, 8, B, a, s, "edge_bwd_step125_cluster");
     }
+    if (step125_stream_ok(a, vec_ok, nhwc)) return ee_shared::canny_stream(a, p, B, blend, true, s);
     if (fast_eligible(a, vec_ok) && W > 128 && H % 4 == 0 && H >= 16 && g_th_bwd.load() == 0 && g_staging.load() != 3) {
         // wide images: chunk-aligned 56 x 56 tiles, one chunk per thread, no row guards (staging 3 = the older strip path;
         // staging 6 = x tiles staged by TMA tensor copies instead of LDGs, C == 3)
@@ -767,6 +778,10 @@ int ee_shared::canny_stream(ee::EdgeArgs& a, const EEParams* p, int B, bool blen
     const long long grid = (long long)B * sa.bands_per_img;
     if (grid > 0x7fffffffLL) return fail(EE_ERR_TOO_LARGE, "too many bands");
     const bool cn = (p->variant == EE_VARIANT_CANNY);
+    if (p->variant == EE_VARIANT_STEP125) {          // backward only (the forward strips are at the HBM roofline already)
+        if (!bwd) return fail(EE_ERR_UNSUPPORTED, "row-streaming kernel: CannyFilter_step125_1 is wired for the backward only");
+        return blend ? stream_by_width<true, 0, true>(sa, W, (unsigned)grid, threads, smem, s) : stream_by_width<false, 0, true>(sa, W, (unsigned)grid, threads, smem, s);
+    }
     if (bwd) {
         if (blend) return cn ? stream_by_width<true, 1, true>(sa, W, (unsigned)grid, threads, smem, s) : stream_by_width<true, 2, true>(sa, W, (unsigned)grid, threads, smem, s);
         return cn ? stream_by_width<false, 1, true>(sa, W, (unsigned)grid, threads, smem, s) : stream_by_width<false, 2, true>(sa, W, (unsigned)grid, threads, smem, s);

@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(256) edge_fwd_canny_kernel(const EdgeArgs a) {
 // dL/d(thin) from dL/d(edge) for one pixel (see oracle g_thin_of and SURVEY.md A.3); `variant` is passed
 // separately so that specialised kernels can make it a compile-time constant
 __device__ __forceinline__ float g_thin_of_v(int variant, float low, float high, int mode, float ge, float thin, int wih) {
+    if (variant == 0) return ste_sel(ge, thin, high);      // CannyFilter_step125_1: To_compare.backward on the gated magnitude
     if (mode == MODE_RAW) return ge;
     if (variant == 1) {   // CannyFilter: (sign(.)+1)/2 with the BinaryConnect STE window
         if (mode == MODE_LOW) return bcd_sel(0.5f * ge, thin, low);

@@ -30,6 +30,10 @@
 // ahead; consumers read their own 16 bytes per row with one conflict-free LDS.128.  Outputs leave with 128-bit streaming
 // stores (full 4 W-byte rows per channel).
 //
+// VAR = 0 runs CannyFilter_step125_1 (utils/core.py:549-585) through the same pipeline -- no suppression, no hysteresis: the
+// NMS stage degenerates to the threshold of the row's own magnitudes, the hysteresis sums are compiled out -- for the
+// BACKWARD of wide images, where the halo tiles of ee_edge_tiles.cuh reach 0.74 of the HBM peak.
+//
 // Arithmetic: the SAME expression trees as the other kernel families, so results are bit-identical.
 #pragma once
 #include "ee_edge_canny_fast.cuh"
@@ -242,24 +246,44 @@ __global__ void __launch_bounds__(TPB, MINB) edge_canny_stream(const __grid_cons
     //      this step (own values mo, packed directions dir_in; neighbours from the exchange)
     Win w0 = zero_win(), w1 = zero_win();                               // M windows of rows m-2, m-1
     int dir_prev = 0;                                                   // packed direction words of row m-1
+    float m_prev[4] = {0.0f, 0.0f, 0.0f, 0.0f};                         // VAR 0: own magnitudes of row m-1
     auto stage3 = [&](auto steady_tag, const int t, const int prv, const float (&mo)[4], const int dir_in) {
         constexpr bool ST = decltype(steady_tag)::value;
         const int m = s_lo + t - 5;                                     // M row pushed (produced by stage 2 last step)
         if (ST || (m >= m_lo && m <= m_hi)) {
-            Win w = zero_win();
-            if (ST || m < m_hi) {
-                const float* L = exL(PM, prv);
-                w.l = L[GXp - 1]; w.r = L[1];
-                w.m0 = mo[0]; w.m1 = mo[1]; w.m2 = mo[2]; w.m3 = mo[3];
+            if constexpr (VAR == 0) {
+                // CannyFilter_step125_1: edge = To_compare(magm, high) of the pixel itself (core.py:578-583); META carries
+                // the bit (and a NaN flag: To_compare leaves NaN alone) with the same one-row lag as the Canny variants
+                const int n = m - 1;
+                if (ST || (n >= c_lo && n < c_hi)) {
+                    const bool neg_hi = (0.0f > a.e.high);
+                    int meta[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float v = m_prev[k];
+                        const int ihi = (v > a.e.high) || (neg_hi && v <= a.e.high);
+                        meta[k] = ((v != v) ? 1 : 0) | ((2 * ihi) << 4) | (ihi << 6);
+                    }
+                    metarow[(t & 1) * GXp + 1 + tx] = pack4(meta);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) m_prev[k] = (ST || m < m_hi) ? mo[k] : 0.0f;
+            } else {
+                Win w = zero_win();
+                if (ST || m < m_hi) {
+                    const float* L = exL(PM, prv);
+                    w.l = L[GXp - 1]; w.r = L[1];
+                    w.m0 = mo[0]; w.m1 = mo[1]; w.m2 = mo[2]; w.m3 = mo[3];
+                }
+                const int n = m - 1;
+                if (ST || (n >= c_lo && n < c_hi)) {
+                    int meta[4];
+                    stream_nms4<VAR>(a, w0, w1, w, dir_prev, meta);
+                    metarow[(t & 1) * GXp + 1 + tx] = pack4(meta);
+                }
+                w0 = w1; w1 = w;
+                dir_prev = dir_in;
             }
-            const int n = m - 1;
-            if (ST || (n >= c_lo && n < c_hi)) {
-                int meta[4];
-                stream_nms4<VAR>(a, w0, w1, w, dir_prev, meta);
-                metarow[(t & 1) * GXp + 1 + tx] = pack4(meta);
-            }
-            w0 = w1; w1 = w;
-            dir_prev = dir_in;
         }
     };
 
@@ -319,8 +343,8 @@ __global__ void __launch_bounds__(TPB, MINB) edge_canny_stream(const __grid_cons
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
                                     const float mag = magnitude(gx1[k], gy1[k]);
-                                    mm[k] = (VAR == 1 && mag < a.e.alpha) ? 0.0f : mag;
-                                    dw[k] = orient_dir(gx1[k], gy1[k]) + 1;
+                                    mm[k] = (VAR != 2 && mag < a.e.alpha) ? 0.0f : mag;
+                                    dw[k] = (VAR == 0) ? 0 : orient_dir(gx1[k], gy1[k]) + 1;
                                     m_own[k] = mm[k];
                                 }
                                 dir_new = pack4(dw);
@@ -536,8 +560,10 @@ __global__ void __launch_bounds__(TPB, MINB) edge_canny_stream(const __grid_cons
                         if (ST || np < c_hi) {
                             const int* mr = metarow + ((t & 1) ^ 1) * GXp + 1 + tx;
                             cwn = mr[0];
-                            const int lhp = (cwn >> 4) & 0x03030303;
-                            hs = lhp + ((lhp << 8) | ((mr[-1] >> 28) & 3)) + ((lhp >> 8) | (((mr[1] >> 4) & 3) << 24));
+                            if constexpr (VAR != 0) {
+                                const int lhp = (cwn >> 4) & 0x03030303;
+                                hs = lhp + ((lhp << 8) | ((mr[-1] >> 28) & 3)) + ((lhp >> 8) | (((mr[1] >> 4) & 3) << 24));
+                            }
                         }
                         const int q = np - 1;
                         if (ST || (q >= ab_lo && q < ab_hi)) {
@@ -546,14 +572,15 @@ __global__ void __launch_bounds__(TPB, MINB) edge_canny_stream(const __grid_cons
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 meta[k] = (cw1 >> (8 * k)) & 255;
-                                wih[k] = (meta_lh(meta[k]) == 1) && (((nsum >> (8 * k)) & 255) >= 2);
+                                wih[k] = (VAR != 0) && (meta_lh(meta[k]) == 1) && (((nsum >> (8 * k)) & 255) >= 2);
                             }
                             const int pix = q * W + col;
                             const float* slot = ring + (size_t)((t >> 1) % kStreamDepth) * 2 * NROWS * W + (t & 1) * W + col;
                             if constexpr (!BWD) {
                                 float e[4];
 #pragma unroll
-                                for (int k = 0; k < 4; ++k) e[k] = (float)(meta_hi(meta[k]) + wih[k]);
+                                for (int k = 0; k < 4; ++k)
+                                    e[k] = (VAR == 0 && (meta[k] & 1)) ? __int_as_float(0x7fc00000) : (float)(meta_hi(meta[k]) + wih[k]);
                                 if (a.e.edge) __stcs(reinterpret_cast<float4*>(a.e.edge + (size_t)b * hw + pix), make_float4(e[0], e[1], e[2], e[3]));
                                 if constexpr (BLEND) {
                                     const float w0_ = wgt * e[0], w1_ = wgt * e[1], w2_ = wgt * e[2], w3_ = wgt * e[3];
@@ -578,7 +605,8 @@ __global__ void __launch_bounds__(TPB, MINB) edge_canny_stream(const __grid_cons
                                 if constexpr (BLEND) {
                                     float we[4];
 #pragma unroll
-                                    for (int k = 0; k < 4; ++k) we[k] = wgt * (float)(meta_hi(meta[k]) + wih[k]);
+                                    for (int k = 0; k < 4; ++k)
+                                        we[k] = wgt * ((VAR == 0 && (meta[k] & 1)) ? __int_as_float(0x7fc00000) : (float)(meta_hi(meta[k]) + wih[k]));
                                     const bool interior = (q >= r0 && q < r1);
                                     float* gbase_p = a.e.g_base ? a.e.g_base + (size_t)b * NC * hw + pix : nullptr;
 #pragma unroll
