@@ -848,6 +848,7 @@ def run_e2e(args, torch, dist, dev, world, rank, F_ee, p, resident, barrier):
     torch.cuda.empty_cache()
 
     floor = copy_floor(torch, dist, dev, world, barrier, nbytes)
+    floor_again = copy_floor(torch, dist, dev, world, barrier, nbytes)      # the box's contention is erratic for N > 2: show the spread
     ms = min(ms_pipe, ms_chunk)
     res = {"value": world * B * steps / (ms / 1e3), "unit": "images/s",
            "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": steps,
@@ -860,9 +861,12 @@ def run_e2e(args, torch, dist, dev, world, rank, F_ee, p, resident, barrier):
                   "`value`; clean batch H2D from pinned host memory and adversarial batch D2H every step; pipeline = one copy per "
                   "direction per step on dedicated copy streams, triple buffered"}
     try:
-        fl = min(v["ms_per_step"] for k, v in floor.items() if k.startswith("both"))
-        res["copy_floor_ms_per_step"] = fl
-        res["frac_of_copy_floor"] = fl / (ms / steps)
+        both = sorted(v["ms_per_step"] for f in (floor, floor_again) for k, v in f.items() if k.startswith("both"))
+        res["copy_floor_pure_cuda_second_pass"] = {k: v["ms_per_step"] for k, v in floor_again.items()}
+        res["copy_floor_ms_per_step"] = both[0]                    # the best the box did for this traffic (min of 6 probes)
+        res["copy_floor_ms_per_step_median"] = both[len(both) // 2]
+        res["frac_of_copy_floor"] = both[0] / (ms / steps)
+        res["frac_of_copy_floor_median"] = both[len(both) // 2] / (ms / steps)
     except Exception:
         pass
     return res
