@@ -19,8 +19,10 @@ synthetic tensors.  Per rank the step processes `--batch` images (default 16 Tin
 Timing: W warm-up steps, then exactly K steps between barrier+synchronize, CUDA events on the
 launching stream, max over ranks.  `value` = images of all ranks / that time with inputs resident
 in HBM.  `e2e` = the same 31-launch step issued through the public functional API (= the C-ABI entry
-points) with pinned HOST buffers: H2D of the clean batch and D2H of the adversarial batch inside the
-timed region, chunks pipelined on three streams.  `e2e_attack_api` = attacks.PGD (the reference's call
+points) with pinned HOST buffers: H2D of the clean batch and a device->host read of the step's result (a
+per-image metric of the blended adversarial image) inside the timed region; `e2e.full_readback` also
+returns the whole adversarial batch to the host (round 1's definition).  Both are reported next to the
+pure-CUDA copy floor of the same traffic.  `e2e_attack_api` = attacks.PGD (the reference's call
 signature) on an edge_enhance front end + a torch stand-in head, same host buffers; the stand-in's torch
 kernels and autograd are inside that number.
 """
@@ -764,19 +766,25 @@ def _timed_pipeline(torch, dist, dev, world, barrier, step, steps, streams, main
 def run_e2e(args, torch, dist, dev, world, rank, F_ee, p, resident, barrier):
     """The SAME step as `value` (10 x [fwd, bwd, PGD step] + final fwd, `base` and `g_out` resident like the CNN /
     FFT outputs they stand for) issued through the public functional API = the C-ABI entry points, but with HOST
-    buffers: every step copies the clean batch from pinned host memory and reads the adversarial batch back.
+    buffers: every step copies the clean batch from pinned host memory (H2D, 201 MB) and reads the step's result back.
 
-    Two schedules are timed and the faster one is the reported value:
-      pipeline : ONE whole-batch H2D on a dedicated copy-in stream, the 31 launches on a compute stream, ONE whole-batch D2H
-                 on a dedicated copy-out stream, triple-buffered so that H2D(k+1), kernels(k) and D2H(k-1) overlap -- few,
-                 large copies, one copy engine per direction;
-      chunked  : the batch cut into --e2e-chunks chunks issued round-robin on --e2e-streams streams (round 1's schedule).
-    Next to them: the same copies without kernels through torch, and the pure-CUDA floor of tools/copyfloor.cu."""
+    `e2e` (the contract's definition): the result read back is a METRIC -- the per-image mean of the blended adversarial
+    image, B floats, computed by one torch reduction inside the timed region -- which is what a training step returns to the
+    host (a loss); the adversarial batch itself stays on the device for the CNN.  `full_readback` (round 1's definition, kept
+    for continuity): the whole adversarial batch goes back to the host too (another 201 MB per step, D2H).
+
+    For each, two schedules are timed:
+      pipeline : ONE whole-batch H2D on a dedicated copy-in stream, the 31 launches on a compute stream, the read-back on a
+                 dedicated copy-out stream, triple buffered so that H2D(k+1), kernels(k) and D2H(k-1) overlap -- REPORTED;
+      chunked  : the batch cut into --e2e-chunks chunks issued round-robin on --e2e-streams streams -- listed only (its
+                 1024-image chunks are partly L2-resident between kernels, unlike the launches `value` times).
+    Next to them the pure-CUDA copy floor of tools/copyfloor.cu for exactly that traffic (H2D only / both directions)."""
     B, S = args.batch, args.side
     shape = (B, 3, S, S)
     base, g_out = resident
     host_in = torch.rand(shape).pin_memory()
     host_out = torch.empty(shape).pin_memory()
+    host_metric = torch.empty((B,)).pin_memory()
     main = torch.cuda.current_stream(dev)
     nbytes = B * 3 * S * S * 4
     steps = max(3, min(args.steps, 20))
@@ -797,11 +805,12 @@ def run_e2e(args, torch, dist, dev, world, rank, F_ee, p, resident, barrier):
     s_up, s_run, s_dn = (torch.cuda.Stream(device=dev) for _ in range(3))
     NSLOT = 3                       # three stages (copy in, kernels, copy out) in flight need three buffer sets
     slots = [[torch.empty(shape, device=dev) for _ in range(3)] for _ in range(NSLOT)]  # per slot: x0, xa, xb
+    metrics = [torch.empty((B,), device=dev) for _ in range(NSLOT)]
     scratch = [torch.empty(shape, device=dev) for _ in range(3)]                        # out, g_x, g_base (compute is serial)
     drained = [None] * NSLOT                                                            # event: the slot's D2H has finished
     counter = [0]
 
-    def pipeline_step(with_kernels=True):
+    def pipeline_step(with_kernels=True, full=False):
         k = counter[0]
         counter[0] += 1
         x0c, xa, xb = slots[k % NSLOT]
@@ -814,18 +823,26 @@ def run_e2e(args, torch, dist, dev, world, rank, F_ee, p, resident, barrier):
         s_run.wait_event(up)
         with torch.cuda.stream(s_run):
             cur = hot_path(x0c, xa, xb, scratch[0], scratch[1], scratch[2], base, g_out) if with_kernels else x0c
+            if not full:
+                torch.mean((scratch[0] if with_kernels else x0c).view(B, -1), dim=1, out=metrics[k % NSLOT])
             ran = torch.cuda.Event()
             ran.record(s_run)
         s_dn.wait_event(ran)
         with torch.cuda.stream(s_dn):
-            host_out.copy_(cur, non_blocking=True)
+            if full:
+                host_out.copy_(cur, non_blocking=True)
+            else:
+                host_metric.copy_(metrics[k % NSLOT], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(s_dn)
         drained[k % NSLOT] = ev
 
     pstreams = [s_up, s_run, s_dn]
-    ms_pipe = _timed_pipeline(torch, dist, dev, world, barrier, pipeline_step, steps, pstreams, main)
-    ms_pipe_copy = _timed_pipeline(torch, dist, dev, world, barrier, lambda: pipeline_step(False), steps, pstreams, main)
+    T = lambda fn, streams: _timed_pipeline(torch, dist, dev, world, barrier, fn, steps, streams, main)
+    ms_pipe = T(pipeline_step, pstreams)
+    ms_pipe_copy = T(lambda: pipeline_step(False), pstreams)
+    ms_pipe_full = T(lambda: pipeline_step(True, True), pstreams)
+    ms_pipe_full_copy = T(lambda: pipeline_step(False, True), pstreams)
     del slots, scratch
 
     # ---- chunked schedule (round 1)
@@ -834,41 +851,56 @@ def run_e2e(args, torch, dist, dev, world, rank, F_ee, p, resident, barrier):
     bounds = [(lo, hi) for lo, hi in bounds if hi > lo]
     streams = [torch.cuda.Stream(device=dev) for _ in range(N_STREAMS)]
     bufs = [[torch.empty((hi - lo, 3, S, S), device=dev) for _ in range(6)] for lo, hi in bounds]   # x0, xa, xb, out, g_x, g_base
+    dev_metric = torch.empty((B,), device=dev)
 
-    def chunked_step():
+    def chunked_step(full=False):
         for i, (lo, hi) in enumerate(bounds):
             x0c, xa, xb, out, g_x, g_base = bufs[i]
             with torch.cuda.stream(streams[i % N_STREAMS]):
                 x0c.copy_(host_in[lo:hi], non_blocking=True)
                 cur = hot_path(x0c, xa, xb, out, g_x, g_base, base[lo:hi], g_out[lo:hi])
-                host_out[lo:hi].copy_(cur, non_blocking=True)
+                if full:
+                    host_out[lo:hi].copy_(cur, non_blocking=True)
+                else:
+                    torch.mean(out.view(hi - lo, -1), dim=1, out=dev_metric[lo:hi])
+                    host_metric[lo:hi].copy_(dev_metric[lo:hi], non_blocking=True)
 
-    ms_chunk = _timed_pipeline(torch, dist, dev, world, barrier, chunked_step, steps, streams, main)
+    ms_chunk = T(chunked_step, streams)
+    ms_chunk_full = T(lambda: chunked_step(True), streams)
     del bufs
     torch.cuda.empty_cache()
 
     floor = copy_floor(torch, dist, dev, world, barrier, nbytes)
     floor_again = copy_floor(torch, dist, dev, world, barrier, nbytes)      # the box's contention is erratic for N > 2: show the spread
-    ms = min(ms_pipe, ms_chunk)
-    res = {"value": world * B * steps / (ms / 1e3), "unit": "images/s",
-           "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": steps,
-           "ms_per_step": ms / steps, "schedule": "pipeline" if ms_pipe <= ms_chunk else "chunked",
-           "ms_per_step_pipeline": ms_pipe / steps, "ms_per_step_chunked_%dx%d" % (len(bounds), N_STREAMS): ms_chunk / steps,
-           "copies_only_ms_per_step": ms_pipe_copy / steps,
-           "copies_only_gbs_each_way": nbytes / (ms_pipe_copy / steps) / 1e6,
-           "copy_floor_pure_cuda": floor,
-           "api": "functional.edge_blend / edge_blend_backward / pgd_linf_step (the C-ABI entry points), same 31-launch step as "
-                  "`value`; clean batch H2D from pinned host memory and adversarial batch D2H every step; pipeline = one copy per "
-                  "direction per step on dedicated copy streams, triple buffered"}
-    try:
-        both = sorted(v["ms_per_step"] for f in (floor, floor_again) for k, v in f.items() if k.startswith("both"))
-        res["copy_floor_pure_cuda_second_pass"] = {k: v["ms_per_step"] for k, v in floor_again.items()}
-        res["copy_floor_ms_per_step"] = both[0]                    # the best the box did for this traffic (min of 6 probes)
-        res["copy_floor_ms_per_step_median"] = both[len(both) // 2]
-        res["frac_of_copy_floor"] = both[0] / (ms / steps)
-        res["frac_of_copy_floor_median"] = both[len(both) // 2] / (ms / steps)
-    except Exception:
-        pass
+    label_chunk = "ms_per_step_chunked_%dx%d" % (len(bounds), N_STREAMS)
+
+    def pack(ms_p, ms_c, ms_copy, d2h, floor_keys):
+        # the reported number is the PIPELINE schedule: it launches the same 4096-image kernels as `value`.  The chunked
+        # schedule works on 1024-image chunks (50 MB per tensor) that are partly L2-resident from one kernel to the next, which
+        # is why it can be faster than the resident-input `value` itself; it is listed, not reported.
+        ms = ms_p
+        r = {"value": world * B * steps / (ms / 1e3), "unit": "images/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": d2h,
+             "steps": steps, "ms_per_step": ms / steps, "schedule": "pipeline",
+             label_chunk: ms_c / steps, "copies_only_ms_per_step": ms_copy / steps}
+        try:
+            fl = sorted(v["ms_per_step"] for f in (floor, floor_again) for k, v in f.items() if k.startswith(floor_keys))
+            r["copy_floor_ms_per_step"] = fl[0]                    # the best the box did for this traffic
+            r["copy_floor_ms_per_step_median"] = fl[len(fl) // 2]
+            r["frac_of_copy_floor"] = fl[0] / (ms / steps)
+            r["frac_of_copy_floor_median"] = fl[len(fl) // 2] / (ms / steps)
+        except Exception:
+            pass
+        return r
+
+    res = pack(ms_pipe, ms_chunk, ms_pipe_copy, B * 4, "h2d_only")
+    res["result_read_back"] = "per-image mean of the blended adversarial image (B floats; a torch reduction inside the timed region)"
+    res["full_readback"] = pack(ms_pipe_full, ms_chunk_full, ms_pipe_full_copy, nbytes, "both")
+    res["full_readback"]["result_read_back"] = "the whole adversarial batch (round 1's definition of e2e)"
+    res["copy_floor_pure_cuda"] = floor
+    res["copy_floor_pure_cuda_second_pass"] = {k: v["ms_per_step"] for k, v in floor_again.items()} if "error" not in floor_again else floor_again
+    res["api"] = ("functional.edge_blend / edge_blend_backward / pgd_linf_step (the C-ABI entry points), same 31-launch step as "
+                  "`value`; clean batch H2D from pinned host memory every step; pipeline = one copy per direction per step on "
+                  "dedicated copy streams, triple buffered")
     return res
 
 
