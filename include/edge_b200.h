@@ -108,7 +108,8 @@ int ee_edge_blend_bwd_f32(const float* g_out, const float* x, const float* base,
  * copies): the edge map goes through a ZERO-padded 3 x 3 Gaussian (get_gaussian_kernel(3, 0, 1)) before the blend,
  *     out = clamp(base + w * conv2d(edge, gauss, padding=1), 0, 1).
  * No reference config enables it, so it is not fused into the filter kernels: the caller runs ee_edge_fwd_f32 first and
- * ee_edge_bwd_f32 last.  fwd reads edge[B,1,H,W] and base, writes out.  bwd reads g_out, edge, base and writes
+ * ee_edge_bwd_f32 last.  `gauss` is a HOST pointer to the nine taps (they travel in kernel-parameter space like
+ * EEParams.gauss); every other pointer is a device pointer.  fwd reads edge[B,1,H,W] and base, writes out.  bwd reads g_out, edge, base and writes
  * g_edge[B,1,H,W] = conv2d^T(w * sum_c g_pre_c) (may be NULL) and g_base = g_pre = g_out * [0 <= pre <= 1] (may be NULL). */
 int ee_gf_blend_fwd_f32(const float* edge, const float* base, float* out, int B, int C, int H, int W,
                         const float gauss[9], float w, void* stream);
