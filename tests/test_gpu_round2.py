@@ -385,3 +385,43 @@ def test_strided_autograd_and_unsupported_strides():
     edge = torch.empty((2, 1, 64, 64), device=DEV)
     rc = L.ee_edge_fwd_strided_f32(xt.data_ptr(), ctypes.byref(s), edge.data_ptr(), None, 2, 3, 64, 64, ctypes.byref(p), None)
     assert rc == -2 and b"column stride" in L.ee_last_error()
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases of the round-2 entry points: empty batches, degenerate shapes, loud errors
+# ---------------------------------------------------------------------------------------------
+def test_round2_entry_points_edge_cases():
+    p = F_ee.make_params("step125", GAUSS, 0.0, None, T.HIGH, False)
+    empty = torch.empty((0, 3, 8, 8), device=DEV)
+    assert F_ee.pgd_l2_step(empty, empty, empty, 0.1, 0.1).shape == (0, 3, 8, 8)
+    assert F_ee.gf_blend(torch.empty((0, 1, 8, 8), device=DEV), empty, GAUSS, 1.0).shape == (0, 3, 8, 8)
+    out, g_x, g_base, x_next = F_ee.pgd_iteration(empty, empty, empty, empty, p, 1.0, 0.01, 0.1)
+    assert x_next.shape == (0, 3, 8, 8)
+    # degenerate planes through the gf kernels (1 x 1, one row, one column)
+    r = T.rng(5)
+    for shape in ((1, 1, 1, 1), (2, 3, 1, 8), (2, 2, 9, 1)):
+        B, C, H, W = shape
+        edge = (r.random((B, 1, H, W)) > 0.5).astype(np.float32)
+        base = r.random(shape, dtype=np.float32)
+        g = r.standard_normal(shape, dtype=np.float32)
+        assert same(F_ee.gf_blend(cu(edge), cu(base), GAUSS, 1.0), O.gf_blend_fwd(edge, base, 1.0))
+        ge, gb = F_ee.gf_blend_backward(cu(g), cu(edge), cu(base), GAUSS, 1.0)
+        oge, ogb = O.gf_blend_bwd(g, edge, base, 1.0)
+        assert same(ge, oge) and same(gb, ogb)
+    # one-pass PGD-L2 on a single sample and on a sample of 4 elements
+    for shape in ((1, 3, 64, 64), (3, 4), (1, 3, 224, 224)):
+        x, g, x0 = T.make_attack_inputs(2, shape, 0.05)
+        assert same(F_ee.pgd_l2_step(cu(x), cu(g), cu(x0), 0.5, 0.01), O.pgd_l2_step(x, g, x0, 0.5, 0.01))
+    # loud errors
+    x = torch.rand((2, 3, 8, 8), device=DEV)
+    with pytest.raises(RuntimeError):
+        F_ee.pgd_l2_step(x.cpu(), x.cpu(), x.cpu(), 0.1, 0.1)
+    with pytest.raises(ValueError):
+        F_ee.gf_blend(torch.rand((2, 1, 8, 9), device=DEV), x, GAUSS, 1.0)
+    bad = GAUSS.copy(); bad[0, 0] += 1
+    with pytest.raises(RuntimeError):
+        F_ee.gf_blend(torch.rand((2, 1, 8, 8), device=DEV), x, bad, 1.0)
+    q = F_ee.make_params("step125", GAUSS, 0.0, None, T.HIGH, False)
+    q.flags = 4
+    with pytest.raises(RuntimeError):
+        F_ee.edge_map(x, q)
