@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(256, 1) hfs_rows_kernel(const HfsArgs a) {
     using D_ = HfsDims<N, R>;
     using Q_ = HfsRowsDims<N, R>;
     constexpr int NJp = D_::NJp, NIp = D_::NIp, NI = D_::NI, NJ = D_::NJ, XS = D_::XS, JS = D_::JS, IS = D_::IS;
-    constexpr int RBK = Q_::RBK, KS1 = Q_::KS1, KS2 = Q_::KS2, NBUF = Q_::NBUF, N4 = N / 4, NBLK = N / RBK;
+    constexpr int RBK = Q_::RBK, KS1 = Q_::KS1, KS2 = Q_::KS2, NBUF = Q_::NBUF, N4 = N / 4, NBLK = N / RBK, HALFN = N / 2;
     static_assert(N % RBK == 0 && N % (4 * KS1) == 0 && N % KS2 == 0, "row blocks and K splits divide the plane");
     static_assert((RBK / 4) * (NJp / 4) * KS1 <= 256, "stage 1 fits one pass of the CTA");
     static_assert(NBUF == 1 || NBLK % 2 == 0, "double buffering: the next plane's first block lands in buffer 0");
@@ -514,21 +514,41 @@ __global__ void __launch_bounds__(256, 1) hfs_rows_kernel(const HfsArgs a) {
             }
             const float* X = XB + (NBUF == 2 ? (blk & 1) : 0) * RBK * XS;
             if constexpr (KS1 == 1) {
-                // one 4 x 4 tile per thread over the whole K range, exactly the whole-plane kernel's stage 1
-                for (int t = tid; t < (RBK / 4) * (NJp / 4); t += 256) {
-                    const int hg = t % (RBK / 4), jg = t / (RBK / 4);
+                // Even / odd folding as in hfs_kernel: fold every row of the block in place (x[w] + x[N-w] for w < N/2,
+                // x[w] - x[N-w] for w > N/2), then one 4 x 4 tile per thread over HALF the K range -- w = 0..N/2 for a tile
+                // of cosine columns, w = N/2..N-1 for sine columns (table entry exactly 0 at N/2)
+                {
+                    constexpr int HP = 128;                                  // N/2 = 112 rounded up to a power of two
+                    static_assert(HALFN <= HP && R % 4 == 0 && HALFN % 4 == 0, "fold indexing");
+                    float* Xw = XB;
+                    for (int e = tid; e < RBK * HP; e += 256) {
+                        const int h = e >> 7, w = e & (HP - 1);
+                        if (w >= 1 && w < HALFN) {
+                            float* row = Xw + h * XS;
+                            const float u = row[w], v = row[N - w];
+                            row[w] = u + v;
+                            row[N - w] = v - u;
+                        }
+                    }
+                }
+                __syncthreads();
+                auto tile1 = [&](auto cos_tag, const int hg, const int jg) {
+                    constexpr bool COS = decltype(cos_tag)::value;
+                    constexpr int W_LO = COS ? 0 : HALFN, W_HI = COS ? HALFN + 1 : N, V_HI = W_HI & ~3;
+                    const float* xr = X + hg * XS;
+                    const float* cr = CB + 4 * jg;
                     float acc[4][4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
                         for (int c = 0; c < 4; ++c) acc[i][c] = 0.0f;
 #pragma unroll 4
-                    for (int w4 = 0; w4 < N4; ++w4) {
+                    for (int w = W_LO; w < V_HI; w += 4) {
                         float4 xv[4], cv[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(X + (hg + (RBK / 4) * i) * XS + 4 * w4);
+                        for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(xr + (RBK / 4) * i * XS + w);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) cv[q] = *reinterpret_cast<const float4*>(CB + (4 * w4 + q) * JS + 4 * jg);
+                        for (int q = 0; q < 4; ++q) cv[q] = *reinterpret_cast<const float4*>(cr + (w + q) * JS);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const float xs[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
@@ -542,9 +562,25 @@ __global__ void __launch_bounds__(256, 1) hfs_rows_kernel(const HfsArgs a) {
                         }
                     }
 #pragma unroll
+                    for (int w = V_HI; w < W_HI; ++w) {                  // the cosine tiles' last term, w = N/2
+                        const float4 cv = *reinterpret_cast<const float4*>(cr + w * JS);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float xs = xr[(RBK / 4) * i * XS + w];
+                            acc[i][0] = fmaf(xs, cv.x, acc[i][0]);
+                            acc[i][1] = fmaf(xs, cv.y, acc[i][1]);
+                            acc[i][2] = fmaf(xs, cv.z, acc[i][2]);
+                            acc[i][3] = fmaf(xs, cv.w, acc[i][3]);
+                        }
+                    }
+#pragma unroll
                     for (int i = 0; i < 4; ++i)
                         *reinterpret_cast<float4*>(T + (blk * RBK + hg + (RBK / 4) * i) * JS + 4 * jg) =
                             make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+                };
+                for (int t = tid; t < (RBK / 4) * (NJp / 4); t += 256) {
+                    const int hg = t % (RBK / 4), jg = t / (RBK / 4);
+                    if (4 * jg < R) tile1(std::true_type{}, hg, jg); else tile1(std::false_type{}, hg, jg);
                 }
                 __syncthreads();               // every thread is done with the single buffer: refill it
                 if (blk + 1 < NBLK) load_block_async(plane, blk + 1, 0);
@@ -677,8 +713,65 @@ __global__ void __launch_bounds__(256, 1) hfs_rows_kernel(const HfsArgs a) {
         }
         __syncthreads();
 
-        // ---- stage 5: y = V CB^T, tiles of rows {hg + N4*i} x columns {wg + N4*c} ------------------------------------
-        {
+        // ---- stage 5: y = V CB^T, tiles of rows {hg + N4*i} x columns {wg + N4*c}; with the folded kernel (KS1 == 1) a
+        //      tile covers columns of the half plane w < N/2 with an even and an odd accumulator: y[w] = Ye + Yo, y[N-w] = Ye - Yo
+        if constexpr (KS1 == 1) {
+            float* py = a.y + (size_t)plane * N * N;
+            const float* pa = a.add ? a.add + (size_t)plane * N * N : nullptr;
+            constexpr int WS = HALFN / 4;
+            for (int t = tid; t < N4 * WS; t += 256) {
+                const int wg = t % WS, hg = t / WS;
+                float ae[4][4], ao[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) { ae[i][c] = 0.0f; ao[i][c] = 0.0f; }
+#pragma unroll
+                for (int q = 0; q < NJp / 4; ++q) {
+                    float4 vv[4], cv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) vv[i] = *reinterpret_cast<const float4*>(V + (hg + N4 * i) * JS + 4 * q);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) cv[c] = *reinterpret_cast<const float4*>(CB + (wg + WS * c) * JS + 4 * q);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            float sacc = (4 * q < R) ? ae[i][c] : ao[i][c];
+                            sacc = fmaf(vv[i].x, cv[c].x, sacc);
+                            sacc = fmaf(vv[i].y, cv[c].y, sacc);
+                            sacc = fmaf(vv[i].z, cv[c].z, sacc);
+                            sacc = fmaf(vv[i].w, cv[c].w, sacc);
+                            if (4 * q < R) ae[i][c] = sacc; else ao[i][c] = sacc;
+                        }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int w = wg + WS * c;
+                        const int o1 = (hg + N4 * i) * N + w;
+                        const float y1 = ae[i][c] + ao[i][c];
+                        __stcs(py + o1, pa ? y1 + __ldcs(pa + o1) : y1);
+                        if (w != 0) {
+                            const int o2 = (hg + N4 * i) * N + N - w;
+                            const float y2 = ae[i][c] - ao[i][c];
+                            __stcs(py + o2, pa ? y2 + __ldcs(pa + o2) : y2);
+                        }
+                    }
+            }
+            for (int h = tid; h < N; h += 256) {                      // the self-mirrored column w = N/2
+                float se = 0.0f, so = 0.0f;
+#pragma unroll
+                for (int j = 0; j < NJp; ++j) {
+                    const float p_ = V[h * JS + j], c_ = CB[HALFN * JS + j];
+                    if (j < R) se = fmaf(p_, c_, se); else so = fmaf(p_, c_, so);
+                }
+                const int o = h * N + HALFN;
+                const float y1 = se + so;
+                __stcs(py + o, pa ? y1 + __ldcs(pa + o) : y1);
+            }
+        } else {
             float* py = a.y + (size_t)plane * N * N;
             const float* pa = a.add ? a.add + (size_t)plane * N * N : nullptr;
             for (int t = tid; t < N4 * N4; t += 256) {

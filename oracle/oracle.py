@@ -280,7 +280,7 @@ def hfs(x, r, add=None):
     ks1, ks2 = (1, 1) if N <= 128 else ((1 if N == 224 else (8 if (rbk // 4) * (cb.shape[1] // 4) * 8 <= 256 else 4)), 2)
     # whole-plane kernel (N <= 128): from 64 px it folds the rows of x into even / odd parts (half the multiply-adds of the two
     # large products)
-    fold = 1 if 64 <= N <= 128 else 0
+    fold = 1 if N in (64, 128, 224) else 0          # 224 px: the half-plane row-blocked kernel folds too (288 px does not)
     _chk(lib().ee_oracle_hfs(_p(x), _p(y), _p(add), x.size // (N * N), N, r, _p(cb), _p(rb), _p(w), gamma, ks1, ks2, fold))
     return y
 
