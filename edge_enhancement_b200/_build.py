@@ -12,7 +12,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libedge_b200.so")
 SOURCES = ["ee_capi.cu"]
-HEADERS = ["ee_device.cuh", "ee_edge_step125.cuh", "ee_edge_canny.cuh", "ee_edge_fast.cuh", "ee_edge_canny_fast.cuh", "ee_attack.cuh", "ee_square.cuh", "ee_hfs.cuh", "ee_edge_cluster.cuh", "ee_edge_tiles.cuh", "ee_edge_canny_tiles.cuh", "ee_edge_stream.cuh", "ee_gf.cuh", "ee_pgd_l2.cuh",
+HEADERS = ["ee_device.cuh", "ee_edge_step125.cuh", "ee_edge_canny.cuh", "ee_edge_fast.cuh", "ee_edge_canny_fast.cuh", "ee_attack.cuh", "ee_square.cuh", "ee_hfs.cuh", "ee_edge_cluster.cuh", "ee_edge_tiles.cuh", "ee_edge_canny_tiles.cuh", "ee_edge_stream.cuh", "ee_gf.cuh", "ee_pgd_l2.cuh", "ee_hfs_tc.cuh",
            os.path.join("..", "..", "include", "edge_b200.h")]
 
 NVCC_FLAGS = [

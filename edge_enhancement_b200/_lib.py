@@ -63,6 +63,8 @@ SIGNATURES = {
     "ee_add_square_bwd_f32": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp],
     "ee_hfs_f32": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _f, _vp],
     "ee_hfs_supported": [_i, _i],
+    "ee_hfs_tc_f32": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _f, _vp],
+    "ee_hfs_tc_supported": [_i, _i],
     "ee_last_error": [],
     "ee_version": [],
     "ee_set_tuning": [_i, _i, _i],

@@ -12,6 +12,7 @@
 #include "ee_edge_step125.cuh"
 #include "ee_square.cuh"
 #include "ee_hfs.cuh"
+#include "ee_hfs_tc.cuh"
 #include "ee_gf.cuh"
 #include "ee_pgd_l2.cuh"
 
@@ -929,6 +930,19 @@ static int launch_hfs(const ee::HfsArgs& a, cudaStream_t s) {
     return EE_OK;
 }
 
+// 64 px / r 8 on the tensor cores (ee_hfs_tc.cuh): persistent CTAs over pairs of planes, two per SM
+static int launch_hfs_tc64(const ee::HfsArgs& a, cudaStream_t s) {
+    auto kernel = ee::hfs_tc::hfs_tc64_kernel;
+    if (int rc = ensure_smem(kernel, ee::hfs_tc::kSmem)) return rc;
+    const int pairs = (a.planes + 1) / 2;
+    int grid = 2 * sm_count();
+    if (grid > pairs) grid = pairs;
+    kernel<<<(unsigned)grid, ee::hfs_tc::kThreads, ee::hfs_tc::kSmem, s>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "ee_hfs_f32");
+    return EE_OK;
+}
+
 template <int N, int R>
 static int launch_hfs_rows(const ee::HfsArgs& a, cudaStream_t s) {
     const size_t smem = (size_t)ee::HfsRowsDims<N, R>::kFloats * sizeof(float);
@@ -1173,6 +1187,22 @@ int ee_hfs_f32(const float* x, float* y, const float* add_or_null, int planes, i
     if (N == 128 && r == 12) return launch_hfs<128, 12, 2>(a, s);          // 2 whole planes per CTA still fit (208 KB)
     if (N == 288 && r == 18) return launch_hfs_rows<288, 18>(a, s);
     return fail(EE_ERR_UNSUPPORTED, "ee_hfs_f32: no kernel for a %d x %d plane with radius %d (ee_hfs_supported)", N, N, r);
+}
+
+int ee_hfs_tc_supported(int N, int r) { return N == 64 && r == 8; }
+int ee_hfs_tc_f32(const float* x, float* y, const float* add_or_null, int planes, int N, int r, const float* cb, const float* rb,
+                  const float* w, float gamma, void* stream) {
+    if (planes < 0) return fail(EE_ERR_INVALID_ARG, "ee_hfs_tc_f32: negative plane count");
+    if (!ee_hfs_tc_supported(N, r))
+        return fail(EE_ERR_UNSUPPORTED, "ee_hfs_tc_f32: the tensor-core kernel exists for 64 x 64 planes with radius 8 only (got %d / %d)", N, r);
+    if (planes == 0) return EE_OK;
+    if (!x || !y || !cb || !rb || !w) return fail(EE_ERR_INVALID_ARG, "ee_hfs_tc_f32: null pointer");
+    if (x == y) return fail(EE_ERR_INVALID_ARG, "ee_hfs_tc_f32: y must not alias x");
+    if (!aligned16(x) || !aligned16(y) || !aligned16(add_or_null) || !aligned16(cb) || !aligned16(rb) || !aligned16(w))
+        return fail(EE_ERR_INVALID_ARG, "ee_hfs_tc_f32: pointers must be 16-byte aligned");
+    ee::HfsArgs a;
+    a.x = x; a.y = y; a.add = add_or_null; a.cb = cb; a.rb = rb; a.w = w; a.gamma = gamma; a.planes = planes;
+    return launch_hfs_tc64(a, (cudaStream_t)stream);
 }
 
 const char* ee_last_error(void) { return g_err; }

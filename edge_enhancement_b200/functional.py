@@ -464,13 +464,17 @@ def hfs_tables(N, r, device):
     return t
 
 
-def hfs_supported(N, r):
-    return bool(_lib.load().ee_hfs_supported(int(N), int(r)))
+def hfs_supported(N, r, impl='native'):
+    L = _lib.load()
+    return bool((L.ee_hfs_tc_supported if impl == 'tcgen05' else L.ee_hfs_supported)(int(N), int(r)))
 
 
-def hfs(x, r, out=None, add=None):
+def hfs(x, r, out=None, add=None, impl='native'):
     """y = HighFreqSuppress(N, N, r)(x) [+ add] for [..., N, N] planes -- ee_hfs_f32 (one kernel; self-adjoint, so the same
-    call on the upstream gradient is the backward; `add` lets it accumulate into another gradient, and may be `out`)."""
+    call on the upstream gradient is the backward; `add` lets it accumulate into another gradient, and may be `out`).
+    impl='tcgen05' selects ee_hfs_tc_f32, the tensor-core variant (64 x 64 / r 8 only; 3 x TF32, not bit-identical)."""
+    if impl not in ('native', 'tcgen05'):
+        raise ValueError("edge_b200: hfs impl must be 'native' or 'tcgen05'")
     x = _chk(x, "x")
     if add is not None:
         add = _chk(add, "add", x.shape)
@@ -481,9 +485,9 @@ def hfs(x, r, out=None, add=None):
     if x.numel():
         cb, rb, w, gamma = hfs_tables(N, r, x.device)
         with _on_device(x):
-            rc = _lib.load().ee_hfs_f32(_ptr(x), _ptr(out), _ptr(add), x.numel() // (N * N), N, int(r), _ptr(cb), _ptr(rb),
-                                        _ptr(w), gamma, _stream(x))
-        _lib.check(rc, "ee_hfs_f32")
+            fn = _lib.load().ee_hfs_tc_f32 if impl == 'tcgen05' else _lib.load().ee_hfs_f32
+            rc = fn(_ptr(x), _ptr(out), _ptr(add), x.numel() // (N * N), N, int(r), _ptr(cb), _ptr(rb), _ptr(w), gamma, _stream(x))
+        _lib.check(rc, "ee_hfs_tc_f32" if impl == 'tcgen05' else "ee_hfs_f32")
     return out
 
 
@@ -602,13 +606,13 @@ class HfsFn(torch.autograd.Function):
     """x_hfs = HighFreqSuppress(x); the operator is symmetric, so the backward applies it to the upstream gradient."""
 
     @staticmethod
-    def forward(ctx, x, r):
-        ctx.r = r
-        return hfs(x, r)
+    def forward(ctx, x, r, impl='native'):
+        ctx.r, ctx.impl = r, impl
+        return hfs(x, r, impl=impl)
 
     @staticmethod
     def backward(ctx, g):
-        return hfs(g, ctx.r), None
+        return hfs(g, ctx.r, impl=ctx.impl), None, None
 
 
 class EdgeEnhanceFrontFn(torch.autograd.Function):

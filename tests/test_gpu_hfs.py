@@ -112,3 +112,62 @@ def test_persistent_loop_many_planes(B, N, r):
         xs = x[lo:lo + 3].cpu().numpy()
         assert np.array_equal(y[lo:lo + 3].cpu().numpy(), O.hfs(xs, r)), lo
     assert torch.equal(F_ee.hfs(x, r), y)
+
+
+# ---- the tensor-core variant (ee_hfs_tc_f32: tcgen05.mma kind::tf32, 3 x TF32 split) -------------------------------------------
+# Floating point on an unspecified accumulation order: NOT bit-identical to the oracle.  Tolerance 4e-6 * max|y| against the
+# oracle (measured 1.5e-6 .. 1.7e-6 on [0,1] inputs at 4096x3x64x64; the oracle itself is 0.6e-6 from float64).
+TC_TOL = 4e-6
+
+
+@pytest.mark.parametrize("planes", [1, 2, 3, 5, 64, 593, 12288])
+@pytest.mark.parametrize("kind", ["uniform", "normal"])
+def test_tensor_core_kernel_matches_oracle_within_tolerance(planes, kind):
+    rng = np.random.default_rng(planes)
+    x = (rng.random((planes, 64, 64)) if kind == "uniform" else rng.standard_normal((planes, 64, 64))).astype(np.float32)
+    x[0, :3] = 0.0
+    assert F_ee.hfs_supported(64, 8, 'tcgen05')
+    xd = cu(x)
+    got = F_ee.hfs(xd, 8, impl='tcgen05')
+    ref = F_ee.hfs(xd, 8)                               # == oracle bit for bit (test above); the oracle itself for small counts
+    if planes <= 64:
+        assert np.array_equal(ref.cpu().numpy(), O.hfs(x, 8))
+    err = float((got - ref).abs().max())
+    assert err <= TC_TOL * float(ref.abs().max()), err
+    assert not bool(torch.isnan(got).any())
+
+
+def test_tensor_core_kernel_accumulate_mode_and_float64_error():
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    x = torch.rand((1000, 64, 64), device=DEV, generator=gen)
+    add = torch.randn((1000, 64, 64), device=DEV, generator=gen)
+    m = core.HighFreqSuppress(64, 64, 8, impl='torch_fft')
+    exact = m._fft_forward(x.double())
+    got = F_ee.hfs(x, 8, impl='tcgen05')
+    e_tc = float((got.double() - exact).abs().max())
+    e_ffma = float((F_ee.hfs(x, 8).double() - exact).abs().max())
+    print("max abs error against float64: tcgen05 %.3e, FFMA %.3e" % (e_tc, e_ffma))
+    assert e_tc <= 3e-6 and e_ffma <= 1.5e-6
+    out = add.clone()
+    F_ee.hfs(x, 8, out=out, add=out, impl='tcgen05')    # y = H x + add, in place
+    assert float((out - (got + add)).abs().max()) <= 1e-6
+    assert F_ee.hfs(x[:0], 8, impl='tcgen05').shape == (0, 64, 64)
+
+
+def test_tensor_core_module_autograd_and_unsupported_shapes():
+    m = core.HighFreqSuppress(64, 64, 8, impl='tcgen05')
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    x = torch.rand((7, 3, 64, 64), device=DEV, generator=gen, requires_grad=True)
+    g = torch.randn((7, 3, 64, 64), device=DEV, generator=gen)
+    y = m(x)
+    y.backward(g)
+    x2 = x.detach().clone().requires_grad_()
+    y2 = m._fft_forward(x2)
+    y2.backward(g)
+    assert float((y - y2).abs().max()) <= 1e-5 * float(y2.abs().max())
+    assert float((x.grad - x2.grad).abs().max()) <= 1e-5 * float(x2.grad.abs().max())
+    assert not F_ee.hfs_supported(28, 4, 'tcgen05')
+    with pytest.raises(RuntimeError):
+        core.HighFreqSuppress(28, 28, 4, impl='tcgen05')(torch.rand((2, 1, 28, 28), device=DEV))
+    with pytest.raises(RuntimeError):
+        F_ee.hfs(torch.rand((2, 28, 28), device=DEV), 4, impl='tcgen05')

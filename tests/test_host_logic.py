@@ -31,7 +31,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), "libedge_b200.so does not export %s" % name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert L.ee_version() == 200
+    assert L.ee_version() == 201
     assert L.ee_aux_bytes(256, 3, 64, 64, 0) == 0
     assert L.ee_last_error() is not None
 
