@@ -932,7 +932,7 @@ static int launch_hfs(const ee::HfsArgs& a, cudaStream_t s) {
 
 // 64 px / r 8 on the tensor cores (ee_hfs_tc.cuh): persistent CTAs over pairs of planes, two per SM
 static int launch_hfs_tc64(const ee::HfsArgs& a, cudaStream_t s) {
-    auto kernel = ee::hfs_tc::hfs_tc64_kernel;
+    auto kernel = ee::hfs_tc::hfs_tc64_kernel<0>;
     if (int rc = ensure_smem(kernel, ee::hfs_tc::kSmem)) return rc;
     const int pairs = (a.planes + 1) / 2;
     int grid = 2 * sm_count();

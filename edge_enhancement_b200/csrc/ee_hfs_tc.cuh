@@ -174,7 +174,8 @@ __device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
 #endif
 
-static __global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a) {
+template <int kInstance>      // a template so that only the translation unit that launches it compiles it
+__global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a) {
     extern __shared__ __align__(128) unsigned char tc_smem[];
     const uint32_t sbase = smem_u32(tc_smem);
     const uint32_t bar = sbase;
