@@ -539,6 +539,24 @@ def run_extra_configs(torch, core, attacks, dev):
     except Exception as e:      # pragma: no cover
         out["configs[3]"] = {"error": repr(e)}
     torch.cuda.empty_cache()
+    # ---- the low-pass of the *_EE front end at the bench batch: exact FFMA kernel (default) and the tensor-core variant
+    try:
+        from edge_enhancement_b200 import functional as F_ee
+        x = torch.rand((4096, 3, 64, 64), device=dev)
+        y = torch.empty_like(x)
+        hf = {}
+        for impl in ("native", "tcgen05"):
+            ms = timed(lambda: F_ee.hfs(x, 8, out=y, impl=impl), 10)
+            hf[impl + "_us"] = ms * 1e3
+            hf[impl + "_gbs"] = 8.0 * x.numel() / ms / 1e6
+        exact = F_ee.hfs(x[:64], 8)
+        hf["tcgen05_max_abs_diff_from_native"] = float((F_ee.hfs(x[:64], 8, impl="tcgen05") - exact).abs().max())
+        hf["workload"] = "HighFreqSuppress(64, 64, 8) on 4096x3x64x64 fp32, 8 B/element algorithmic (ee_hfs_f32 / ee_hfs_tc_f32)"
+        out["highfreqsuppress"] = hf
+        del x, y
+    except Exception as e:      # pragma: no cover
+        out["highfreqsuppress"] = {"error": repr(e)}
+    torch.cuda.empty_cache()
     return out
 
 
