@@ -930,16 +930,38 @@ static int launch_hfs(const ee::HfsArgs& a, cudaStream_t s) {
     return EE_OK;
 }
 
-// 64 px / r 8 on the tensor cores (ee_hfs_tc.cuh): persistent CTAs over pairs of planes, two per SM
+// 64 px / r 8 on the tensor cores (ee_hfs_tc.cuh): persistent CTAs over pairs of planes, two per SM.  x is described to the
+// TMA engine as a [planes * 64][64] fp32 matrix, box 32 x 128 (one K block of a pair of planes), 128 B swizzle.
 static int launch_hfs_tc64(const ee::HfsArgs& a, cudaStream_t s) {
+    typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static std::atomic<encode_fn> cached{nullptr};
+    encode_fn fn = cached.load();
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) return fail(EE_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available");
+        fn = (encode_fn)p;
+        cached.store(fn);
+    }
+    CUtensorMap map;
+    const cuuint64_t dims[2] = {64u, (cuuint64_t)a.planes * 64u};
+    const cuuint64_t strides[1] = {64u * sizeof(float)};
+    const cuuint32_t box[2] = {32u, 128u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(EE_ERR_UNSUPPORTED, "ee_hfs_tc_f32: cuTensorMapEncodeTiled failed (%d)", (int)r);
     auto kernel = ee::hfs_tc::hfs_tc64_kernel<0>;
     if (int rc = ensure_smem(kernel, ee::hfs_tc::kSmem)) return rc;
     const int pairs = (a.planes + 1) / 2;
     int grid = 2 * sm_count();
     if (grid > pairs) grid = pairs;
-    kernel<<<(unsigned)grid, ee::hfs_tc::kThreads, ee::hfs_tc::kSmem, s>>>(a);
+    kernel<<<(unsigned)grid, ee::hfs_tc::kThreads, ee::hfs_tc::kSmem, s>>>(a, map);
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "ee_hfs_f32");
+    if (e != cudaSuccess) return cuda_fail(e, "ee_hfs_tc_f32");
     return EE_OK;
 }
 

@@ -61,16 +61,26 @@ constexpr uint32_t G_LBO = 128, G_SBO = 6 * 128, G_BYTES = 4 * G_SBO;           
 constexpr uint32_t V_LBO = 128, V_SBO = 4 * 128;                                   // 128 rows (plane, h) x 16 (j)
 constexpr uint32_t CB_LBO = 128, CB_SBO = 4 * 128, CB_BYTES = 8 * CB_SBO;          // 64 rows (w) x 16 (j)
 constexpr uint32_t Y_ROW = 272;                     // y staging rows: 68 floats, 4 mod 32 words
-static_assert(8 * TT_SBO <= X_BYTES && 16 * V_SBO <= X_BYTES && 128 * Y_ROW <= 2 * X_BYTES, "T~ / V~ alias the x operand");
+static_assert(128 * Y_ROW <= X_BYTES + 2048, "T~ / V~ alias the x operand");
 
 constexpr uint32_t OFF_W = 128;
 constexpr uint32_t OFF_CBT = OFF_W + NIt * NJt * 4;         // hi, then lo
 constexpr uint32_t OFF_RBT = OFF_CBT + 2 * CBT_BYTES;
 constexpr uint32_t OFF_RB = OFF_RBT + 2 * RBT_BYTES;
 constexpr uint32_t OFF_CB = OFF_RB + 2 * RB_BYTES;
-constexpr uint32_t OFF_G = OFF_CB + 2 * CB_BYTES;
-constexpr uint32_t OFF_X = OFF_G + 2 * G_BYTES;
-constexpr uint32_t kSmem = OFF_X + 2 * X_BYTES;             // 114304 B: two CTAs per SM
+// work area A (x_hi operand; then T~ hi | lo, G~ hi | lo, V~ hi | lo, the y staging rows -- each dead before the next is
+// written), 2 KB of spill for the 272 B-strided y rows, work area B (x_lo operand ONLY: free from the commit of product 1 to
+// the next pair, which is when the next pair's x is copied into it asynchronously)
+constexpr uint32_t OFF_XH = (OFF_CB + 2 * CB_BYTES + 1023u) & ~1023u;      // SWIZZLE_128B operands: 1024 B aligned
+constexpr uint32_t OFF_XL = OFF_XH + X_BYTES + 2048;
+constexpr uint32_t kSmem = OFF_XL + X_BYTES;                // 110592 B: two CTAs per SM
+static_assert(OFF_XH % 1024 == 0 && OFF_XL % 1024 == 0, "swizzle atoms");
+constexpr uint32_t XSW_KB = 128 * 128;                      // one K block (32 floats = 128 B per row) of the swizzled x operand
+constexpr uint32_t A_TT_LO = 4 * TT_SBO;                    // T~ lo behind the 32 valid rows of T~ hi
+constexpr uint32_t A_G_HI = 20480, A_G_LO = A_G_HI + G_BYTES;
+constexpr uint32_t A_V_LO = 16 * V_SBO;
+static_assert(A_TT_LO + 8 * TT_SBO <= X_BYTES, "the M = 64 read of T~ lo stays inside work area A");
+static_assert(A_G_LO + G_BYTES <= X_BYTES && A_G_HI >= 2 * A_TT_LO && A_G_HI >= 2 * A_V_LO, "G~ clear of the valid T~ / V~ rows");
 
 __device__ __forceinline__ uint32_t op_off(int row, int k, uint32_t lbo, uint32_t sbo) {
     return (uint32_t)(row >> 3) * sbo + (uint32_t)(k >> 2) * lbo + (uint32_t)(row & 7) * 16u + (uint32_t)(k & 3) * 4u;
@@ -79,6 +89,11 @@ __device__ __forceinline__ uint32_t op_off(int row, int k, uint32_t lbo, uint32_
 // offsets in 16 B units, descriptor version 1 (sm_100)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// K-major SWIZZLE_128B: rows of 128 B, 16 B chunks XOR-ed with (row % 8), 8-row groups 1024 B apart (what a TMA tensor copy
+// with CU_TENSOR_MAP_SWIZZLE_128B writes); leading offset unused (1), layout type 2
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // instruction descriptor: D = f32 (bit 4), A = B = tf32 (2 at bits 7 and 10), both K-major, N / 8 at bit 17, M / 16 at bit 24
 __host__ __device__ constexpr uint32_t idesc(int M, int Nn) {
@@ -109,6 +124,16 @@ __device__ __forceinline__ void mma_split(uint32_t d_tmem, uint64_t a_hi, uint64
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
         const uint64_t ao = (uint64_t)((ks * 2 * A_LBO) >> 4), bo = (uint64_t)((ks * 2 * B_LBO) >> 4);
+        if (ks == 0) mma_tf32<false>(d_tmem, a_hi + ao, b + bo, id_wide);
+        else mma_tf32<true>(d_tmem, a_hi + ao, b + bo, id_wide);
+        mma_tf32<true>(d_tmem, a_lo + ao, b + bo, id_narrow);
+    }
+}
+// product 1: A = x in the swizzled layout (two K blocks of 32), B = [CB_hi ; CB_lo] un-swizzled
+__device__ __forceinline__ void mma_split_x(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b, uint32_t id_wide, uint32_t id_narrow) {
+#pragma unroll
+    for (int ks = 0; ks < N / 8; ++ks) {
+        const uint64_t ao = (uint64_t)(((ks >> 2) * XSW_KB + (ks & 3) * 32) >> 4), bo = (uint64_t)((ks * 2 * CBT_LBO) >> 4);
         if (ks == 0) mma_tf32<false>(d_tmem, a_hi + ao, b + bo, id_wide);
         else mma_tf32<true>(d_tmem, a_hi + ao, b + bo, id_wide);
         mma_tf32<true>(d_tmem, a_lo + ao, b + bo, id_narrow);
@@ -175,11 +200,11 @@ __device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity) { mbar_wa
 #endif
 
 template <int kInstance>      // a template so that only the translation unit that launches it compiles it
-__global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a) {
-    extern __shared__ __align__(128) unsigned char tc_smem[];
+__global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a, const __grid_constant__ CUtensorMap xmap) {
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
     const uint32_t sbase = smem_u32(tc_smem);
-    const uint32_t bar = sbase;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tc_smem + 16);
+    const uint32_t bar = sbase, xbar = sbase + 8;             // commits of the products; arrival of the next pair's x
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tc_smem + 32);
     float* Wt = reinterpret_cast<float*>(tc_smem + OFF_W);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int quad = warp & 3;            // tensor-memory lanes 32 quad .. 32 quad + 31 (fixed by the warp's rank in its warpgroup)
@@ -193,6 +218,7 @@ __global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a) 
     }
     if (tid == 0) {
         mbar_init(bar, 1);
+        mbar_init(xbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     auto st_pair = [&](uint32_t off_hi, uint32_t off_lo, uint32_t o, float v) {
@@ -224,30 +250,38 @@ __global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a) 
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
 
-    unsigned char* pXh = tc_smem + OFF_X;
-    unsigned char* pXl = pXh + X_BYTES;
+    unsigned char* pA = tc_smem + OFF_XH;        // work area A
+    unsigned char* pXl = tc_smem + OFF_XL;       // work area B
     // loop-invariant descriptors of the four products (used by thread 0 only)
-    const uint64_t dXh = make_desc(sbase + OFF_X, X_LBO, X_SBO), dXl = make_desc(sbase + OFF_X + X_BYTES, X_LBO, X_SBO);
+    const uint32_t sA = sbase + OFF_XH;
+    const uint64_t dXh = make_desc_sw128(sA), dXl = make_desc_sw128(sbase + OFF_XL);
     const uint64_t dCBt = make_desc(sbase + OFF_CBT, CBT_LBO, CBT_SBO);
-    const uint64_t dTh = make_desc(sbase + OFF_X, TT_LBO, TT_SBO), dTl = make_desc(sbase + OFF_X + X_BYTES, TT_LBO, TT_SBO);
+    const uint64_t dTh = make_desc(sA, TT_LBO, TT_SBO), dTl = make_desc(sA + A_TT_LO, TT_LBO, TT_SBO);
     const uint64_t dRBt = make_desc(sbase + OFF_RBT, RBT_LBO, RBT_SBO);
     const uint64_t dRBh = make_desc(sbase + OFF_RB, RB_LBO, RB_SBO), dRBl = make_desc(sbase + OFF_RB + RB_BYTES, RB_LBO, RB_SBO);
-    const uint64_t dG = make_desc(sbase + OFF_G, G_LBO, G_SBO);
-    const uint64_t dVh = make_desc(sbase + OFF_X, V_LBO, V_SBO), dVl = make_desc(sbase + OFF_X + X_BYTES, V_LBO, V_SBO);
+    const uint64_t dGh = make_desc(sA + A_G_HI, G_LBO, G_SBO), dGl = make_desc(sA + A_G_LO, G_LBO, G_SBO);
+    const uint64_t dVh = make_desc(sA, V_LBO, V_SBO), dVl = make_desc(sA + A_V_LO, V_LBO, V_SBO);
     const uint64_t dCB = make_desc(sbase + OFF_CB, CB_LBO, CB_SBO);
     const int npairs = (a.planes + 1) >> 1;
 
-    // x of one pair: 128 rows x 16 chunks of 16 B.  Instruction q of warp w covers rows 8 (2 w + q / 4) .. + 7 (lane % 8) and the
-    // chunks 4 (q % 4) + lane / 8: 64 contiguous bytes per row in global memory, 128 contiguous bytes per quarter warp in shared
-    float4 xr[8];
-    auto load_pair = [&](int pair) {
+    // x of one pair (128 rows x 64 floats, contiguous in global memory) is brought in by the TMA engine: two tensor copies of
+    // 32 floats x 128 rows with the 128 B swizzle, i.e. straight into the K-major SWIZZLE_128B operand layout, into work area B
+    // (the lo operand), completion on `xbar`.  No load / store unit traffic, no registers; rows beyond the last plane are
+    // zero-filled by the copy.  The split then runs in place: the thread that reads a 16 B chunk writes hi to the same offset
+    // of work area A and lo back.  Chunk (row, c): offset (c / 8) * 16 KB + row * 128 + ((c % 8) ^ (row % 8)) * 16; a quarter
+    // warp takes one logical chunk of 8 consecutive rows = 8 distinct physical chunks (conflict free).
+    auto x_off = [&](int q) {
+        const int row = (warp * 2 + (q >> 2)) * 8 + (lane & 7), c = (q & 3) * 4 + (lane >> 3);
+        return (uint32_t)(c >> 3) * XSW_KB + (uint32_t)row * 128u + (uint32_t)(((c & 7) ^ (row & 7)) * 16);
+    };
+    auto copy_pair = [&](int pair) {                         // one thread
+        mbar_arrive_expect_tx(xbar, 2 * XSW_KB);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int row = (warp * 2 + (q >> 2)) * 8 + (lane & 7), c = (q & 3) * 4 + (lane >> 3);
-            const int plane = pair * 2 + (row >> 6);
-            xr[q] = (plane < a.planes) ? __ldcs(reinterpret_cast<const float4*>(a.x + (size_t)plane * N * N + (row & 63) * N + c * 4))
-                                       : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        }
+        for (int kb = 0; kb < 2; ++kb)
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                             sbase + OFF_XL + kb * XSW_KB),
+                         "l"(reinterpret_cast<uint64_t>(&xmap)), "r"(kb * 32), "r"(pair * 2 * N), "r"(xbar)
+                         : "memory");
     };
 
     int pair = blockIdx.x;
@@ -259,7 +293,8 @@ __global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a) 
 #else
 #define TC_MARK(k) do { } while (0)
 #endif
-    if (pair < npairs) load_pair(pair);
+    uint32_t xph = 0;
+    if (tid == 0 && pair < npairs) copy_pair(pair);
 #ifdef EE_TC_PROFILE
     const long long k0 = clock64();
     unsigned long long g0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
@@ -268,14 +303,16 @@ __global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a) 
 #ifdef EE_TC_PROFILE
         tlast = clock64(); ++iters;
 #endif
-        // ---- 0. x -> hi / lo operand ---------------------------------------------------------------------------------------
+        // ---- 0. x (landed in work area B) -> hi to work area A, lo in place ----------------------------------------------------
+        mbar_wait(xbar, xph); xph ^= 1u;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const uint32_t o = (uint32_t)(warp * 2 + (q >> 2)) * X_SBO + (uint32_t)((q & 3) * 4 + (lane >> 3)) * X_LBO + (uint32_t)(lane & 7) * 16u;
+            const uint32_t o = x_off(q);
+            const float4 v = *reinterpret_cast<const float4*>(pXl + o);
             float4 hi, lo;
-            split_tf32(xr[q].x, hi.x, lo.x); split_tf32(xr[q].y, hi.y, lo.y);
-            split_tf32(xr[q].z, hi.z, lo.z); split_tf32(xr[q].w, hi.w, lo.w);
-            *reinterpret_cast<float4*>(pXh + o) = hi;
+            split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
+            split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+            *reinterpret_cast<float4*>(pA + o) = hi;
             *reinterpret_cast<float4*>(pXl + o) = lo;
         }
         fence_async_smem();
@@ -284,15 +321,15 @@ __global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a) 
         // ---- 1. T = X CB ---------------------------------------------------------------------------------------------------
         if (tid == 0) {
             tc_fence_after();
-            mma_split<N / 8, X_LBO, CBT_LBO>(tmem + COL_T, dXh, dXl, dCBt, idesc(128, 2 * NJt), idesc(128, NJt));
+            mma_split_x(tmem + COL_T, dXh, dXl, dCBt, idesc(128, 2 * NJt), idesc(128, NJt));
             mma_commit(bar);
         }
-        {
-            const int next = pair + (int)gridDim.x;
-            if (next < npairs) load_pair(next);              // lands behind the rest of this iteration
-        }
+        const int next = pair + (int)gridDim.x;
         tc_wait(bar, ph); ph ^= 1u;
         tc_fence_after();
+        const bool more = next < npairs;
+        if (tid == 0 && more) copy_pair(next);               // product 1 is done with work area B: the next x lands behind the
+                                                             // rest of this iteration
         TC_MARK(1);
         // ---- 2. T -> T~ (transposed: rows (plane, j), K = h); this warp's half of the 16 columns ------------------------------
         {
@@ -306,8 +343,8 @@ __global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a) 
                 float hi, lo;
                 split_tf32(__uint_as_float(t[jj]) + __uint_as_float(t2[jj]), hi, lo);
                 const uint32_t o = op_off(p * NJt + 8 * half + jj, h, TT_LBO, TT_SBO);
-                *reinterpret_cast<float*>(pXh + o) = hi;
-                *reinterpret_cast<float*>(pXl + o) = lo;
+                *reinterpret_cast<float*>(pA + o) = hi;
+                *reinterpret_cast<float*>(pA + A_TT_LO + o) = lo;
             }
         }
         fence_async_smem();
@@ -353,8 +390,8 @@ __global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a) 
                     }
                     g[ii] = (i < NI && j < NJ) ? v : 0.0f;
                 }
-                unsigned char* pGh = tc_smem + OFF_G;
-                unsigned char* pGl = pGh + G_BYTES;
+                unsigned char* pGh = pA + A_G_HI;
+                unsigned char* pGl = pA + A_G_LO;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     float4 hi, lo;
@@ -373,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a) 
         // ---- 5. V = RB G -----------------------------------------------------------------------------------------------------
         if (tid == 0) {
             tc_fence_after();
-            mma_three<NIt / 8, RB_LBO, G_LBO>(tmem + COL_V, dRBh, dRBl, dG, dG + (uint64_t)(G_BYTES >> 4), idesc(64, 2 * NJt));
+            mma_three<NIt / 8, RB_LBO, G_LBO>(tmem + COL_V, dRBh, dRBl, dGh, dGl, idesc(64, 2 * NJt));
             mma_commit(bar);
         }
         tc_wait(bar, ph); ph ^= 1u;
@@ -392,8 +429,8 @@ __global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a) 
                 split_tf32(__uint_as_float(v[4 * c + 0]), hi.x, lo.x); split_tf32(__uint_as_float(v[4 * c + 1]), hi.y, lo.y);
                 split_tf32(__uint_as_float(v[4 * c + 2]), hi.z, lo.z); split_tf32(__uint_as_float(v[4 * c + 3]), hi.w, lo.w);
                 const uint32_t o = op_off(half * N + h, 4 * (c0 + c), V_LBO, V_SBO);
-                *reinterpret_cast<float4*>(pXh + o) = hi;
-                *reinterpret_cast<float4*>(pXl + o) = lo;
+                *reinterpret_cast<float4*>(pA + o) = hi;
+                *reinterpret_cast<float4*>(pA + A_V_LO + o) = lo;
             }
         }
         fence_async_smem();
@@ -413,7 +450,7 @@ __global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a) 
         //         memory (row per lane, conflict-free 128-bit stores) -> read back 4 rows x 128 B per instruction -> (+ add) ->
         //         coalesced 128-bit global stores ------------------------------------------------------------------------------
         {
-            unsigned char* pw = pXh + (size_t)(quad * 32) * Y_ROW + 128 * half;      // this warp's 32 rows
+            unsigned char* pw = pA + (size_t)(quad * 32) * Y_ROW + 128 * half;      // this warp's 32 rows
             unsigned char* prow = pw + (size_t)lane * Y_ROW;
 #pragma unroll
             for (int blk = 0; blk < 2; ++blk) {
