@@ -954,12 +954,17 @@ static int launch_hfs_tc64(const ee::HfsArgs& a, cudaStream_t s) {
     CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(EE_ERR_UNSUPPORTED, "ee_hfs_tc_f32: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    CUtensorMap ymap;                               // y with a box of 32 x 32: one store per warp
+    const cuuint32_t ybox[2] = {32u, 32u};
+    r = fn(&ymap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.y, dims, strides, ybox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(EE_ERR_UNSUPPORTED, "ee_hfs_tc_f32: cuTensorMapEncodeTiled failed (%d)", (int)r);
     auto kernel = ee::hfs_tc::hfs_tc64_kernel<0>;
     if (int rc = ensure_smem(kernel, ee::hfs_tc::kSmem)) return rc;
     const int pairs = (a.planes + 1) / 2;
     int grid = 2 * sm_count();
     if (grid > pairs) grid = pairs;
-    kernel<<<(unsigned)grid, ee::hfs_tc::kThreads, ee::hfs_tc::kSmem, s>>>(a, map);
+    kernel<<<(unsigned)grid, ee::hfs_tc::kThreads, ee::hfs_tc::kSmem, s>>>(a, map, ymap);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "ee_hfs_tc_f32");
     return EE_OK;

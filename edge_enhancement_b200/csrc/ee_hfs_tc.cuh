@@ -200,7 +200,7 @@ __device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity) { mbar_wa
 #endif
 
 template <int kInstance>      // a template so that only the translation unit that launches it compiles it
-__global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a, const __grid_constant__ CUtensorMap xmap) {
+__global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a, const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     const uint32_t sbase = smem_u32(tc_smem);
     const uint32_t bar = sbase, xbar = sbase + 8;             // commits of the products; arrival of the next pair's x
@@ -446,9 +446,33 @@ __global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a, 
         tc_wait(bar, ph); ph ^= 1u;
         tc_fence_after();
         TC_MARK(7);
-        // ---- 8. this warp's half (32 columns) of the output rows of its quadrant: tensor memory -> 272 B-strided rows in shared
-        //         memory (row per lane, conflict-free 128-bit stores) -> read back 4 rows x 128 B per instruction -> (+ add) ->
-        //         coalesced 128-bit global stores ------------------------------------------------------------------------------
+        // ---- 8. this warp's half (32 columns) of the output rows of its quadrant.  Without `add`: tensor memory -> the
+        //         128 B-swizzled layout in work area A (row per lane: 8 consecutive rows hit 8 distinct chunks) -> ONE TMA
+        //         tensor store of 32 x 32 floats per warp (no load / store unit traffic to global memory).  With `add`:
+        //         272 B-strided rows -> read back 4 rows x 128 B per instruction -> + add -> coalesced 128-bit stores.
+        if (a.add == nullptr) {
+            const int row = quad * 32 + lane;
+            unsigned char* prow = pA + half * XSW_KB + (size_t)row * 128;
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk) {
+                uint32_t yv[16];
+                tmem_ld16(lane_base + COL_Y + 32 * half + blk * 16, yv);
+                tmem_wait_ld();
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    *reinterpret_cast<float4*>(prow + (((blk * 4 + c) ^ (row & 7)) * 16)) =
+                        make_float4(__uint_as_float(yv[4 * c]), __uint_as_float(yv[4 * c + 1]), __uint_as_float(yv[4 * c + 2]), __uint_as_float(yv[4 * c + 3]));
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<uint64_t>(&ymap)),
+                             "r"(32 * half), "r"(pair * 2 * N + quad * 32), "r"(sA + half * XSW_KB + quad * 32 * 128)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");        // work area A is free again after the barrier below
+            }
+        } else
         {
             unsigned char* pw = pA + (size_t)(quad * 32) * Y_ROW + 128 * half;      // this warp's 32 rows
             unsigned char* prow = pw + (size_t)lane * Y_ROW;
@@ -489,6 +513,7 @@ __global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a, 
                iters, prof[0] / iters, prof[1] / iters, prof[2] / iters, prof[3] / iters, prof[4] / iters, prof[5] / iters, prof[6] / iters,
                prof[7] / iters, prof[8] / iters);
 #endif
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
