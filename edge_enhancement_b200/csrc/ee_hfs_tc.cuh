@@ -446,11 +446,12 @@ __global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a, 
         tc_wait(bar, ph); ph ^= 1u;
         tc_fence_after();
         TC_MARK(7);
-        // ---- 8. this warp's half (32 columns) of the output rows of its quadrant.  Without `add`: tensor memory -> the
+        // ---- 8. this warp's half (32 columns) of the output rows of its quadrant.  Without `add` (or with `add` == y): tensor memory -> the
         //         128 B-swizzled layout in work area A (row per lane: 8 consecutive rows hit 8 distinct chunks) -> ONE TMA
         //         tensor store of 32 x 32 floats per warp (no load / store unit traffic to global memory).  With `add`:
         //         272 B-strided rows -> read back 4 rows x 128 B per instruction -> + add -> coalesced 128-bit stores.
-        if (a.add == nullptr) {
+        if (a.add == nullptr || a.add == a.y) {              // `add` aliasing y (the in-place accumulation of the front end's
+                                                             // backward): the same store as a TMA reduction, y += staged
             const int row = quad * 32 + lane;
             unsigned char* prow = pA + half * XSW_KB + (size_t)row * 128;
 #pragma unroll
@@ -466,9 +467,15 @@ __global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a, 
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
-                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<uint64_t>(&ymap)),
-                             "r"(32 * half), "r"(pair * 2 * N + quad * 32), "r"(sA + half * XSW_KB + quad * 32 * 128)
-                             : "memory");
+                if (a.add == nullptr)
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(reinterpret_cast<uint64_t>(&ymap)),
+                                 "r"(32 * half), "r"(pair * 2 * N + quad * 32), "r"(sA + half * XSW_KB + quad * 32 * 128)
+                                 : "memory");
+                else
+                    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                                     reinterpret_cast<uint64_t>(&ymap)),
+                                 "r"(32 * half), "r"(pair * 2 * N + quad * 32), "r"(sA + half * XSW_KB + quad * 32 * 128)
+                                 : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");        // work area A is free again after the barrier below
             }

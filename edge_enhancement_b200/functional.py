@@ -622,9 +622,9 @@ class EdgeEnhanceFrontFn(torch.autograd.Function):
                   into the low-pass kernel's store, so autograd never runs a separate accumulation pass)"""
 
     @staticmethod
-    def forward(ctx, x, r, params, w):
-        base = hfs(x, r)
-        ctx.r, ctx.params, ctx.w = r, params, w
+    def forward(ctx, x, r, params, w, hfs_impl='native'):
+        base = hfs(x, r, impl=hfs_impl)
+        ctx.r, ctx.params, ctx.w, ctx.hfs_impl = r, params, w, hfs_impl
         ctx.save_for_backward(x, base)
         return edge_blend(x, base, params, w)
 
@@ -632,7 +632,7 @@ class EdgeEnhanceFrontFn(torch.autograd.Function):
     def backward(ctx, g):
         x, base = ctx.saved_tensors
         g_x, g_base = edge_blend_backward(g, x, base, ctx.params, ctx.w)
-        return hfs(g_base, ctx.r, out=g_x, add=g_x), None, None, None
+        return hfs(g_base, ctx.r, out=g_x, add=g_x, impl=ctx.hfs_impl), None, None, None, None
 
 
 class AddSquareFn(torch.autograd.Function):

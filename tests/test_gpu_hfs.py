@@ -171,3 +171,30 @@ def test_tensor_core_module_autograd_and_unsupported_shapes():
         core.HighFreqSuppress(28, 28, 4, impl='tcgen05')(torch.rand((2, 1, 28, 28), device=DEV))
     with pytest.raises(RuntimeError):
         F_ee.hfs(torch.rand((2, 28, 28), device=DEV), 4, impl='tcgen05')
+
+
+def test_front_end_with_the_tensor_core_low_pass_and_in_place_accumulation():
+    """EdgeEnhance(hfs_impl='tcgen05'): same masks, blended image and gradient within the tolerances of north_star (1e-5); the
+    backward accumulates H(g_base) into g_x through the TMA reduction store (add aliasing y)."""
+    import contextlib, io
+    gen = torch.Generator(device=DEV).manual_seed(21)
+    x = torch.rand((37, 3, 64, 64), device=DEV, generator=gen)
+    g = torch.randn((37, 3, 64, 64), device=DEV, generator=gen)
+    outs = []
+    for impl in ('native', 'tcgen05'):
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = core.EdgeEnhance(cize=64, r=8, w=1.0, low=38.0, high=76.0, type_canny='CannyFilter_step125_1', hfs_impl=impl).to(DEV)
+        xi = x.clone().requires_grad_()
+        y = m(xi)
+        y.backward(g)
+        outs.append((y.detach(), xi.grad.detach()))
+    (y0, g0), (y1, g1) = outs
+    assert float((y0 - y1).abs().max()) <= 1e-5
+    assert float((g0 - g1).abs().max()) <= 1e-5 * float(g0.abs().max())
+    # the in-place accumulation alone, odd plane count: y = H x + y
+    acc = torch.randn((5, 64, 64), device=DEV, generator=gen)
+    xs = torch.rand((5, 64, 64), device=DEV, generator=gen)
+    want = F_ee.hfs(xs, 8) + acc
+    got = acc.clone()
+    F_ee.hfs(xs, 8, out=got, add=got, impl='tcgen05')
+    assert float((got - want).abs().max()) <= TC_TOL * float(want.abs().max())
