@@ -10,12 +10,13 @@
 // tensor core is not specified): measured 1.3e-6 max abs error against float64 on [0,1] inputs (FFMA kernel: 0.6e-6);
 // tests/test_gpu_hfs.py bounds it.  Entry point: ee_hfs_tc_f32 (opt-in; ee_hfs_f32 keeps the bit-exact FFMA kernel).
 //
-// One CTA of 256 threads works on a PAIR of planes at a time, persistent over pairs, two CTAs per SM (111.6 KB of shared
+// One CTA of 256 threads works on a PAIR of planes at a time, persistent over pairs, two CTAs per SM (108 KB of shared
 // memory, 256 of the 512 tensor-memory columns each).  Warps w and w + 4 share tensor-memory lanes 32 (w % 4) .. + 31 and
 // take half of the columns each.
 //
-//   0. x of the pair (prefetched into registers one iteration ahead, LDG.128) is split into hi / lo and stored as the A
-//      operand of product 1: rows m = (plane, h), K = w.
+//   0. x of the pair arrives by TMA: two tensor copies (32 floats x 128 rows, 128 B swizzle) write it straight into the
+//      K-major SWIZZLE_128B operand layout of the lo operand's buffer, issued one iteration ahead (as soon as product 1 of
+//      the previous pair has been committed); the split runs in place: hi to work area A, lo back to the same offset.
 //   1. T[128 x 16] = X CB                       M = 128, N = 32 | 16, K = 64    (B = [CB_hi ; CB_lo] stacked along N: the
 //                                               reader adds column 16 + j to column j; 2 MMAs per K step instead of 3)
 //   2. each thread reads its row of T from tensor memory and stores it TRANSPOSED: rows m = (plane, j), K = h.
@@ -24,15 +25,19 @@
 //   5. V[64 x (plane, j)] = RB G                M = 64, N = 32, K = 24           (3 MMAs per K step)
 //   6. V -> rows m = (plane, h), K = j (16-lane tensor-memory loads: the M = 64 accumulator uses lanes 0..15 of a quadrant).
 //   7. y[128 x 64] = V CB^T                     M = 128, N = 64, K = 16          (3 MMAs per K step)
-//   8. output rows: tensor memory -> 272 B-strided rows in shared memory -> (+ add) -> coalesced 128-bit stores.
+//   8. output: tensor memory -> the 128 B-swizzled layout in work area A -> one TMA tensor store of 32 x 32 floats per warp
+//      (a TMA REDUCTION store, y += tile, when `add` aliases y: the in-place accumulation of the front end's backward);
+//      with a separate `add` buffer: 272 B-strided rows -> + add -> coalesced 128-bit stores.
 //
 // The constant operands (CB, RB in both orientations, hi and lo: 40 KB) are built once per CTA from the caller's tables.
-// T~, V~ and the output staging alias the x operand (dead once product 1 has been committed).  Each product is issued by
+// T~, G~, V~ and the output staging share work area A (each dead before the next is written).  Each product is issued by
 // thread 0 (descriptors precomputed, a K step adds a constant to the address field) and committed to one mbarrier that all
 // threads wait on; generic-proxy writes are fenced (fence.proxy.async) before the barrier that precedes the issue.
 //
-// Measured (profiles/README.md, r2z): 152 us at 4096x3x64x64 against 153 us for the FFMA kernel -- 2.55x fewer warp
-// instructions (32.0 M vs 81.7 M) but four dependent MMA round trips per pair with only two pairs in flight per SM.
+// Measured (profiles/README.md, r2z): 107 us at 4096x3x64x64 against 153 us for the FFMA kernel (3.0x fewer warp
+// instructions).  Global memory is touched by the TMA engine only: with LDG / STG for x and y the same kernel took 151 us --
+// the bursts of global requests sat in front of the shared- and tensor-memory traffic of the other stages in the load /
+// store unit (ablation in profiles/README.md).
 #pragma once
 #include "ee_edge_stream.cuh"      // smem_u32, mbarrier helpers
 #include "ee_hfs.cuh"

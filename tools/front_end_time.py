@@ -19,6 +19,10 @@ g = torch.randn_like(x)
 with contextlib.redirect_stdout(io.StringIO()):
     ours = core.EdgeEnhance(cize=S, r=r, w=1.0, low=38.0, high=76.0, alpha=0.0, sigma=1, type_canny='CannyFilter_step125_1')
 fronts = {"ours (fused node)": ours, "eager_clean (no dead host allocations)": EagerFront(S, r, 1.0, 76 / 255, dev, faithful=False)}
+if S == 64:       # the same node on the tensor-core low-pass (ee_hfs_tc_f32)
+    with contextlib.redirect_stdout(io.StringIO()):
+        fronts["ours (fused node, hfs_impl='tcgen05')"] = core.EdgeEnhance(cize=S, r=r, w=1.0, low=38.0, high=76.0, alpha=0.0, sigma=1,
+                                                                            type_canny='CannyFilter_step125_1', hfs_impl='tcgen05')
 if B * C * S * S <= 64 * 3 * 224 * 224 * 8:
     fronts["eager (reference-style, incl. per-call host scratch + H2D)"] = EagerFront(S, r, 1.0, 76 / 255, dev, faithful=True)
 res = {}
