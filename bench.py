@@ -552,8 +552,20 @@ def run_extra_configs(torch, core, attacks, dev):
         exact = F_ee.hfs(x[:64], 8)
         hf["tcgen05_max_abs_diff_from_native"] = float((F_ee.hfs(x[:64], 8, impl="tcgen05") - exact).abs().max())
         hf["workload"] = "HighFreqSuppress(64, 64, 8) on 4096x3x64x64 fp32, 8 B/element algorithmic (ee_hfs_f32 / ee_hfs_tc_f32)"
+        # the whole *_EE front end (low-pass + edge filter + blend) as one autograd node, forward + backward, on either low-pass
+        g = torch.randn_like(x)
+        for impl in ("native", "tcgen05"):
+            with contextlib.redirect_stdout(io.StringIO()):
+                fe = core.EdgeEnhance(cize=64, r=8, w=1.0, low=38.0, high=76.0, type_canny="CannyFilter_step125_1", hfs_impl=impl).to(dev)
+            xr = x.clone().requires_grad_()
+
+            def fwd_bwd():
+                fe(xr).backward(g)
+                xr.grad = None
+            hf["front_end_fwd_bwd_us_" + impl] = timed(fwd_bwd, 5) * 1e3
+            del xr
         out["highfreqsuppress"] = hf
-        del x, y
+        del x, y, g
     except Exception as e:      # pragma: no cover
         out["highfreqsuppress"] = {"error": repr(e)}
     torch.cuda.empty_cache()
