@@ -311,7 +311,7 @@ class HighFreqSuppress(torch.nn.Module):
     silent fallback.  impl='torch_fft' is the explicit opt-in to the torch.fft restatement (library code, any shape, any
     device); it is what the native kernel is pinned to (tests).  impl='tcgen05' runs the same five products on the tensor
     cores (ee_hfs_tc_f32: tcgen05.mma kind::tf32 with a 3 x TF32 split, accumulators in tensor memory, x / y moved by TMA tensor copies; 64 / 8 only):
-    1.4x faster than the FFMA kernel (107 vs 153 us at 4096x3x64x64), 1.3e-6 from float64 instead of 0.6e-6 and not
+    1.5x faster than the FFMA kernel (103 vs 153 us at 4096x3x64x64), 1.3e-6 from float64 instead of 0.6e-6 and not
     bit-identical to the oracle, hence opt-in."""
 
     def __init__(self, w, h, r, c2r='onesided', impl='native'):

@@ -34,7 +34,7 @@
 // thread 0 (descriptors precomputed, a K step adds a constant to the address field) and committed to one mbarrier that all
 // threads wait on; generic-proxy writes are fenced (fence.proxy.async) before the barrier that precedes the issue.
 //
-// Measured (profiles/README.md, r2z): 107 us at 4096x3x64x64 against 153 us for the FFMA kernel (3.0x fewer warp
+// Measured (profiles/README.md, r2z): 103 us at 4096x3x64x64 against 153 us for the FFMA kernel (3.0x fewer warp
 // instructions).  Global memory is touched by the TMA engine only: with LDG / STG for x and y the same kernel took 151 us --
 // the bursts of global requests sat in front of the shared- and tensor-memory traffic of the other stages in the load /
 // store unit (ablation in profiles/README.md).
@@ -275,9 +275,12 @@ __global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a, 
     // zero-filled by the copy.  The split then runs in place: the thread that reads a 16 B chunk writes hi to the same offset
     // of work area A and lo back.  Chunk (row, c): offset (c / 8) * 16 KB + row * 128 + ((c % 8) ^ (row % 8)) * 16; a quarter
     // warp takes one logical chunk of 8 consecutive rows = 8 distinct physical chunks (conflict free).
+    // Warp (quad, half) splits K block `half` of rows 32 quad .. 32 quad + 31 -- exactly the 4 KB of work area A that it
+    // stages its part of y in at the end of the iteration, so the only hazard between one pair's output and the next pair's
+    // split is inside the warp (no CTA barrier between iterations).
     auto x_off = [&](int q) {
-        const int row = (warp * 2 + (q >> 2)) * 8 + (lane & 7), c = (q & 3) * 4 + (lane >> 3);
-        return (uint32_t)(c >> 3) * XSW_KB + (uint32_t)row * 128u + (uint32_t)(((c & 7) ^ (row & 7)) * 16);
+        const int row = quad * 32 + (q >> 1) * 8 + (lane & 7), c = (q & 1) * 4 + (lane >> 3);
+        return (uint32_t)half * XSW_KB + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) * 16);
     };
     auto copy_pair = [&](int pair) {                         // one thread
         mbar_arrive_expect_tx(xbar, 2 * XSW_KB);
@@ -482,8 +485,9 @@ __global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a, 
                                  "r"(32 * half), "r"(pair * 2 * N + quad * 32), "r"(sA + half * XSW_KB + quad * 32 * 128)
                                  : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");        // work area A is free again after the barrier below
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");        // this warp's 4 KB of work area A are free again
             }
+            __syncwarp();
         } else
         {
             unsigned char* pw = pA + (size_t)(quad * 32) * Y_ROW + 128 * half;      // this warp's 32 rows
@@ -512,8 +516,8 @@ __global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a, 
             }
         }
         TC_MARK(8);
-        tc_fence_before();
-        __syncthreads();          // every warp has drained y before the next pair's products reuse the columns
+        tc_fence_before();        // (every warp has drained y before the barrier that precedes the next pair's first product)
+        if (a.add != nullptr && a.add != a.y) __syncthreads();      // the strided staging rows are shared between warps
     }
 
 #ifdef EE_TC_PROFILE

@@ -231,8 +231,8 @@ int ee_hfs_supported(int N, int r);
 /* The same operator with the four dense products on the tensor cores (tcgen05.mma kind::tf32, 3 x TF32 split, accumulators in
  * tensor memory; csrc/ee_hfs_tc.cuh).  Same arguments and tables as ee_hfs_f32; 64 x 64 planes with radius 8 only
  * (ee_hfs_tc_supported), EE_ERR_UNSUPPORTED otherwise.  NOT bit-identical to ee_hfs_f32 / the oracle: the accumulation order
- * inside the tensor core is unspecified; max abs error 1.3e-6 against float64 on [0,1] inputs (ee_hfs_f32: 0.6e-6).  1.4x
- * faster than ee_hfs_f32 (107 vs 153 us at 4096x3x64x64), which stays the default because it is exact.
+ * inside the tensor core is unspecified; max abs error 1.3e-6 against float64 on [0,1] inputs (ee_hfs_f32: 0.6e-6).  1.5x
+ * faster than ee_hfs_f32 (103 vs 153 us at 4096x3x64x64), which stays the default because it is exact.
  * x and y go through TMA tensor copies (the call encodes two tensor maps on the host); add_or_null == y is the fast
  * accumulate path (TMA reduction store). */
 int ee_hfs_tc_f32(const float* x, float* y, const float* add_or_null, int planes, int N, int r, const float* cb,
