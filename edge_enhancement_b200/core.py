@@ -162,6 +162,15 @@ class _EdgeFilterBase(nn.Module):
         return F_ee.EdgeMapFn.apply(img, self.params(low_threshold, high_threshold, hysteresis))
 
 
+def set_hfs_impl(impl='native'):
+    """Default low-pass kernel of every HighFreqSuppress / EdgeEnhance built afterwards without an explicit impl (i.e. by the
+    reference's own model files): 'native' (FFMA, bit-identical to the oracle) or 'tcgen05' (tensor cores, 1.5x faster at
+    64 px / r 8, 1.5e-6 from the FFMA kernel; shapes it does not cover keep the FFMA kernel)."""
+    if impl not in ('native', 'tcgen05'):
+        raise ValueError("set_hfs_impl: 'native' or 'tcgen05'")
+    HighFreqSuppress.default_impl = impl
+
+
 def set_nan_compat(enabled=True):
     """Default of `nan_compat` for every filter module that does not set its own (see _EdgeFilterBase.nan_compat)."""
     _EdgeFilterBase.nan_compat = bool(enabled)
@@ -256,8 +265,8 @@ class EdgeEnhance(nn.Module):
     ImageNet/models_imagenet/resnet_EE.py:167-179, AWP/.../preactresnet_EE*.py:145-159)."""
 
     def __init__(self, cize=224, r=16, w=0.5, low=60.0, high=120.0, alpha=0.0, sigma=1,
-                 type_canny='CannyFilter', hfs=True, with_gf=False, hfs_impl='native'):
-        """hfs_impl: 'native' (default: the FFMA low-pass kernel, bit-identical to the oracle), 'tcgen05' (64 px / r 8 only: the
+                 type_canny='CannyFilter', hfs=True, with_gf=False, hfs_impl=None):
+        """hfs_impl: None (the package default, see set_hfs_impl), 'native' (the FFMA low-pass kernel, bit-identical to the oracle), 'tcgen05' (64 px / r 8 only: the
         tensor-core low-pass, 1.4x faster, base within 1.5e-6 -- inside the 1e-5 tolerance of the blended image; the threshold
         masks do not depend on it) or 'torch_fft'."""
         super(EdgeEnhance, self).__init__()
@@ -314,8 +323,14 @@ class HighFreqSuppress(torch.nn.Module):
     1.5x faster than the FFMA kernel (103 vs 153 us at 4096x3x64x64), 1.3e-6 from float64 instead of 0.6e-6 and not
     bit-identical to the oracle, hence opt-in."""
 
-    def __init__(self, w, h, r, c2r='onesided', impl='native'):
+    default_impl = 'native'        # set_hfs_impl(): what modules built WITHOUT an explicit impl use (the reference's model files)
+
+    def __init__(self, w, h, r, c2r='onesided', impl=None):
         super(HighFreqSuppress, self).__init__()
+        if impl is None:           # 'tcgen05' as a default applies where that kernel exists; other shapes keep the FFMA kernel
+            impl = HighFreqSuppress.default_impl
+            if impl == 'tcgen05' and not (w == h == 64 and r == 8 and c2r == 'onesided'):
+                impl = 'native'
         if c2r not in ('onesided', 'full') or impl not in ('native', 'tcgen05', 'torch_fft'):
             raise ValueError("HighFreqSuppress: c2r must be 'onesided' or 'full', impl 'native', 'tcgen05' or 'torch_fft'")
         if c2r == 'full' and impl != 'torch_fft':

@@ -313,3 +313,25 @@ def test_reference_scripts_run_their_main_up_to_the_first_kernel(script, tmp_pat
         assert "validate(): 6-argument calls" in r.stdout
     if script == "tiny":
         assert "duplicate keys" in r.stdout and "step_size_1" in r.stdout
+
+
+def test_low_pass_implementation_switch_applies_where_the_kernel_exists():
+    """core.set_hfs_impl('tcgen05') is the package-wide default for modules built without an explicit impl (the reference's own
+    model files); shapes the tensor-core kernel does not cover keep the FFMA kernel; an explicit impl always wins."""
+    import contextlib, io
+    from edge_enhancement_b200 import core
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            assert core.HighFreqSuppress(64, 64, 8).impl == 'native'
+            core.set_hfs_impl('tcgen05')
+            assert core.HighFreqSuppress(64, 64, 8).impl == 'tcgen05'
+            assert core.HighFreqSuppress(224, 224, 16).impl == 'native'
+            assert core.HighFreqSuppress(28, 28, 4).impl == 'native'
+            assert core.HighFreqSuppress(64, 64, 8, impl='native').impl == 'native'
+            assert core.HighFreqSuppress(64, 64, 8, impl='torch_fft').impl == 'torch_fft'
+            assert core.EdgeEnhance(cize=64, r=8, type_canny='CannyFilter_step125_1').hfs.impl == 'tcgen05'
+            assert core.EdgeEnhance(cize=64, r=8, type_canny='CannyFilter_step125_1', hfs_impl='native').hfs.impl == 'native'
+        with pytest.raises(ValueError):
+            core.set_hfs_impl('torch_fft')
+    finally:
+        core.set_hfs_impl('native')
