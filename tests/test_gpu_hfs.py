@@ -198,3 +198,23 @@ def test_front_end_with_the_tensor_core_low_pass_and_in_place_accumulation():
     got = acc.clone()
     F_ee.hfs(xs, 8, out=got, add=got, impl='tcgen05')
     assert float((got - want).abs().max()) <= TC_TOL * float(want.abs().max())
+
+
+def test_tensor_core_kernel_is_cuda_graph_capturable():
+    """The tensor maps are encoded on the host and passed by value: the call can be captured and replayed on new contents."""
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    x = torch.rand((48, 64, 64), device=DEV, generator=gen)
+    y = torch.empty_like(x)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        F_ee.hfs(x, 8, out=y, impl='tcgen05')             # warm-up outside the capture (attribute set-up)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        F_ee.hfs(x, 8, out=y, impl='tcgen05')
+    x.copy_(torch.rand((48, 64, 64), device=DEV, generator=gen))
+    graph.replay()
+    torch.cuda.synchronize()
+    ref = F_ee.hfs(x, 8)
+    assert float((y - ref).abs().max()) <= TC_TOL * float(ref.abs().max())
