@@ -191,6 +191,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--batch", type=int, default=256, help="images per GPU")
     ap.add_argument("--side", type=int, default=64)
+    ap.add_argument("--hfs-impl", default="native", choices=["native", "tcgen05"],
+                    help="low-pass kernel of the `ours` front end (core.set_hfs_impl): FFMA (exact) or tensor cores (64 px only)")
     ap.add_argument("--pgd-steps", type=int, default=10)
     ap.add_argument("--config", default="tiny_pgd", choices=["tiny_pgd", "imagenet_free"],
                     help="tiny_pgd: BASELINE configs[1] (default); imagenet_free: configs[3], ResNet-50, 3x224x224, 32 images per GPU, "
@@ -207,6 +209,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from edge_enhancement_b200 import attacks, core
+    core.set_hfs_impl(args.hfs_impl)
 
     class A:
         random = True
@@ -290,8 +293,9 @@ def main():
                                          "edge-enhanced PGD-%d adversarial training images/sec" % args.pgd_steps), "front_end": front_name,
                               "value": ips, "unit": "images/s", "n_gpus": world, "ms_per_iteration": float(ms.item()) / args.iters,
                               "config": "%s (stock torch ops, fp32, cudnn TF32 default), 3x%dx%d, batch %d per GPU, "
-                                        "CannyFilter_step125_1 + torch.fft low-pass, %s, SGD; DDP/NCCL for N > 1"
+                                        "CannyFilter_step125_1 + %s low-pass, %s, SGD; DDP/NCCL for N > 1"
                                         % ("ResNet-50 + SyncBN" if free else "PreAct-ResNet18", args.side, args.side, args.batch,
+                                           ("native (%s)" % args.hfs_impl) if front_name == "ours" else "torch.fft",
                                            "clip_eps = fgsm_step = 4/255, 4 replays per batch" if free else "eps 16/255, step 2/255"),
                               "final_loss": float(loss.item()), "data": "synthetic"}), flush=True)
         del net, model, opt
