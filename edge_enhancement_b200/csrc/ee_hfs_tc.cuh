@@ -221,10 +221,21 @@ __global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a, 
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    auto copy_pair = [&](int pair) {                         // one thread
+        mbar_arrive_expect_tx(xbar, 2 * XSW_KB);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                             sbase + OFF_XL + kb * XSW_KB),
+                         "l"(reinterpret_cast<uint64_t>(&xmap)), "r"(kb * 32), "r"(pair * 2 * N), "r"(xbar)
+                         : "memory");
+    };
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_init(xbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_async_smem();
+        if ((int)blockIdx.x < ((a.planes + 1) >> 1)) copy_pair((int)blockIdx.x);      // the first pair's x lands behind the prologue
     }
     auto st_pair = [&](uint32_t off_hi, uint32_t off_lo, uint32_t o, float v) {
         float hi, lo;
@@ -282,15 +293,6 @@ __global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a, 
         const int row = quad * 32 + (q >> 1) * 8 + (lane & 7), c = (q & 1) * 4 + (lane >> 3);
         return (uint32_t)half * XSW_KB + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) * 16);
     };
-    auto copy_pair = [&](int pair) {                         // one thread
-        mbar_arrive_expect_tx(xbar, 2 * XSW_KB);
-#pragma unroll
-        for (int kb = 0; kb < 2; ++kb)
-            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-                             sbase + OFF_XL + kb * XSW_KB),
-                         "l"(reinterpret_cast<uint64_t>(&xmap)), "r"(kb * 32), "r"(pair * 2 * N), "r"(xbar)
-                         : "memory");
-    };
 
     int pair = blockIdx.x;
     uint32_t ph = 0;
@@ -302,7 +304,6 @@ __global__ void __launch_bounds__(kThreads, 2) hfs_tc64_kernel(const HfsArgs a, 
 #define TC_MARK(k) do { } while (0)
 #endif
     uint32_t xph = 0;
-    if (tid == 0 && pair < npairs) copy_pair(pair);
 #ifdef EE_TC_PROFILE
     const long long k0 = clock64();
     unsigned long long g0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
